@@ -1,0 +1,301 @@
+"""Configuration system: a self-contained yacs-compatible ``CfgNode`` plus the
+Distribuuuu schema.
+
+Parity target: reference ``distribuuuu/config.py:7-100`` (schema 10-63, yaml merge
+69-72, dump 75-79, reset 82-84, CLI 87-100).  yacs and iopath are not available in
+this image, so the node type is implemented here from scratch: attribute access,
+type-checked merges, freeze/defrost, clone, yaml dump/load and ``KEY VALUE`` list
+overrides with Python-literal parsing.
+
+Additive keys (all defaults preserve reference behaviour) live under ``B200`` and
+are ignored by reference yamls, which load unchanged.
+"""
+from __future__ import annotations
+
+import argparse
+import ast
+import copy
+import io
+import os
+from typing import Any, Iterable
+
+import yaml
+
+_VALID_TYPES = (tuple, list, str, int, float, bool, type(None))
+
+
+class CfgNode(dict):
+    """Nested attribute dictionary with immutability and typed merging."""
+
+    _IMMUTABLE = "__immutable__"
+
+    def __init__(self, init: dict | None = None):
+        super().__init__()
+        self.__dict__[CfgNode._IMMUTABLE] = False
+        for k, v in (init or {}).items():
+            self[k] = CfgNode(v) if isinstance(v, dict) and not isinstance(v, CfgNode) else v
+
+    # -- attribute protocol -------------------------------------------------
+    def __getattr__(self, name: str) -> Any:
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+    def __setattr__(self, name: str, value: Any) -> None:
+        if self.is_frozen():
+            raise AttributeError(f"Attempted to set {name} to {value}, but CfgNode is immutable")
+        if name in self.__dict__:
+            raise AttributeError(f"Invalid attempt to modify internal CfgNode state: {name}")
+        if not isinstance(value, _VALID_TYPES + (CfgNode, dict)):
+            raise AttributeError(f"Invalid type {type(value)} for key {name}")
+        self[name] = CfgNode(value) if isinstance(value, dict) and not isinstance(value, CfgNode) else value
+
+    # -- immutability ---------------------------------------------------------
+    def is_frozen(self) -> bool:
+        return self.__dict__[CfgNode._IMMUTABLE]
+
+    def _set_immutable(self, flag: bool) -> None:
+        self.__dict__[CfgNode._IMMUTABLE] = flag
+        for v in self.values():
+            if isinstance(v, CfgNode):
+                v._set_immutable(flag)
+
+    def freeze(self) -> None:
+        self._set_immutable(True)
+
+    def defrost(self) -> None:
+        self._set_immutable(False)
+
+    def clone(self) -> "CfgNode":
+        return copy.deepcopy(self)
+
+    def __deepcopy__(self, memo):
+        new = CfgNode()
+        for k, v in self.items():
+            dict.__setitem__(new, k, copy.deepcopy(v, memo))
+        new.__dict__[CfgNode._IMMUTABLE] = False
+        return new
+
+    # -- (de)serialisation ------------------------------------------------------
+    def to_dict(self) -> dict:
+        return {k: (v.to_dict() if isinstance(v, CfgNode) else (list(v) if isinstance(v, tuple) else v))
+                for k, v in self.items()}
+
+    def dump(self, stream=None, **kwargs):
+        kwargs.setdefault("default_flow_style", None)
+        return yaml.safe_dump(self.to_dict(), stream, **kwargs)
+
+    @classmethod
+    def load_cfg(cls, src) -> "CfgNode":
+        text = src.read() if hasattr(src, "read") else src
+        data = yaml.safe_load(io.StringIO(text)) or {}
+        if not isinstance(data, dict):
+            raise ValueError("config yaml must be a mapping at top level")
+        return cls(data)
+
+    def __str__(self) -> str:
+        return self.dump()
+
+    __repr__ = __str__
+
+    # -- merging -------------------------------------------------------------------
+    def merge_from_other_cfg(self, other: "CfgNode") -> None:
+        if self.is_frozen():
+            raise AttributeError("cannot merge into a frozen CfgNode")
+        _merge_a_into_b(other, self, self, [])
+
+    def merge_from_file(self, path: str) -> None:
+        with open(path, "r") as f:
+            self.merge_from_other_cfg(CfgNode.load_cfg(f))
+
+    def merge_from_list(self, pairs: Iterable[Any]) -> None:
+        pairs = list(pairs)
+        if len(pairs) % 2 != 0:
+            raise ValueError(f"Override list has odd length: {pairs}; it must be a list of pairs")
+        if self.is_frozen():
+            raise AttributeError("cannot merge into a frozen CfgNode")
+        for full_key, raw in zip(pairs[0::2], pairs[1::2]):
+            node = self
+            parts = full_key.split(".")
+            for sub in parts[:-1]:
+                if sub not in node or not isinstance(node[sub], CfgNode):
+                    raise KeyError(f"Non-existent config key: {full_key}")
+                node = node[sub]
+            leaf = parts[-1]
+            if leaf not in node:
+                raise KeyError(f"Non-existent config key: {full_key}")
+            value = _decode_value(raw)
+            node[leaf] = _coerce(value, node[leaf], full_key)
+
+
+def _decode_value(value: Any) -> Any:
+    """Turn a CLI string into a Python literal when it parses as one."""
+    if not isinstance(value, str):
+        return value
+    try:
+        return ast.literal_eval(value)
+    except (ValueError, SyntaxError):
+        low = value.strip().lower()
+        if low in ("true", "false"):
+            return low == "true"
+        if low in ("none", "null", "~"):
+            return None
+        return value
+
+
+def _coerce(new: Any, old: Any, key: str) -> Any:
+    """Type check a replacement value the way yacs does (with its few casts)."""
+    if old is None or new is None or type(new) is type(old):
+        return new
+    if isinstance(old, CfgNode) or isinstance(new, CfgNode):
+        raise ValueError(f"Type mismatch for key {key}: cannot replace {type(old)} with {type(new)}")
+    casts = {(tuple, list): list, (list, tuple): tuple, (int, float): float}
+    fn = casts.get((type(new), type(old)))
+    if fn is not None:
+        return fn(new)
+    raise ValueError(
+        f"Type mismatch ({type(old)} vs. {type(new)}) with values ({old} vs. {new}) for config key: {key}")
+
+
+def _merge_a_into_b(a: CfgNode, b: CfgNode, root: CfgNode, stack: list) -> None:
+    for k, v in a.items():
+        full = ".".join(stack + [k])
+        if k not in b:
+            raise KeyError(f"Non-existent config key: {full}")
+        if isinstance(v, dict) and not isinstance(v, CfgNode):
+            v = CfgNode(v)
+        if isinstance(b[k], CfgNode):
+            if not isinstance(v, CfgNode):
+                raise ValueError(f"Type mismatch for key {full}: expected a section")
+            _merge_a_into_b(v, b[k], root, stack + [k])
+        else:
+            dict.__setitem__(b, k, _coerce(copy.deepcopy(v), b[k], full))
+
+
+CN = CfgNode
+
+# ---------------------------------------------------------------------------------
+# Schema. Keys/defaults mirror reference config.py:10-63 exactly.
+# ---------------------------------------------------------------------------------
+_C = CN()
+cfg = _C
+
+_C.MODEL = CN()
+_C.MODEL.ARCH = "resnet18"
+_C.MODEL.NUM_CLASSES = 1000
+_C.MODEL.PRETRAINED = False
+_C.MODEL.SYNCBN = False
+_C.MODEL.WEIGHTS = None
+_C.MODEL.DUMMY_INPUT = False
+
+_C.TRAIN = CN()
+_C.TRAIN.BATCH_SIZE = 32
+_C.TRAIN.IM_SIZE = 224
+_C.TRAIN.DATASET = "./data/ILSVRC/"
+_C.TRAIN.SPLIT = "train"
+_C.TRAIN.AUTO_RESUME = True
+_C.TRAIN.LOAD_OPT = True
+_C.TRAIN.WORKERS = 4
+_C.TRAIN.PIN_MEMORY = True
+_C.TRAIN.PRINT_FREQ = 30
+_C.TRAIN.TOPK = 5
+
+_C.TEST = CN()
+_C.TEST.DATASET = "./data/ILSVRC/"
+_C.TEST.SPLIT = "val"
+_C.TEST.BATCH_SIZE = 200
+_C.TEST.IM_SIZE = 256
+_C.TEST.PRINT_FREQ = 10
+
+_C.CUDNN = CN()
+_C.CUDNN.BENCHMARK = True
+_C.CUDNN.DETERMINISTIC = False
+
+_C.OPTIM = CN()
+_C.OPTIM.MAX_EPOCH = 100
+_C.OPTIM.LR_POLICY = "cos"  # {'cos', 'steps'}
+_C.OPTIM.BASE_LR = 0.2
+_C.OPTIM.MIN_LR = 0.0
+_C.OPTIM.STEPS = []
+_C.OPTIM.LR_MULT = 0.1
+_C.OPTIM.MOMENTUM = 0.9
+_C.OPTIM.DAMPENING = 0.0
+_C.OPTIM.NESTEROV = True
+_C.OPTIM.WARMUP_FACTOR = 0.1
+_C.OPTIM.WARMUP_EPOCHS = 5
+_C.OPTIM.WEIGHT_DECAY = 5e-5
+
+_C.OUT_DIR = "./exp"
+_C.CFG_DEST = "config.yaml"
+_C.RNG_SEED = None
+
+# ---- additive B200 section (absent from the reference) ----------------------------
+_C.B200 = CN()
+# "auto": cuda if visible else cpu. Reference hard-codes cuda (trainer.py:113).
+_C.B200.DEVICE = "auto"
+# "auto": nccl on cuda, gloo on cpu. Reference hard-codes nccl (utils.py:19).
+_C.B200.DIST_BACKEND = "auto"
+# compute dtype of the native path: "bf16" (tcgen05) or "fp32" (reference semantics)
+_C.B200.PRECISION = "bf16"
+# "native": sm_100a kernels + peer-memory collectives; "torch": reference-semantics path
+# (torch ops + bucketed all_reduce). "auto" = native on cuda, torch on cpu.
+_C.B200.ENGINE = "auto"
+# gradient all-reduce transport for the native engine: "peer" (fused multimem / P2P kernel)
+# or "nccl" (baseline)
+_C.B200.COMM = "peer"
+# bytes per gradient bucket (first bucket is capped at 1 MiB like torch DDP's)
+_C.B200.BUCKET_MB = 25
+# length of the synthetic dataset used with MODEL.DUMMY_INPUT (reference: 1000, utils.py:125,
+# which yields zero iterations at >=4 ranks x batch 256 -- SURVEY 2.6-6)
+_C.B200.DUMMY_LEN = 1000
+# generate dummy batches on the device instead of a host tensor + H2D copy
+_C.B200.DUMMY_ON_DEVICE = False
+# read metrics back to the host every N iterations (reference: every iteration)
+_C.B200.METRIC_SYNC_FREQ = 1
+# capture per-phase CUDA-event timings
+_C.B200.PROFILE = False
+# stop an epoch after this many iterations (0 = full epoch); used by tests/smoke
+_C.B200.MAX_ITERS = 0
+
+_CFG_DEFAULT = _C.clone()
+_CFG_DEFAULT.freeze()
+
+
+def merge_from_file(cfg_file: str) -> None:
+    """Merge a yaml preset into the global config (reference config.py:69-72)."""
+    _C.merge_from_file(cfg_file)
+
+
+def dump_cfg() -> None:
+    """Write the config to OUT_DIR/CFG_DEST (reference config.py:75-79)."""
+    os.makedirs(_C.OUT_DIR, exist_ok=True)
+    with open(os.path.join(_C.OUT_DIR, _C.CFG_DEST), "w") as f:
+        _C.dump(stream=f)
+
+
+def reset_cfg() -> None:
+    """Restore defaults (reference config.py:82-84)."""
+    _C.defrost()
+    _C.merge_from_other_cfg(_CFG_DEFAULT)
+
+
+def load_cfg_fom_args(description: str = "Config file options.", argv=None) -> None:
+    """Parse ``--cfg FILE [KEY VALUE ...]`` (name keeps the reference's spelling,
+    config.py:87-100; ``--local_rank`` is accepted for torch.distributed.launch)."""
+    parser = argparse.ArgumentParser(description=description)
+    parser.add_argument("--cfg", dest="cfg_file", default=None, type=str, help="Config file location")
+    parser.add_argument("--local_rank", "--local-rank", default=None,
+                        help="accepted for torch.distributed.launch; LOCAL_RANK env wins")
+    parser.add_argument("opts", default=None, nargs=argparse.REMAINDER,
+                        help="KEY VALUE overrides, see distribuuuu_b200/config.py")
+    args = parser.parse_args(argv)
+    if args.local_rank is not None and "LOCAL_RANK" not in os.environ:
+        os.environ["LOCAL_RANK"] = str(args.local_rank)
+    if args.cfg_file is not None:
+        merge_from_file(args.cfg_file)
+    if args.opts:
+        _C.merge_from_list(args.opts)
+
+
+load_cfg_from_args = load_cfg_fom_args

@@ -1,0 +1,161 @@
+"""Datasets and loaders.
+
+Parity: reference ``utils.py:109-184``: ``DummyDataset`` (host randn, label 0),
+ImageFolder train pipeline (RandomResizedCrop(IM_SIZE) / HFlip / ToTensor / Normalize,
+DistributedSampler(shuffle), drop_last) and val pipeline (Resize(TEST.IM_SIZE) /
+CenterCrop(224) / ..., padded DistributedSampler, keep last).
+
+New: ``SyntheticDeviceLoader`` generates ImageNet-shaped batches directly on the GPU
+(no 602 MB host tensor, no zero-iteration corner when ranks x batch > 1000)
+and ``PinnedPrefetcher`` overlaps the H2D copy of batch i+1 with step i.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+from torch.utils.data import DataLoader, Dataset
+from torch.utils.data.distributed import DistributedSampler
+
+from ..config import cfg
+from .dist import get_rank, get_world_size
+
+IMAGENET_MEAN = (0.485, 0.456, 0.406)
+IMAGENET_STD = (0.229, 0.224, 0.225)
+
+
+class DummyDataset(Dataset):
+    """``length`` random images of shape ``size``; every label is 0."""
+
+    def __init__(self, length: int, size):
+        self.len = int(length)
+        gen = torch.Generator().manual_seed(0)
+        self.data = torch.randn([self.len] + list(size), generator=gen)
+
+    def __getitem__(self, index):
+        return self.data[index], 0
+
+    def __len__(self):
+        return self.len
+
+
+class _NoopSampler:
+    def set_epoch(self, epoch: int) -> None:  # same surface as DistributedSampler
+        self.epoch = epoch
+
+
+class SyntheticDeviceLoader:
+    """Endless-epoch-free synthetic source living on the compute device.
+
+    Yields ``iters`` batches per epoch of ``(randn[B,3,S,S], randint[B])``; images are
+    regenerated per batch by a device RNG so nothing crosses PCIe.
+    """
+
+    def __init__(self, batch_size: int, im_size: int, num_classes: int, length: int,
+                 device: torch.device, drop_last: bool = True, dtype=torch.float32):
+        per_rank = length // get_world_size() if drop_last else -(-length // get_world_size())
+        self.iters = per_rank // batch_size if drop_last else -(-per_rank // batch_size)
+        self.batch_size, self.im_size, self.num_classes = batch_size, im_size, num_classes
+        self.device, self.dtype = device, dtype
+        self.sampler = _NoopSampler()
+        self.gen = torch.Generator(device=device).manual_seed(1234 + get_rank())
+
+    def __len__(self):
+        return self.iters
+
+    def __iter__(self):
+        for _ in range(self.iters):
+            x = torch.randn(self.batch_size, 3, self.im_size, self.im_size, device=self.device,
+                            dtype=self.dtype, generator=self.gen)
+            y = torch.randint(0, self.num_classes, (self.batch_size,), device=self.device, generator=self.gen)
+            yield x, y
+
+
+class PinnedPrefetcher:
+    """Wraps a host loader: copies batch i+1 to the device on a side stream while the
+    caller computes on batch i (replaces the blocking ``inputs.cuda()`` at reference
+    trainer.py:40)."""
+
+    def __init__(self, loader, device: torch.device):
+        self.loader, self.device = loader, device
+        self.sampler = getattr(loader, "sampler", _NoopSampler())
+        self.stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+
+    def __len__(self):
+        return len(self.loader)
+
+    def _stage(self, batch):
+        x, y = batch
+        if not torch.is_tensor(y):
+            y = torch.as_tensor(y)
+        if self.stream is None:
+            return x.to(self.device), y.to(self.device)
+        with torch.cuda.stream(self.stream):
+            return x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+
+    def __iter__(self):
+        it = iter(self.loader)
+        try:
+            nxt = self._stage(next(it))
+        except StopIteration:
+            return
+        while nxt is not None:
+            if self.stream is not None:
+                torch.cuda.current_stream(self.device).wait_stream(self.stream)
+                for t in nxt:
+                    t.record_stream(torch.cuda.current_stream(self.device))
+            cur = nxt
+            try:
+                nxt = self._stage(next(it))
+            except StopIteration:
+                nxt = None
+            yield cur
+
+
+def _transforms():
+    import torchvision.transforms as T
+    return T
+
+
+def _image_folder(root, transform):
+    import torchvision
+    return torchvision.datasets.ImageFolder(root=root, transform=transform)
+
+
+def _use_device_synthetic() -> bool:
+    return bool(cfg.MODEL.DUMMY_INPUT and cfg.B200.DUMMY_ON_DEVICE)
+
+
+def construct_train_loader(device: torch.device | None = None):
+    if _use_device_synthetic() and device is not None:
+        return SyntheticDeviceLoader(cfg.TRAIN.BATCH_SIZE, cfg.TRAIN.IM_SIZE, cfg.MODEL.NUM_CLASSES,
+                                     cfg.B200.DUMMY_LEN, device, drop_last=True)
+    if cfg.MODEL.DUMMY_INPUT:
+        trainset = DummyDataset(cfg.B200.DUMMY_LEN, [3, cfg.TRAIN.IM_SIZE, cfg.TRAIN.IM_SIZE])
+    else:
+        T = _transforms()
+        trainset = _image_folder(os.path.join(cfg.TRAIN.DATASET, cfg.TRAIN.SPLIT), T.Compose([
+            T.RandomResizedCrop(cfg.TRAIN.IM_SIZE), T.RandomHorizontalFlip(), T.ToTensor(),
+            T.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)]))
+    sampler = DistributedSampler(trainset, num_replicas=get_world_size(), rank=get_rank(), shuffle=True)
+    return DataLoader(trainset, batch_size=cfg.TRAIN.BATCH_SIZE, num_workers=cfg.TRAIN.WORKERS,
+                      pin_memory=cfg.TRAIN.PIN_MEMORY and torch.cuda.is_available(),
+                      sampler=sampler, drop_last=True, persistent_workers=cfg.TRAIN.WORKERS > 0)
+
+
+def construct_val_loader(device: torch.device | None = None):
+    if _use_device_synthetic() and device is not None:
+        return SyntheticDeviceLoader(cfg.TEST.BATCH_SIZE, 224, cfg.MODEL.NUM_CLASSES,
+                                     cfg.B200.DUMMY_LEN, device, drop_last=False)
+    if cfg.MODEL.DUMMY_INPUT:
+        valset = DummyDataset(cfg.B200.DUMMY_LEN, [3, 224, 224])
+    else:
+        T = _transforms()
+        # the reference reads the val split under TRAIN.DATASET (utils.py:157); kept.
+        valset = _image_folder(os.path.join(cfg.TRAIN.DATASET, cfg.TEST.SPLIT), T.Compose([
+            T.Resize(cfg.TEST.IM_SIZE), T.CenterCrop(224), T.ToTensor(),
+            T.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)]))
+    sampler = DistributedSampler(valset, num_replicas=get_world_size(), rank=get_rank(), shuffle=False)
+    return DataLoader(valset, batch_size=cfg.TEST.BATCH_SIZE, shuffle=False, sampler=sampler,
+                      num_workers=cfg.TRAIN.WORKERS, pin_memory=cfg.TRAIN.PIN_MEMORY and torch.cuda.is_available(),
+                      drop_last=False, persistent_workers=cfg.TRAIN.WORKERS > 0)
