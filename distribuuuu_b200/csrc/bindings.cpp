@@ -1,0 +1,523 @@
+// Python bindings (pybind11 / torch tensors) for the sm_100a kernels.  Host-side work done here:
+// TMA descriptor (CUtensorMap) construction -- tiled and im2col -- with a small cache, UMMA descriptor /
+// tile-shape selection, split-K planning, and marshalling of the peer-memory contexts.
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <torch/extension.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "comm.h"
+#include "conv_gemm.h"
+#include "elementwise.h"
+
+namespace {
+
+#define B200_CUDA_OK(expr)                                                                          \
+  do {                                                                                              \
+    int _e = (int)(expr);                                                                           \
+    TORCH_CHECK(_e == 0, #expr " failed: ", cudaGetErrorString((cudaError_t)_e), " (", _e, ")");   \
+  } while (0)
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+template <typename Fn>
+Fn driver_fn(const char* name) {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &qres);
+  TORCH_CHECK(e == cudaSuccess && qres == cudaDriverEntryPointSuccess && fn != nullptr, "driver entry point ", name,
+              " unavailable");
+  return reinterpret_cast<Fn>(fn);
+}
+
+struct MapKey {
+  uint64_t v[12];
+  bool operator==(const MapKey& o) const { return memcmp(v, o.v, sizeof(v)) == 0; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    uint64_t h = 1469598103934665603ull;
+    for (uint64_t x : k.v) { h ^= x; h *= 1099511628211ull; }
+    return (size_t)h;
+  }
+};
+std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_map_cache;
+std::mutex g_map_mutex;
+
+// Rank-3 tiled map over a bf16 tensor: dims (d0 inner, d1, d2), strides in ELEMENTS for d1/d2, 128B swizzle.
+CUtensorMap tiled_map_3d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1, uint64_t s2, uint32_t b0,
+                         uint32_t b1, uint32_t b2) {
+  MapKey key{{(uint64_t)ptr, d0, d1, d2, s1, s2, b0, b1, b2, 0, 0, 1}};
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) return it->second;
+  static EncodeTiledFn encode = driver_fn<EncodeTiledFn>("cuTensorMapEncodeTiled");
+  TORCH_CHECK(((uintptr_t)ptr & 15) == 0, "TMA base address must be 16-byte aligned");
+  TORCH_CHECK((s1 * 2) % 16 == 0 && (s2 * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes (", s1, ", ", s2, ")");
+  CUtensorMap m;
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {s1 * 2, s2 * 2};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with ", (int)r, " dims=(", d0, ",", d1, ",", d2,
+              ") strides=(", s1, ",", s2, ") box=(", b0, ",", b1, ",", b2, ")");
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache.emplace(key, m);
+  return m;
+}
+
+// im2col map over an NHWC bf16 activation (dims C, W, H, N).
+CUtensorMap im2col_map_4d(const void* ptr, int N, int H, int W, int C, int low_w, int low_h, int up_w, int up_h,
+                          int stride, uint32_t channels_per_pixel, uint32_t pixels_per_column) {
+  MapKey key{{(uint64_t)ptr, (uint64_t)N, (uint64_t)H, (uint64_t)W, (uint64_t)C, (uint64_t)(uint32_t)low_w,
+              (uint64_t)(uint32_t)low_h, (uint64_t)(uint32_t)up_w, (uint64_t)(uint32_t)up_h, (uint64_t)stride,
+              ((uint64_t)channels_per_pixel << 32) | pixels_per_column, 2}};
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) return it->second;
+  static EncodeIm2colFn encode = driver_fn<EncodeIm2colFn>("cuTensorMapEncodeIm2col");
+  TORCH_CHECK(((uintptr_t)ptr & 15) == 0 && (C % 8) == 0, "im2col TMA needs 16-byte aligned base and C % 8 == 0");
+  CUtensorMap m;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  int lower[2] = {low_w, low_h};
+  int upper[2] = {up_w, up_h};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper,
+                      channels_per_pixel, pixels_per_column, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeIm2col failed with ", (int)r, " NHWC=(", N, ",", H, ",", W, ",", C,
+              ") corners=(", low_w, ",", low_h, ",", up_w, ",", up_h, ") stride=", stride);
+  // Driver <= 13.1 sets a descriptor bit that breaks im2col loads on tensors smaller than 128 KiB (same
+  // workaround CUTLASS applies in make_im2col_tma_copy_desc).
+  int drv = 0;
+  cudaDriverGetVersion(&drv);
+  if (drv <= 13010 && (uint64_t)N * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache.emplace(key, m);
+  return m;
+}
+
+inline uint64_t desc_hi_sw128(uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+inline uint32_t idesc_bf16(uint32_t m, uint32_t n, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | (a_mn << 15) | (b_mn << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// K-major operand: rows of 128 B, 8-row swizzle atoms 1024 B apart; a UMMA_K=16 step advances 32 B.
+constexpr uint32_t kKMajorLbo = 16, kKMajorSbo = 1024, kKMajorStep16 = 2;
+// MN-major operand: [64 k-rows][64 mn] boxes of 8 KB; 8-row groups 1024 B apart; UMMA_K=16 step = 2 groups.
+constexpr uint32_t kMnMajorLbo = 8192, kMnMajorSbo = 1024, kMnMajorStep16 = 128;
+
+int pick_bn(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
+
+void check_bf16_contig(const at::Tensor& t, const char* name) {
+  TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.is_contiguous(), name, " must be a contiguous CUDA bf16 tensor");
+}
+
+int g_num_sms = 0;
+int num_sms() {
+  if (!g_num_sms) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return g_num_sms;
+}
+
+cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
+
+struct ConvGeom { int N, H, W, C, K, R, S, P, Q, stride, pad, dil; };
+
+ConvGeom geom(const at::Tensor& x, const at::Tensor& w, int stride, int pad, int dil) {
+  ConvGeom g;
+  g.N = x.size(0); g.H = x.size(1); g.W = x.size(2); g.C = x.size(3);
+  g.K = w.size(0); g.R = w.size(1); g.S = w.size(2);
+  TORCH_CHECK(w.size(3) == g.C, "weight Cin ", w.size(3), " != activation channels ", g.C);
+  g.stride = stride; g.pad = pad; g.dil = dil;
+  g.P = (g.H + 2 * pad - dil * (g.R - 1) - 1) / stride + 1;
+  g.Q = (g.W + 2 * pad - dil * (g.S - 1) - 1) / stride + 1;
+  return g;
+}
+
+// ---------------------------------------------------------------------------------------------- conv fprop
+// x [N,H,W,C], w [K,R,S,C], out [N,P,Q,K] (all bf16, contiguous).  stats: fp32 [2*K] accumulated, bias fp32 [K].
+void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const c10::optional<at::Tensor>& stats,
+                const c10::optional<at::Tensor>& bias, int64_t stride, int64_t pad, int64_t dil) {
+  check_bf16_contig(x, "x"); check_bf16_contig(w, "w"); check_bf16_contig(out, "out");
+  c10::cuda::CUDAGuard guard(x.device());
+  const ConvGeom g = geom(x, w, stride, pad, dil);
+  TORCH_CHECK(out.numel() == (int64_t)g.N * g.P * g.Q * g.K, "bad output shape");
+  TORCH_CHECK(g.C % 8 == 0 && g.K % 8 == 0, "channels must be multiples of 8 (C=", g.C, " K=", g.K, ")");
+  const int M = g.N * g.P * g.Q;
+  const int bn = pick_bn(g.K);
+  const bool pointwise = (g.R == 1 && g.S == 1 && stride == 1 && pad == 0);
+  ConvGemmParams p{};
+  p.kind = KIND_FPROP; p.epi = EPI_BF16;
+  p.M = M; p.N = g.K;
+  p.m_blocks = (M + 127) / 128; p.n_blocks = (g.K + bn - 1) / bn;
+  p.taps = g.R * g.S; p.S = g.S; p.kb_per_tap = (g.C + 63) / 64; p.dil = dil;
+  p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
+  p.b_im2col = 0; p.b_nbox = 1; p.b_kstep16 = kKMajorStep16; p.b_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
+  p.b_flip_taps = 0;
+  p.idesc = idesc_bf16(128, bn, 0, 0);
+  p.im_P = g.P; p.im_Q = g.Q; p.im_stride = stride; p.im_low_w = -pad; p.im_low_h = -pad;
+  p.k_blocks_total = 0; p.splits = 1;
+  p.out = out.data_ptr(); p.ldo = g.K; p.tap_stride = 0;
+  p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;
+  p.bias = bias.has_value() ? bias->data_ptr<float>() : nullptr;
+  if (stats.has_value()) TORCH_CHECK(stats->numel() >= 2 * g.K && stats->scalar_type() == at::kFloat, "stats must be fp32 [2*K]");
+  p.total_items = p.m_blocks * p.n_blocks;
+  CUtensorMap ma = pointwise
+                       ? tiled_map_3d(x.data_ptr(), g.C, 1, M, g.C, g.C, 64, 1, 128)
+                       : im2col_map_4d(x.data_ptr(), g.N, g.H, g.W, g.C, -pad, -pad, pad - (g.S - 1) * dil,
+                                       pad - (g.R - 1) * dil, stride, 64, 128);
+  CUtensorMap mb = tiled_map_3d(w.data_ptr(), g.C, p.taps, g.K, g.C, (uint64_t)p.taps * g.C, 64, 1, bn);
+  const int grid = std::min(p.total_items, num_sms());
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &p, bn, grid, cur_stream()));
+}
+
+// ---------------------------------------------------------------------------------------------- conv dgrad (stride 1)
+// dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C].
+void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64_t stride, int64_t pad, int64_t dil) {
+  check_bf16_contig(dy, "dy"); check_bf16_contig(w, "w"); check_bf16_contig(dx, "dx");
+  TORCH_CHECK(stride == 1, "tcgen05 dgrad handles stride 1 (strided layers use the zero-insertion path)");
+  c10::cuda::CUDAGuard guard(dy.device());
+  const int N = dx.size(0), H = dx.size(1), W = dx.size(2), C = dx.size(3);
+  const int K = w.size(0), R = w.size(1), S = w.size(2);
+  const int P = dy.size(1), Q = dy.size(2);
+  TORCH_CHECK(dy.size(3) == K && w.size(3) == C, "dgrad shape mismatch");
+  TORCH_CHECK(P == H + 2 * pad - dil * (R - 1) && Q == W + 2 * pad - dil * (S - 1), "dgrad: dy spatial size inconsistent");
+  TORCH_CHECK(C % 8 == 0 && K % 8 == 0, "channels must be multiples of 8");
+  const int M = N * H * W;
+  const int bn = pick_bn(C);
+  const bool pointwise = (R == 1 && S == 1 && pad == 0);
+  const int padp_h = dil * (R - 1) - pad, padp_w = dil * (S - 1) - pad;  // padding of the transposed problem
+  ConvGemmParams p{};
+  p.kind = KIND_DGRAD; p.epi = EPI_BF16;
+  p.M = M; p.N = C;
+  p.m_blocks = (M + 127) / 128; p.n_blocks = (C + bn - 1) / bn;
+  p.taps = R * S; p.S = S; p.kb_per_tap = (K + 63) / 64; p.dil = dil;
+  p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
+  p.b_im2col = 0; p.b_nbox = bn / 64; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
+  p.b_flip_taps = 1;
+  p.idesc = idesc_bf16(128, bn, 0, 1);
+  p.im_P = H; p.im_Q = W; p.im_stride = 1; p.im_low_w = -padp_w; p.im_low_h = -padp_h;
+  p.splits = 1;
+  p.out = dx.data_ptr(); p.ldo = C;
+  p.total_items = p.m_blocks * p.n_blocks;
+  CUtensorMap ma = pointwise ? tiled_map_3d(dy.data_ptr(), K, 1, M, K, K, 64, 1, 128)
+                             : im2col_map_4d(dy.data_ptr(), N, P, Q, K, -padp_w, -padp_h, padp_w - (S - 1) * dil,
+                                             padp_h - (R - 1) * dil, 1, 64, 128);
+  // weights viewed as (C inner, taps, K): MN-major B boxes of [64 k-rows (Cout)][64 n (Cin)]
+  CUtensorMap mb = tiled_map_3d(w.data_ptr(), C, p.taps, K, C, (uint64_t)p.taps * C, 64, 1, 64);
+  const int grid = std::min(p.total_items, num_sms());
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &p, bn, grid, cur_stream()));
+}
+
+// ---------------------------------------------------------------------------------------------- conv wgrad
+// dy [N,P,Q,K], x [N,H,W,C] -> dw fp32 [K,R,S,C] (accumulated with red.add; caller zeroes).
+void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64_t stride, int64_t pad, int64_t dil) {
+  check_bf16_contig(dy, "dy"); check_bf16_contig(x, "x");
+  TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.is_contiguous(), "dw must be contiguous fp32");
+  c10::cuda::CUDAGuard guard(dy.device());
+  const int N = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
+  const int K = dw.size(0), R = dw.size(1), S = dw.size(2);
+  const int P = dy.size(1), Q = dy.size(2);
+  TORCH_CHECK(dy.size(3) == K && dw.size(3) == C && dy.size(0) == N, "wgrad shape mismatch");
+  TORCH_CHECK(C % 8 == 0 && K % 8 == 0, "channels must be multiples of 8");
+  const long long pixels = (long long)N * P * Q;
+  const int bn = pick_bn(C);
+  const bool pointwise = (R == 1 && S == 1 && stride == 1 && pad == 0);
+  ConvGemmParams p{};
+  p.kind = KIND_WGRAD; p.epi = EPI_F32_RED;
+  p.M = K; p.N = C;
+  p.m_blocks = (K + 127) / 128; p.n_blocks = (C + bn - 1) / bn;
+  p.taps = R * S; p.S = S; p.kb_per_tap = 0; p.dil = dil;
+  p.a_im2col = 0; p.a_nbox = 2; p.a_kstep16 = kMnMajorStep16; p.a_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
+  p.b_im2col = pointwise ? 0 : 1; p.b_nbox = bn / 64; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
+  p.b_flip_taps = 0;
+  p.idesc = idesc_bf16(128, bn, 1, 1);
+  p.im_P = P; p.im_Q = Q; p.im_stride = stride; p.im_low_w = -pad; p.im_low_h = -pad;
+  p.k_blocks_total = (int)((pixels + 63) / 64);
+  const int base_items = p.m_blocks * p.n_blocks * p.taps;
+  int splits = (2 * num_sms() + base_items - 1) / base_items;
+  splits = std::max(1, std::min(splits, std::max(1, p.k_blocks_total / 8)));
+  p.splits = splits;
+  p.out = dw.data_ptr(); p.ldo = (long long)p.taps * C; p.tap_stride = C;
+  p.total_items = base_items * splits;
+  CUtensorMap ma = tiled_map_3d(dy.data_ptr(), K, 1, pixels, K, K, 64, 1, 64);
+  CUtensorMap mb = pointwise ? tiled_map_3d(x.data_ptr(), C, 1, pixels, C, C, 64, 1, 64)
+                             : im2col_map_4d(x.data_ptr(), N, H, W, C, -pad, -pad, pad - (S - 1) * dil,
+                                             pad - (R - 1) * dil, stride, 64, 64);
+  const int grid = std::min(p.total_items, num_sms());
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &p, bn, grid, cur_stream()));
+}
+
+// ---------------------------------------------------------------------------------------------- peer contexts
+struct PeerState {
+  int world = 1, rank = 0, slot_base = 0;
+  std::vector<int64_t> signal_pads, sym_bufs;
+  int64_t ticket = 0;
+  uint32_t epoch = 0;
+  PeerCtx make() {
+    PeerCtx c{};
+    c.world = world; c.rank = rank; c.slot_base = slot_base;
+    if (world > 1) {
+      TORCH_CHECK((int)signal_pads.size() == world && (int)sym_bufs.size() == world && world <= kMaxPeers, "bad peer state");
+      for (int i = 0; i < world; ++i) {
+        c.signal_pads[i] = reinterpret_cast<uint32_t*>(signal_pads[i]);
+        c.sym_bufs[i] = reinterpret_cast<float*>(sym_bufs[i]);
+      }
+      c.epoch = ++epoch;
+    }
+    c.ticket = reinterpret_cast<int*>(ticket);
+    return c;
+  }
+};
+
+const float* fptr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+float* fptr_mut(c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+const __nv_bfloat16* bptr(const at::Tensor& t) { return reinterpret_cast<const __nv_bfloat16*>(t.data_ptr()); }
+__nv_bfloat16* bptr_mut(at::Tensor& t) { return reinterpret_cast<__nv_bfloat16*>(t.data_ptr()); }
+
+// y/out/residual are [rows, C] views (last dim contiguous, arbitrary row pitch).
+void bn_apply(const at::Tensor& y, const c10::optional<at::Tensor>& residual, at::Tensor& out, const at::Tensor& stats,
+              int64_t sym_offset, const c10::optional<at::Tensor>& gamma, const c10::optional<at::Tensor>& beta,
+              c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var, at::Tensor& save_mean,
+              at::Tensor& save_invstd, double count, double eps, double momentum, int64_t act, bool training,
+              PeerState* peer) {
+  c10::cuda::CUDAGuard guard(y.device());
+  TORCH_CHECK(y.dim() == 2 && y.stride(1) == 1 && out.stride(1) == 1 && y.size(1) % 8 == 0, "bn_apply expects [rows, C] with C % 8 == 0");
+  BnApplyParams p{};
+  p.y = bptr(y); p.ldy = y.stride(0);
+  p.residual = residual.has_value() ? bptr(*residual) : nullptr; p.ldr = residual.has_value() ? residual->stride(0) : 0;
+  p.out = bptr_mut(out); p.ldo = out.stride(0);
+  p.rows = y.size(0); p.C = y.size(1);
+  p.stats = stats.data_ptr<float>(); p.sym_offset = sym_offset;
+  p.gamma = fptr(gamma); p.beta = fptr(beta);
+  p.running_mean = fptr_mut(running_mean); p.running_var = fptr_mut(running_var);
+  p.save_mean = save_mean.data_ptr<float>(); p.save_invstd = save_invstd.data_ptr<float>();
+  p.count = (float)count; p.eps = (float)eps; p.momentum = (float)momentum; p.act = act; p.training = training;
+  if (peer && training) p.peer = peer->make(); else { p.peer = PeerCtx{}; p.peer.world = 1; }
+  B200_CUDA_OK(b200_bn_apply(&p, cur_stream()));
+}
+
+void bn_stats(const at::Tensor& y, at::Tensor& stats) {
+  c10::cuda::CUDAGuard guard(y.device());
+  TORCH_CHECK(y.dim() == 2 && y.stride(1) == 1 && y.size(1) % 8 == 0, "bn_stats expects [rows, C]");
+  B200_CUDA_OK(b200_bn_stats(y.data_ptr(), y.size(0), y.size(1), y.stride(0), stats.data_ptr<float>(), cur_stream()));
+}
+
+void bn_backward(const at::Tensor& y, const at::Tensor& dout, const c10::optional<at::Tensor>& residual, at::Tensor& dy,
+                 c10::optional<at::Tensor> dresidual, at::Tensor& sums, int64_t sym_offset,
+                 const c10::optional<at::Tensor>& gamma, const c10::optional<at::Tensor>& beta, const at::Tensor& save_mean,
+                 const at::Tensor& save_invstd, c10::optional<at::Tensor> dgamma, c10::optional<at::Tensor> dbeta,
+                 double count, int64_t act, PeerState* peer) {
+  c10::cuda::CUDAGuard guard(y.device());
+  TORCH_CHECK(y.dim() == 2 && y.stride(1) == 1 && dout.stride(1) == 1 && dy.stride(1) == 1, "bn_backward expects [rows, C] views");
+  TORCH_CHECK(dy.stride(0) == y.stride(0), "dy must share y's row pitch");
+  BnBwdParams p{};
+  p.y = bptr(y); p.ldy = y.stride(0);
+  p.dout = bptr(dout); p.ldd = dout.stride(0);
+  p.residual = residual.has_value() ? bptr(*residual) : nullptr; p.ldr = residual.has_value() ? residual->stride(0) : 0;
+  p.dy = bptr_mut(dy);
+  p.dresidual = dresidual.has_value() ? bptr_mut(*dresidual) : nullptr;
+  if (dresidual.has_value()) { TORCH_CHECK(!residual.has_value() || dresidual->stride(0) == residual->stride(0), "dresidual pitch"); p.ldr = dresidual->stride(0); }
+  p.rows = y.size(0); p.C = y.size(1);
+  p.sums = sums.data_ptr<float>(); p.sym_offset = sym_offset;
+  p.gamma = fptr(gamma); p.beta = fptr(beta);
+  p.save_mean = save_mean.data_ptr<float>(); p.save_invstd = save_invstd.data_ptr<float>();
+  p.dgamma = fptr_mut(dgamma); p.dbeta = fptr_mut(dbeta);
+  p.count = (float)count; p.act = act;
+  p.peer = PeerCtx{}; p.peer.world = 1;
+  B200_CUDA_OK(b200_bn_bwd_reduce(&p, cur_stream()));
+  if (peer) p.peer = peer->make();
+  B200_CUDA_OK(b200_bn_bwd_apply(&p, cur_stream()));
+}
+
+void maxpool_fwd(const at::Tensor& x, at::Tensor& out, c10::optional<at::Tensor> argmax, int64_t k, int64_t stride, int64_t pad) {
+  check_bf16_contig(x, "x"); check_bf16_contig(out, "out");
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.size(3) % 8 == 0 && k * k <= 255, "maxpool: C % 8 == 0");
+  B200_CUDA_OK(b200_maxpool_fwd(x.data_ptr(), out.data_ptr(), argmax.has_value() ? argmax->data_ptr() : nullptr, x.size(0),
+                                x.size(1), x.size(2), x.size(3), out.size(1), out.size(2), k, stride, pad, cur_stream()));
+}
+void maxpool_bwd(const at::Tensor& dout, const at::Tensor& argmax, at::Tensor& dx, int64_t k, int64_t stride, int64_t pad) {
+  check_bf16_contig(dout, "dout"); check_bf16_contig(dx, "dx");
+  c10::cuda::CUDAGuard guard(dout.device());
+  B200_CUDA_OK(b200_maxpool_bwd(dout.data_ptr(), argmax.data_ptr(), dx.data_ptr(), dx.size(0), dx.size(1), dx.size(2),
+                                dx.size(3), dout.size(1), dout.size(2), k, stride, pad, cur_stream()));
+}
+void gap_fwd(const at::Tensor& x, at::Tensor& out) {
+  check_bf16_contig(x, "x"); check_bf16_contig(out, "out");
+  c10::cuda::CUDAGuard guard(x.device());
+  B200_CUDA_OK(b200_gap_fwd(x.data_ptr(), out.data_ptr(), x.size(0), x.size(1) * x.size(2), x.size(3), cur_stream()));
+}
+void gap_bwd(const at::Tensor& dout, at::Tensor& dx) {
+  check_bf16_contig(dout, "dout"); check_bf16_contig(dx, "dx");
+  c10::cuda::CUDAGuard guard(dout.device());
+  B200_CUDA_OK(b200_gap_bwd(dout.data_ptr(), dx.data_ptr(), dx.size(0), dx.size(1) * dx.size(2), dx.size(3), cur_stream()));
+}
+void avgpool2_fwd(const at::Tensor& x, at::Tensor& out) {
+  check_bf16_contig(x, "x"); check_bf16_contig(out, "out");
+  c10::cuda::CUDAGuard guard(x.device());
+  B200_CUDA_OK(b200_avgpool2_fwd(x.data_ptr(), out.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), cur_stream()));
+}
+void avgpool2_bwd(const at::Tensor& dout, at::Tensor& dx) {
+  check_bf16_contig(dout, "dout"); check_bf16_contig(dx, "dx");
+  c10::cuda::CUDAGuard guard(dout.device());
+  B200_CUDA_OK(b200_avgpool2_bwd(dout.data_ptr(), dx.data_ptr(), dx.size(0), dx.size(1), dx.size(2), dx.size(3), cur_stream()));
+}
+
+// accum: fp32 [3] = (sum of per-sample losses, top-1 hits, top-k hits), accumulated.
+void ce_topk(const at::Tensor& logits, const at::Tensor& target, c10::optional<at::Tensor> dlogits, at::Tensor& accum,
+             int64_t topk, double grad_scale) {
+  c10::cuda::CUDAGuard guard(logits.device());
+  TORCH_CHECK(logits.scalar_type() == at::kBFloat16 && logits.dim() == 2 && logits.stride(1) == 1, "logits: bf16 [B, classes]");
+  TORCH_CHECK(target.scalar_type() == at::kLong && target.is_contiguous(), "target: int64");
+  if (dlogits.has_value()) TORCH_CHECK(dlogits->stride(0) == logits.stride(0) && dlogits->scalar_type() == at::kBFloat16, "dlogits layout");
+  B200_CUDA_OK(b200_ce_topk(logits.data_ptr(), (const long long*)target.data_ptr<int64_t>(),
+                            dlogits.has_value() ? dlogits->data_ptr() : nullptr, accum.data_ptr<float>(), logits.size(0),
+                            logits.size(1), logits.stride(0), topk, (float)grad_scale, cur_stream()));
+}
+
+void nchw_to_nhwc(const at::Tensor& x, at::Tensor& out) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.scalar_type() == at::kFloat && x.is_contiguous() && out.scalar_type() == at::kBFloat16, "nchw_to_nhwc: fp32 -> bf16");
+  B200_CUDA_OK(b200_nchw_to_nhwc(x.data_ptr<float>(), out.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), cur_stream()));
+}
+void stem_im2col(const at::Tensor& x, at::Tensor& patches, int64_t R, int64_t S, int64_t stride, int64_t pad, int64_t P, int64_t Q) {
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.scalar_type() == at::kFloat && x.is_contiguous() && patches.scalar_type() == at::kBFloat16 && patches.is_contiguous(), "stem_im2col dtypes");
+  B200_CUDA_OK(b200_stem_im2col(x.data_ptr<float>(), patches.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), P, Q, R, S,
+                                stride, pad, patches.size(-1), cur_stream()));
+}
+void pad_rows(const at::Tensor& src, at::Tensor& dst, int64_t rows, int64_t cols, int64_t cols_pad) {
+  c10::cuda::CUDAGuard guard(src.device());
+  B200_CUDA_OK(b200_pad_rows(src.data_ptr(), dst.data_ptr(), rows, cols, cols_pad, cur_stream()));
+}
+void unpad_add(const at::Tensor& src, at::Tensor& dst, int64_t rows, int64_t cols, int64_t cols_pad) {
+  c10::cuda::CUDAGuard guard(src.device());
+  B200_CUDA_OK(b200_unpad_add(src.data_ptr<float>(), dst.data_ptr<float>(), rows, cols, cols_pad, cur_stream()));
+}
+
+// ---------------------------------------------------------------------------------------------- optimizer / comm
+SgdHyper hyper(double lr, double momentum, double dampening, double wd, bool nesterov, bool first) {
+  SgdHyper h; h.lr = lr; h.momentum = momentum; h.dampening = dampening; h.weight_decay = wd; h.nesterov = nesterov; h.first_step = first;
+  return h;
+}
+void sgd_local(at::Tensor& master, at::Tensor& mom, at::Tensor& grad, c10::optional<at::Tensor> w16, int64_t off, int64_t n,
+               double lr, double momentum, double dampening, double wd, bool nesterov, bool first, double grad_scale, bool zero_grad) {
+  c10::cuda::CUDAGuard guard(master.device());
+  TORCH_CHECK(off % 8 == 0 && n % 8 == 0, "flat ranges must be multiples of 8 elements");
+  SgdHyper h = hyper(lr, momentum, dampening, wd, nesterov, first);
+  B200_CUDA_OK(b200_sgd_local(master.data_ptr<float>() + off, mom.data_ptr<float>() + off, grad.data_ptr<float>() + off,
+                              w16.has_value() ? (void*)(reinterpret_cast<__nv_bfloat16*>(w16->data_ptr()) + off) : nullptr, n, &h,
+                              (float)grad_scale, zero_grad, cur_stream()));
+}
+void cast_bf16(const at::Tensor& src, at::Tensor& dst) {
+  c10::cuda::CUDAGuard guard(src.device());
+  TORCH_CHECK(src.numel() % 8 == 0 && src.numel() == dst.numel(), "cast_bf16: numel % 8");
+  B200_CUDA_OK(b200_cast_bf16(src.data_ptr<float>(), dst.data_ptr(), src.numel(), cur_stream()));
+}
+
+struct CommState {
+  int world = 1, rank = 0, slot_base = 0;
+  std::vector<int64_t> signal_pads, stage, w16;
+  int64_t mc_stage = 0, mc_w16 = 0, local_counter = 0, local_release = 0;
+  uint32_t epoch = 0;
+  CommCtx make() const {
+    CommCtx c{};
+    c.world = world; c.rank = rank; c.slot_base = slot_base;
+    TORCH_CHECK(world <= kCommMaxPeers && (int)signal_pads.size() == world && (int)stage.size() == world && (int)w16.size() == world, "bad comm state");
+    for (int i = 0; i < world; ++i) {
+      c.signal_pads[i] = reinterpret_cast<uint32_t*>(signal_pads[i]);
+      c.stage[i] = reinterpret_cast<__nv_bfloat16*>(stage[i]);
+      c.w16[i] = reinterpret_cast<__nv_bfloat16*>(w16[i]);
+    }
+    c.mc_stage = reinterpret_cast<__nv_bfloat16*>(mc_stage);
+    c.mc_w16 = reinterpret_cast<__nv_bfloat16*>(mc_w16);
+    c.local_counter = reinterpret_cast<int*>(local_counter);
+    c.local_release = reinterpret_cast<uint32_t*>(local_release);
+    return c;
+  }
+};
+
+void allreduce_sgd(CommState* cs, at::Tensor& master, at::Tensor& mom, at::Tensor& grad, int64_t off, int64_t n, double lr,
+                   double momentum, double dampening, double wd, bool nesterov, bool first, bool one_shot, int64_t grid) {
+  c10::cuda::CUDAGuard guard(master.device());
+  TORCH_CHECK(off % 8 == 0 && n % 8 == 0, "bucket ranges must be multiples of 8 elements");
+  AllreduceSgdParams p{};
+  p.comm = cs->make();
+  p.master = master.data_ptr<float>(); p.mom = mom.data_ptr<float>(); p.grad = grad.data_ptr<float>();
+  p.off8 = off / 8; p.n8 = n / 8;
+  p.hyper = hyper(lr, momentum, dampening, wd, nesterov, first);
+  p.epoch = cs->epoch; cs->epoch += 2;
+  p.one_shot = one_shot;
+  B200_CUDA_OK(b200_allreduce_sgd(&p, (int)std::max<int64_t>(1, std::min<int64_t>(grid, num_sms())), cur_stream()));
+}
+void rank_barrier(CommState* cs) {
+  CommCtx c = cs->make();
+  cs->epoch += 1;
+  B200_CUDA_OK(b200_rank_barrier(&c, cs->epoch, cur_stream()));
+}
+
+}  // namespace
+
+PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
+  m.doc() = "distribuuuu_b200 sm_100a kernels";
+  m.def("conv_fprop", &conv_fprop, "tcgen05 implicit-GEMM convolution forward (NHWC bf16)");
+  m.def("conv_dgrad", &conv_dgrad, "tcgen05 implicit-GEMM data gradient (stride 1)");
+  m.def("conv_wgrad", &conv_wgrad, "tcgen05 split-K weight gradient (fp32 accumulate)");
+  py::class_<PeerState>(m, "PeerState")
+      .def(py::init<>())
+      .def_readwrite("world", &PeerState::world).def_readwrite("rank", &PeerState::rank)
+      .def_readwrite("slot_base", &PeerState::slot_base).def_readwrite("signal_pads", &PeerState::signal_pads)
+      .def_readwrite("sym_bufs", &PeerState::sym_bufs).def_readwrite("ticket", &PeerState::ticket)
+      .def_readwrite("epoch", &PeerState::epoch);
+  py::class_<CommState>(m, "CommState")
+      .def(py::init<>())
+      .def_readwrite("world", &CommState::world).def_readwrite("rank", &CommState::rank)
+      .def_readwrite("slot_base", &CommState::slot_base).def_readwrite("signal_pads", &CommState::signal_pads)
+      .def_readwrite("stage", &CommState::stage).def_readwrite("w16", &CommState::w16)
+      .def_readwrite("mc_stage", &CommState::mc_stage).def_readwrite("mc_w16", &CommState::mc_w16)
+      .def_readwrite("local_counter", &CommState::local_counter).def_readwrite("local_release", &CommState::local_release)
+      .def_readwrite("epoch", &CommState::epoch);
+  m.def("bn_apply", &bn_apply);
+  m.def("bn_stats", &bn_stats);
+  m.def("bn_backward", &bn_backward);
+  m.def("maxpool_fwd", &maxpool_fwd);
+  m.def("maxpool_bwd", &maxpool_bwd);
+  m.def("gap_fwd", &gap_fwd);
+  m.def("gap_bwd", &gap_bwd);
+  m.def("avgpool2_fwd", &avgpool2_fwd);
+  m.def("avgpool2_bwd", &avgpool2_bwd);
+  m.def("ce_topk", &ce_topk);
+  m.def("nchw_to_nhwc", &nchw_to_nhwc);
+  m.def("stem_im2col", &stem_im2col);
+  m.def("pad_rows", &pad_rows);
+  m.def("unpad_add", &unpad_add);
+  m.def("sgd_local", &sgd_local);
+  m.def("cast_bf16", &cast_bf16);
+  m.def("allreduce_sgd", &allreduce_sgd);
+  m.def("rank_barrier", &rank_barrier);
+}

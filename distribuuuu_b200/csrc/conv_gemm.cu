@@ -1,0 +1,329 @@
+// Implicit-GEMM convolution / GEMM for sm_100a: TMA (tiled + im2col) -> swizzled smem -> tcgen05.mma with
+// fp32 accumulators in TMEM -> tcgen05.ld epilogue.  One persistent, warp-specialised kernel covers
+//   fprop : Y[M=pixels, N=Cout]  = sum_taps  X_tap[M, Cin]   * W_tap[Cout, Cin]^T      (+ BN statistics / bias)
+//   dgrad : dX[M=pixels, N=Cin]  = sum_taps dY_tap[M, Cout]  * W_flip(tap)[Cout, Cin]
+//   wgrad : dW[M=Cout, tap, N=Cin] += sum_pixels dY[pix, Cout]^T * X_tap[pix, Cin]     (split-K, fp32 red.add)
+// Activations are NHWC bf16, weights are [Cout][R][S][Cin] bf16 (physical layout of a channels_last OIHW tensor).
+//
+// Replaces what the reference reaches through cuDNN/cuBLAS (reference resnet.py:36-54 convs, :211 fc; SURVEY G1-G3,G10).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
+// (TMEM lane quarter = warp_idx % 4).  smem ring of kStages {A 128x64, B BNx64} bf16 tiles; TMEM holds two
+// accumulator stages of BN fp32 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "conv_gemm.h"
+
+namespace b200 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;                       // reduction elements per smem stage (128 bytes of bf16)
+constexpr int kABytes = BM * BK * 2;         // 16 KB
+constexpr int kBoxBytes = 64 * BK * 2;       // one 64x64 MN-major box = 8 KB
+constexpr int kNumThreads = 192;
+constexpr int kEpiThreads = 128;
+
+template <int BN>
+struct Cfg {
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;  // two accumulator stages; 128/256/512 are all legal allocations
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+struct PixelCoord { int w, h, n; };
+
+__device__ __forceinline__ PixelCoord decode_pixel(const ConvGemmParams& p, int pix) {
+  // linear output-pixel index -> base (w, h, n) coordinate of the im2col traversal
+  int pq = p.im_P * p.im_Q;
+  int n = pix / pq;
+  int rem = pix - n * pq;
+  int ph = rem / p.im_Q;
+  int q = rem - ph * p.im_Q;
+  return {q * p.im_stride + p.im_low_w, ph * p.im_stride + p.im_low_h, n};
+}
+
+struct WorkItem { int m0, n0, nb, tap, it_begin, it_end; };
+
+__device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn) {
+  WorkItem w;
+  if (p.kind != KIND_WGRAD) {
+    int nb = item % p.n_blocks;
+    int mb = item / p.n_blocks;
+    w.m0 = mb * BM; w.n0 = nb * bn; w.nb = nb; w.tap = 0;
+    w.it_begin = 0; w.it_end = p.taps * p.kb_per_tap;
+  } else {
+    int split = item % p.splits; int rest = item / p.splits;
+    int tap = rest % p.taps; rest /= p.taps;
+    int nb = rest % p.n_blocks; int mb = rest / p.n_blocks;
+    w.m0 = mb * BM; w.n0 = nb * bn; w.nb = nb; w.tap = tap;
+    w.it_begin = (int)(((long long)p.k_blocks_total * split) / p.splits);
+    w.it_end = (int)(((long long)p.k_blocks_total * (split + 1)) / p.splits);
+  }
+  return w;
+}
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(kNumThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                 const __grid_constant__ ConvGemmParams p) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128B swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + C::kStages * kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint64_t* full_bar = bars;                       // [kStages] TMA -> MMA
+  uint64_t* empty_bar = bars + C::kStages;         // [kStages] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * C::kStages;     // [2] MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;            // [2] epilogue -> MMA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+    for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiThreads); }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(smem_u32(tmem_ptr), C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const WorkItem w = decode_item(p, item, BN);
+        PixelCoord pa{0, 0, 0};
+        if (p.kind != KIND_WGRAD && p.a_im2col) pa = decode_pixel(p, w.m0);
+        for (int it = w.it_begin; it < w.it_end; ++it) {
+          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[stage]);
+          const uint32_t dst_a = smem_u32(smem_a + stage * kABytes);
+          const uint32_t dst_b = smem_u32(smem_b + stage * C::kBBytes);
+          mbar_expect_tx(bar, C::kStageBytes);
+          if (p.kind != KIND_WGRAD) {
+            const int tap = it / p.kb_per_tap;
+            const int kb = it - tap * p.kb_per_tap;
+            const int r = tap / p.S, s = tap - r * p.S;
+            if (p.a_im2col)
+              tma_load_im2col_4d(dst_a, &map_a, bar, kb * BK, pa.w, pa.h, pa.n, (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+            else
+              tma_load_3d(dst_a, &map_a, bar, kb * BK, 0, w.m0);
+            const int btap = p.b_flip_taps ? (p.taps - 1 - tap) : tap;
+            if (p.b_nbox == 1) {
+              tma_load_3d(dst_b, &map_b, bar, kb * BK, btap, w.n0);          // K-major weights [N][tap][K]
+            } else {
+              for (int j = 0; j < p.b_nbox; ++j)                              // MN-major weights [K][tap][N]
+                tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + 64 * j, btap, kb * BK);
+            }
+          } else {
+            const int k0 = it * BK;  // first reduction pixel of this block
+            for (int j = 0; j < p.a_nbox; ++j) tma_load_3d(dst_a + j * kBoxBytes, &map_a, bar, w.m0 + 64 * j, 0, k0);
+            if (p.b_im2col) {
+              const PixelCoord pb = decode_pixel(p, k0);
+              const int r = w.tap / p.S, s = w.tap - r * p.S;
+              for (int j = 0; j < p.b_nbox; ++j)
+                tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + 64 * j, pb.w, pb.h, pb.n,
+                                   (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+            } else {
+              for (int j = 0; j < p.b_nbox; ++j) tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + 64 * j, 0, k0);
+            }
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const WorkItem w = decode_item(p, item, BN);
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);   // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int it = w.it_begin; it < w.it_end; ++it) {
+          mbar_wait(smem_u32(&full_bar[stage]), phase);          // TMA bytes have landed
+          tc_fence_after();
+          const uint64_t a_desc = p.a_desc_hi | (uint64_t)((smem_u32(smem_a + stage * kABytes) >> 4) & 0x3fff);
+          const uint64_t b_desc = p.b_desc_hi | (uint64_t)((smem_u32(smem_b + stage * C::kBBytes) >> 4) & 0x3fff);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, a_desc + (uint64_t)(k * p.a_kstep16), b_desc + (uint64_t)(k * p.b_kstep16), p.idesc,
+                      (it > w.it_begin || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when the MMAs retire
+          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(smem_u32(&tmem_full[acc]));                   // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
+    const int row_in_tile = quarter * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    float st_sum[BN / 32], st_sq[BN / 32];
+#pragma unroll
+    for (int c = 0; c < BN / 32; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
+    int st_nb = -1;
+    const bool want_stats = (EPI == EPI_BF16) && (p.stats != nullptr);
+
+    auto flush_stats = [&](int nb) {
+      if (nb < 0) return;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col = nb * BN + c * 32 + lane;
+        if (col < p.N) {
+          atomicAdd(p.stats + col, st_sum[c]);
+          atomicAdd(p.stats + p.N + col, st_sq[c]);
+        }
+        st_sum[c] = 0.f; st_sq[c] = 0.f;
+      }
+    };
+
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+      const WorkItem w = decode_item(p, item, BN);
+      if (want_stats && w.nb != st_nb) { flush_stats(st_nb); st_nb = w.nb; }
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      const int row = w.m0 + row_in_tile;
+      const bool row_ok = row < p.M;
+      const bool has_k = w.it_end > w.it_begin;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        const int col0 = w.n0 + c * 32;
+        if (!has_k) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+        if constexpr (EPI == EPI_BF16) {
+          if (p.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              const float b = (col < p.N) ? __ldg(p.bias + col) : 0.f;
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
+            }
+          }
+          if (row_ok && col0 < p.N) {
+            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
+            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int g = 0; g < 4; ++g) {
+                uint4 pk;
+                pk.x = pack_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
+                pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+                pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+                pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+                reinterpret_cast<uint4*>(dst)[g] = pk;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(__uint_as_float(v[j]));
+            }
+          }
+          if (want_stats) {
+            // statistics of the values the next layer will actually read (bf16-rounded); rows past M are zero
+            float s1[32], s2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float f = row_ok ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))) : 0.f;
+              s1[j] = f; s2[j] = f * f;
+            }
+            // butterfly transpose-reduce: afterwards lane l holds the column-(c*32+l) sum over the warp's 32 rows
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) {
+              const bool upper = (lane & off) != 0;
+#pragma unroll
+              for (int i = 0; i < off; ++i) {
+                const float send1 = upper ? s1[i] : s1[i + off];
+                const float keep1 = upper ? s1[i + off] : s1[i];
+                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
+                const float send2 = upper ? s2[i] : s2[i + off];
+                const float keep2 = upper ? s2[i + off] : s2[i];
+                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
+              }
+            }
+            st_sum[c] += s1[0];
+            st_sq[c] += s2[0];
+          }
+        } else {  // EPI_F32_RED: split-K partial sums into fp32 dW[M][taps][N]
+          if (row_ok && col0 < p.N && has_k) {
+            float* dst = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + (long long)w.tap * p.tap_stride + col0;
+            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + 4 * g),
+                             "f"(__uint_as_float(v[4 * g + 0])), "f"(__uint_as_float(v[4 * g + 1])),
+                             "f"(__uint_as_float(v[4 * g + 2])), "f"(__uint_as_float(v[4 * g + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (col0 + j < p.N) atomicAdd(dst + j, __uint_as_float(v[j]));
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(smem_u32(&tmem_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (want_stats) flush_stats(st_nb);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+template <int BN, int EPI>
+static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const ConvGemmParams& p, int grid,
+                              cudaStream_t stream) {
+  using C = Cfg<BN>;
+  auto kern = conv_gemm_kernel<BN, EPI>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ma, mb, p);
+  return cudaGetLastError();
+}
+
+}  // namespace b200
+
+extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap* map_b, const ConvGemmParams* p,
+                                     int bn, int grid, cudaStream_t stream) {
+  using namespace b200;
+  cudaError_t e = cudaErrorInvalidValue;
+  if (p->epi == EPI_BF16) {
+    if (bn == 64) e = launch_one<64, EPI_BF16>(*map_a, *map_b, *p, grid, stream);
+    else if (bn == 128) e = launch_one<128, EPI_BF16>(*map_a, *map_b, *p, grid, stream);
+    else if (bn == 256) e = launch_one<256, EPI_BF16>(*map_a, *map_b, *p, grid, stream);
+  } else {
+    if (bn == 64) e = launch_one<64, EPI_F32_RED>(*map_a, *map_b, *p, grid, stream);
+    else if (bn == 128) e = launch_one<128, EPI_F32_RED>(*map_a, *map_b, *p, grid, stream);
+    else if (bn == 256) e = launch_one<256, EPI_F32_RED>(*map_a, *map_b, *p, grid, stream);
+  }
+  return (int)e;
+}

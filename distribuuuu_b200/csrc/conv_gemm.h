@@ -1,0 +1,37 @@
+// Host/device shared parameter block of the tcgen05 implicit-GEMM kernel (conv_gemm.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum ConvGemmKind { KIND_FPROP = 0, KIND_DGRAD = 1, KIND_WGRAD = 2 };
+enum ConvGemmEpi { EPI_BF16 = 0, EPI_F32_RED = 1 };
+
+struct ConvGemmParams {
+  int kind;            // ConvGemmKind
+  int epi;             // ConvGemmEpi
+  int M, N;            // GEMM extents used for masking (rows / columns of the output)
+  int m_blocks, n_blocks;
+  int taps, S;         // R*S filter taps, filter width
+  int kb_per_tap;      // fprop/dgrad: ceil(K_channels / 64)
+  int dil;
+  int a_im2col, a_nbox;
+  uint32_t a_kstep16;  // smem-descriptor start-address advance per UMMA_K=16 step (16-byte units)
+  uint64_t a_desc_hi;
+  int b_im2col, b_nbox;
+  uint32_t b_kstep16;
+  uint64_t b_desc_hi;
+  int b_flip_taps;
+  uint32_t idesc;
+  int im_P, im_Q, im_stride, im_low_w, im_low_h;  // pixel enumeration of the im2col operand
+  int k_blocks_total, splits;                     // wgrad: 64-pixel reduction blocks and split-K factor
+  void* out;
+  long long ldo;        // output row pitch in elements
+  long long tap_stride; // wgrad: element offset between taps inside one output row
+  float* stats;         // optional [2][N] per-column sum / sum of squares (fp32, atomically accumulated)
+  const float* bias;    // optional [N]
+  int total_items;
+};
+
+extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap* map_b, const ConvGemmParams* p,
+                                     int bn, int grid, cudaStream_t stream);

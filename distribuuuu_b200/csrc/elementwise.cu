@@ -1,0 +1,686 @@
+// Memory-bound NHWC bf16 kernels: BatchNorm (apply / backward, with optional peer-memory SyncBN reduction),
+// pooling, fused softmax-cross-entropy-topk, input layout conversion, stem im2col.
+// Replaces the ATen/cuDNN calls the reference makes for BN/ReLU/add/pool/CE/topk.
+// All kernels process 8 channels (one 16-byte vector) per thread and keep per-channel state in registers.
+#include "common.cuh"
+#include "elementwise.h"
+
+namespace b200 {
+
+constexpr int VEC = 8;
+
+struct alignas(16) BF8 { __nv_bfloat162 v[4]; };
+
+__device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
+  BF8 raw = *reinterpret_cast<const BF8*>(p);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(raw.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
+  BF8 raw;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) raw.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  *reinterpret_cast<BF8*>(p) = raw;
+}
+__device__ __forceinline__ float act_fwd(float z, int act) {
+  if (act == ACT_RELU) return fmaxf(z, 0.f);
+  if (act == ACT_SILU) return z / (1.f + __expf(-z));
+  return z;
+}
+__device__ __forceinline__ float act_bwd(float z, int act) {  // d act / d z
+  if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (act == ACT_SILU) { float s = 1.f / (1.f + __expf(-z)); return s * (1.f + z * (1.f - s)); }
+  return 1.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Peer exchange used by SyncBN: every rank publishes "my statistics for exchange #epoch are final" to all peers'
+// signal pads, then waits until every peer has done the same.  Statistics are then read straight out of the peers'
+// symmetric buffers (P2P loads over NVLink) -- no NCCL call, no staging copy.  
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__device__ void peer_exchange_wait(const PeerCtx& pc) {
+  // One CTA (the first to take a ticket) announces; every CTA waits.
+  __shared__ int s_ticket;
+  if (threadIdx.x == 0 && threadIdx.y == 0) s_ticket = atomicAdd(pc.ticket, 1);
+  __syncthreads();
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  if (s_ticket == 0 && tid < pc.world) {
+    __threadfence_system();
+    st_release_sys(pc.signal_pads[tid] + pc.slot_base + pc.rank, pc.epoch);
+  }
+  if (tid < pc.world) {
+    const uint32_t* flag = pc.signal_pads[pc.rank] + pc.slot_base + tid;
+    long long t0 = clock64();
+    while ((int)(ld_acquire_sys(flag) - pc.epoch) < 0) {
+      if (clock64() - t0 > B200_SPIN_LIMIT_CYCLES * 4) {
+        printf("b200: peer exchange timed out (rank %d waiting for %d, epoch %u)\n", pc.rank, tid, pc.epoch);
+        __trap();
+      }
+    }
+  }
+  __syncthreads();
+  // last CTA out resets the ticket for the next launch that uses it
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    int done = atomicAdd(pc.ticket + 1, 1);
+    if (done == (int)(gridDim.x * gridDim.y) - 1) { pc.ticket[0] = 0; pc.ticket[1] = 0; __threadfence(); }
+  }
+}
+
+// Sum the [2][C] statistics of this thread's 8 channels over all ranks (local only when world == 1).
+__device__ __forceinline__ void gather_stats(const PeerCtx& pc, const float* local, long long sym_offset, int C, int c0,
+                                             float (&s0)[8], float (&s1)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
+  if (pc.world <= 1) {
+    const float4* a = reinterpret_cast<const float4*>(local + c0);
+    const float4* b = reinterpret_cast<const float4*>(local + C + c0);
+    float4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    s0[0] = a0.x; s0[1] = a0.y; s0[2] = a0.z; s0[3] = a0.w; s0[4] = a1.x; s0[5] = a1.y; s0[6] = a1.z; s0[7] = a1.w;
+    s1[0] = b0.x; s1[1] = b0.y; s1[2] = b0.z; s1[3] = b0.w; s1[4] = b1.x; s1[5] = b1.y; s1[6] = b1.z; s1[7] = b1.w;
+    return;
+  }
+  for (int r = 0; r < pc.world; ++r) {
+    const float* base = pc.sym_bufs[r] + sym_offset;  // peer pointer: this is a load over NVLink for r != rank
+    const float4* a = reinterpret_cast<const float4*>(base + c0);
+    const float4* b = reinterpret_cast<const float4*>(base + C + c0);
+    float4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+    s0[0] += a0.x; s0[1] += a0.y; s0[2] += a0.z; s0[3] += a0.w; s0[4] += a1.x; s0[5] += a1.y; s0[6] += a1.z; s0[7] += a1.w;
+    s1[0] += b0.x; s1[1] += b0.y; s1[2] += b0.z; s1[3] += b0.w; s1[4] += b1.x; s1[5] += b1.y; s1[6] += b1.z; s1[7] += b1.w;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN forward: finalize statistics (optionally across ranks), update running stats, normalise + affine
+// (+ residual) + activation in ONE pass over the conv output.
+// grid: (ceil(C/8 / blockDim.x), row_chunks); block: (cvx, rows_per_block)
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_apply_kernel(BnApplyParams p) {
+  if (p.peer.world > 1 && p.training) peer_exchange_wait(p.peer);
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  if (c0 >= p.C) return;
+  float scale[8], shift[8];
+  if (p.training) {
+    float s0[8], s1[8];
+    gather_stats(p.peer, p.stats, p.sym_offset, p.C, c0, s0, s1);
+    const float inv_n = 1.f / p.count;
+    const bool writer = (blockIdx.y == 0 && threadIdx.y == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float mean = s0[i] * inv_n;
+      const float var = fmaxf(s1[i] * inv_n - mean * mean, 0.f);
+      const float invstd = rsqrtf(var + p.eps);
+      const float g = p.gamma ? p.gamma[c0 + i] : 1.f;
+      const float b = p.beta ? p.beta[c0 + i] : 0.f;
+      scale[i] = g * invstd;
+      shift[i] = b - mean * scale[i];
+      if (writer) {
+        p.save_mean[c0 + i] = mean;
+        p.save_invstd[c0 + i] = invstd;
+        if (p.running_mean) {
+          const float unbiased = var * (p.count / fmaxf(p.count - 1.f, 1.f));
+          p.running_mean[c0 + i] = (1.f - p.momentum) * p.running_mean[c0 + i] + p.momentum * mean;
+          p.running_var[c0 + i] = (1.f - p.momentum) * p.running_var[c0 + i] + p.momentum * unbiased;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float invstd = rsqrtf(p.running_var[c0 + i] + p.eps);
+      const float g = p.gamma ? p.gamma[c0 + i] : 1.f;
+      const float b = p.beta ? p.beta[c0 + i] : 0.f;
+      scale[i] = g * invstd;
+      shift[i] = b - p.running_mean[c0 + i] * scale[i];
+    }
+  }
+  for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += (long long)gridDim.y * blockDim.y) {
+    float x[8];
+    load8(p.y + row * p.ldy + c0, x);
+    if (p.residual) {
+      float r[8];
+      load8(p.residual + row * p.ldr + c0, r);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]) + r[i], p.act);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]), p.act);
+    }
+    store8(p.out + row * p.ldo + c0, x);
+  }
+}
+
+// Per-channel sum / sum-of-squares of a [rows][C] bf16 tensor (used when the producer is not our conv kernel).
+__global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long rows, int C, long long ldy, float* stats) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
+  if (c0 < C) {
+    for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.y * blockDim.y) {
+      float x[8];
+      load8(y + row * ldy + c0, x);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += x[i]; b[i] = fmaf(x[i], x[i], b[i]); }
+    }
+  }
+  // reduce over threadIdx.y through shared memory
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  extern __shared__ float dyn[];
+  float* sm = dyn;  // [blockDim.y][blockDim.x][16]
+  float* mine = sm + ((size_t)ty * blockDim.x + tx) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = a[i]; mine[8 + i] = b[i]; }
+  __syncthreads();
+  if (ty == 0 && c0 < C) {
+    for (int yy = 1; yy < blockDim.y; ++yy) {
+      const float* o = sm + ((size_t)yy * blockDim.x + tx) * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += o[i]; b[i] += o[8 + i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(stats + c0 + i, a[i]); atomicAdd(stats + C + c0 + i, b[i]); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BN backward, pass 1: per-channel sum(dz) and sum(dz * xhat), dz = dout * act'(z), z recomputed from y.
+// ------------------------------------------------------------------------------------------------
+__global__ void bn_bwd_reduce_kernel(BnBwdParams p) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
+  if (c0 < p.C) {
+    float mean[8], invstd[8], g[8], be[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = p.save_mean[c0 + i]; invstd[i] = p.save_invstd[c0 + i];
+      g[i] = p.gamma ? p.gamma[c0 + i] : 1.f; be[i] = p.beta ? p.beta[c0 + i] : 0.f;
+    }
+    for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += (long long)gridDim.y * blockDim.y) {
+      float y[8], d[8];
+      load8(p.y + row * p.ldy + c0, y);
+      load8(p.dout + row * p.ldd + c0, d);
+      if (p.act != ACT_NONE) {
+        if (p.residual) {
+          float r[8];
+          load8(p.residual + row * p.ldr + c0, r);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (y[i] - mean[i]) * invstd[i];
+            d[i] *= act_bwd(fmaf(xh, g[i], be[i]) + r[i], p.act);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float xh = (y[i] - mean[i]) * invstd[i];
+            d[i] *= act_bwd(fmaf(xh, g[i], be[i]), p.act);
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xh = (y[i] - mean[i]) * invstd[i];
+        a[i] += d[i];
+        b[i] = fmaf(d[i], xh, b[i]);
+      }
+    }
+  }
+  extern __shared__ float dyn[];
+  float* mine = dyn + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 16;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { mine[i] = a[i]; mine[8 + i] = b[i]; }
+  __syncthreads();
+  if (threadIdx.y == 0 && c0 < p.C) {
+    for (int yy = 1; yy < blockDim.y; ++yy) {
+      const float* o = dyn + ((size_t)yy * blockDim.x + threadIdx.x) * 16;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { a[i] += o[i]; b[i] += o[8 + i]; }
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(p.sums + c0 + i, a[i]); atomicAdd(p.sums + p.C + c0 + i, b[i]); }
+  }
+}
+
+// BN backward, pass 2: dy = (dz - mean(dz) - xhat * mean(dz*xhat)) * gamma * invstd (means over all ranks for SyncBN);
+// also emits d(residual) = dz and the local dgamma / dbeta.
+__global__ void bn_bwd_apply_kernel(BnBwdParams p) {
+  if (p.peer.world > 1) peer_exchange_wait(p.peer);
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  if (c0 >= p.C) return;
+  float mean[8], invstd[8], g[8], be[8], m_dz[8], m_dzx[8];
+  {
+    float s0[8], s1[8];
+    gather_stats(p.peer, p.sums, p.sym_offset, p.C, c0, s0, s1);
+    const float inv_n = 1.f / p.count;
+    const bool writer = (blockIdx.y == 0 && threadIdx.y == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      mean[i] = p.save_mean[c0 + i]; invstd[i] = p.save_invstd[c0 + i];
+      g[i] = p.gamma ? p.gamma[c0 + i] : 1.f; be[i] = p.beta ? p.beta[c0 + i] : 0.f;
+      m_dz[i] = s0[i] * inv_n; m_dzx[i] = s1[i] * inv_n;
+    }
+    if (writer && p.dgamma) {
+      // parameter gradients use the LOCAL sums (the gradient all-reduce averages them afterwards, as DDP does)
+      const float* loc = p.sums;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        p.dgamma[c0 + i] += loc[p.C + c0 + i];
+        p.dbeta[c0 + i] += loc[c0 + i];
+      }
+    }
+  }
+  for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += (long long)gridDim.y * blockDim.y) {
+    float y[8], d[8];
+    load8(p.y + row * p.ldy + c0, y);
+    load8(p.dout + row * p.ldd + c0, d);
+    float xh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) xh[i] = (y[i] - mean[i]) * invstd[i];
+    if (p.act != ACT_NONE) {
+      if (p.residual) {
+        float r[8];
+        load8(p.residual + row * p.ldr + c0, r);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] *= act_bwd(fmaf(xh[i], g[i], be[i]) + r[i], p.act);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[i] *= act_bwd(fmaf(xh[i], g[i], be[i]), p.act);
+      }
+    }
+    if (p.dresidual) store8(p.dresidual + row * p.ldr + c0, d);
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = (d[i] - m_dz[i] - xh[i] * m_dzx[i]) * (g[i] * invstd[i]);
+    store8(p.dy + row * p.ldy + c0, o);
+  }
+}
+
+// Plain activation backward when there is no BN (conv + bias + act): dz = dout * act'(z) with z the stored output.
+// ------------------------------------------------------------------------------------------------
+// Max-pool 3x3 / stride 2 / pad 1 (NHWC), forward stores the argmax tap (0..8) for an atomic-free backward.
+// ------------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+                                   uint8_t* __restrict__ argmax, int N, int H, int W, int C, int P, int Q, int k,
+                                   int stride, int pad) {
+  const long long total = (long long)N * P * Q * (C / VEC);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = idx % (C / VEC);
+    long long pix = idx / (C / VEC);
+    const int q = pix % Q; pix /= Q;
+    const int ph = pix % P; const int n = pix / P;
+    float best[8]; int arg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; arg[i] = 0; }
+    for (int r = 0; r < k; ++r) {
+      const int h = ph * stride - pad + r;
+      if (h < 0 || h >= H) continue;
+      for (int s = 0; s < k; ++s) {
+        const int w = q * stride - pad + s;
+        if (w < 0 || w >= W) continue;
+        float v[8];
+        load8(x + (((long long)n * H + h) * W + w) * C + cv * VEC, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; arg[i] = r * k + s; }
+      }
+    }
+    const long long o = (((long long)n * P + ph) * Q + q) * C + cv * VEC;
+    store8(out + o, best);
+    if (argmax) {
+      uint2 packed;
+      packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(argmax + o) = packed;
+    }
+  }
+}
+
+__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
+                                   __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k,
+                                   int stride, int pad) {
+  // gather form: each input pixel looks at the (<= ceil(k/stride)^2) windows that contain it
+  const long long total = (long long)N * H * W * (C / VEC);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = idx % (C / VEC);
+    long long pix = idx / (C / VEC);
+    const int w = pix % W; pix /= W;
+    const int h = pix % H; const int n = pix / H;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int ph = max(0, (h + pad - k + stride) / stride); ph < P && ph * stride - pad <= h; ++ph) {
+      const int r = h - (ph * stride - pad);
+      if (r < 0 || r >= k) continue;
+      for (int q = max(0, (w + pad - k + stride) / stride); q < Q && q * stride - pad <= w; ++q) {
+        const int s = w - (q * stride - pad);
+        if (s < 0 || s >= k) continue;
+        const long long o = (((long long)n * P + ph) * Q + q) * C + cv * VEC;
+        const uint2 packed = *reinterpret_cast<const uint2*>(argmax + o);
+        float d[8];
+        load8(dout + o, d);
+        const int tap = r * k + s;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int a = ((i < 4 ? packed.x : packed.y) >> (8 * (i & 3))) & 0xff;
+          if (a == tap) acc[i] += d[i];
+        }
+      }
+    }
+    store8(dx + (((long long)n * H + h) * W + w) * C + cv * VEC, acc);
+  }
+}
+
+// Global average pool [N][HW][C] -> [N][C] and its backward (broadcast / HW).
+__global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int HW, int C) {
+  const int total = N * (C / VEC);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int cv = idx % (C / VEC), n = idx / (C / VEC);
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int t = 0; t < HW; ++t) {
+      float v[8];
+      load8(x + ((long long)n * HW + t) * C + cv * VEC, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+    const float inv = 1.f / HW;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    store8(out + (long long)n * C + cv * VEC, acc);
+  }
+}
+__global__ void gap_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int N, int HW, int C) {
+  const long long total = (long long)N * HW * (C / VEC);
+  const float inv = 1.f / HW;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = idx % (C / VEC);
+    const int n = (idx / (C / VEC)) / HW;
+    float v[8];
+    load8(dout + (long long)n * C + cv * VEC, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= inv;
+    store8(dx + idx * VEC, v);
+  }
+}
+
+// 2x2 / stride-2 average pool (DenseNet transitions, BoTNet stride-2 block).
+__global__ void avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
+  const int P = H / 2, Q = W / 2;
+  const long long total = (long long)N * P * Q * (C / VEC);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = idx % (C / VEC);
+    long long pix = idx / (C / VEC);
+    const int q = pix % Q; pix /= Q;
+    const int ph = pix % P; const int n = pix / P;
+    float acc[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        float v[8];
+        load8(x + (((long long)n * H + 2 * ph + r) * W + 2 * q + s) * C + cv * VEC, v);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += 0.25f * v[i];
+      }
+    store8(out + idx * VEC, acc);
+  }
+}
+__global__ void avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
+  const int P = H / 2, Q = W / 2;
+  const long long total = (long long)N * H * W * (C / VEC);
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int cv = idx % (C / VEC);
+    long long pix = idx / (C / VEC);
+    const int w = pix % W; pix /= W;
+    const int h = pix % H; const int n = pix / H;
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = 0.f;
+    if (h / 2 < P && w / 2 < Q) {
+      load8(dout + (((long long)n * P + h / 2) * Q + w / 2) * C + cv * VEC, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] *= 0.25f;
+    }
+    store8(dx + idx * VEC, v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused softmax cross-entropy + top-1/top-k hit counting + dlogits, one CTA per sample.
+// loss_sum / hits are accumulated atomically; dlogits = (softmax - onehot) * grad_scale.
+// ------------------------------------------------------------------------------------------------
+__global__ void ce_topk_kernel(const __nv_bfloat16* __restrict__ logits, const long long* __restrict__ target,
+                               __nv_bfloat16* __restrict__ dlogits, float* __restrict__ accum /*[3]*/, int ncls,
+                               long long ld, int topk, float grad_scale) {
+  const int row = blockIdx.x;
+  const __nv_bfloat16* lg = logits + (long long)row * ld;
+  const int tgt = (int)target[row];
+  __shared__ float s_red[32];
+  __shared__ float s_bcast[2];
+  float mx = -INFINITY;
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) mx = fmaxf(mx, __bfloat162float(lg[c]));
+  // block max
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float v = threadIdx.x < (blockDim.x >> 5) ? s_red[threadIdx.x] : -INFINITY;
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (threadIdx.x == 0) s_bcast[0] = v;
+  }
+  __syncthreads();
+  mx = s_bcast[0];
+  const float tv = __bfloat162float(lg[tgt]);
+  float sum = 0.f, rank_gt = 0.f;  // rank_gt: number of classes that beat the target (ties broken by lower index)
+  for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+    const float v = __bfloat162float(lg[c]);
+    sum += __expf(v - mx);
+    rank_gt += (v > tv || (v == tv && c < tgt)) ? 1.f : 0.f;
+  }
+  sum = warp_sum(sum); rank_gt = warp_sum(rank_gt);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5] = sum; s_red[16 + (threadIdx.x >> 5)] = rank_gt; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const int nw = blockDim.x >> 5;
+    float a = threadIdx.x < nw ? s_red[threadIdx.x] : 0.f;
+    float b = threadIdx.x < nw ? s_red[16 + threadIdx.x] : 0.f;
+    a = warp_sum(a); b = warp_sum(b);
+    if (threadIdx.x == 0) { s_bcast[0] = a; s_bcast[1] = b; }
+  }
+  __syncthreads();
+  sum = s_bcast[0]; rank_gt = s_bcast[1];
+  const float lse = mx + __logf(sum);
+  if (threadIdx.x == 0) {
+    atomicAdd(accum + 0, lse - tv);
+    if (rank_gt < 0.5f) atomicAdd(accum + 1, 1.f);
+    if (rank_gt < (float)topk - 0.5f) atomicAdd(accum + 2, 1.f);
+  }
+  if (dlogits) {
+    __nv_bfloat16* dl = dlogits + (long long)row * ld;
+    const float inv = 1.f / sum;
+    for (int c = threadIdx.x; c < ncls; c += blockDim.x) {
+      float pr = __expf(__bfloat162float(lg[c]) - mx) * inv;
+      if (c == tgt) pr -= 1.f;
+      dl[c] = __float2bfloat16_rn(pr * grad_scale);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Input staging: NCHW fp32 (what the data loader / reference produces) -> NHWC bf16, and the explicit im2col of
+// the 7x7/2 stem (Cin=3 makes K=147: the GEMM runs on [pixels][160] patches, columns 147..159 are zero).
+// ------------------------------------------------------------------------------------------------
+__global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int C, int H, int W) {
+  const long long total = (long long)N * H * W * C;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = idx % C;
+    long long pix = idx / C;
+    const int w = pix % W; pix /= W;
+    const int h = pix % H; const int n = pix / H;
+    out[idx] = __float2bfloat16_rn(x[(((long long)n * C + c) * H + h) * W + w]);
+  }
+}
+
+__global__ void stem_im2col_kernel(const float* __restrict__ x /*NCHW fp32*/, __nv_bfloat16* __restrict__ patches,
+                                   int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad) {
+  // one thread per (pixel, r): writes S*C contiguous bf16 (row layout [r][s][c], matching weights [Cout][R][S][C])
+  const long long total = (long long)N * P * Q * (R + 1);  // the extra "r == R" slot zero-fills the K padding
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int r = idx % (R + 1);
+    long long pix = idx / (R + 1);
+    __nv_bfloat16* dst = patches + pix * Kpad;
+    if (r == R) {
+      for (int k = R * S * C; k < Kpad; ++k) dst[k] = __float2bfloat16_rn(0.f);
+      continue;
+    }
+    const int q = pix % Q; long long t = pix / Q;
+    const int ph = t % P; const int n = t / P;
+    const int h = ph * stride - pad + r;
+    dst += r * S * C;
+    for (int s = 0; s < S; ++s) {
+      const int w = q * stride - pad + s;
+      const bool ok = (h >= 0 && h < H && w >= 0 && w < W);
+      for (int c = 0; c < C; ++c)
+        dst[s * C + c] = __float2bfloat16_rn(ok ? x[(((long long)n * C + c) * H + h) * W + w] : 0.f);
+    }
+  }
+}
+
+// rows x cols (bf16) -> rows x cols_pad with zero fill; used to give the stem weight a TMA-legal row pitch.
+__global__ void pad_rows_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* __restrict__ dst, int rows, int cols, int cols_pad) {
+  const int total = rows * cols_pad;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx % cols_pad, r = idx / cols_pad;
+    dst[idx] = c < cols ? src[r * cols + c] : __float2bfloat16_rn(0.f);
+  }
+}
+// fp32 [rows][cols_pad] -> accumulate the first `cols` columns into fp32 [rows][cols]
+__global__ void unpad_add_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int cols_pad) {
+  const int total = rows * cols;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+    const int c = idx % cols, r = idx / cols;
+    dst[idx] += src[r * cols_pad + c];
+  }
+}
+
+}  // namespace b200
+
+// ================================================================================================
+// host launchers (C linkage, no torch dependency)
+// ================================================================================================
+using namespace b200;
+
+static inline void bn_launch_dims(int C, long long rows, dim3& grid, dim3& block) {
+  const int cvs = C / VEC;
+  int bx = 1;
+  while (bx < 32 && bx < cvs) bx <<= 1;     // power of two <= 32 covering the channel vectors
+  const int by = 256 / bx;
+  const int gx = (cvs + bx - 1) / bx;
+  long long want = (rows + by - 1) / by;
+  long long cap = (148 * 8 + gx - 1) / gx;   // ~8 CTAs per SM in total
+  int gy = (int)(want < cap ? want : cap);
+  if (gy < 1) gy = 1;
+  grid = dim3(gx, gy);
+  block = dim3(bx, by);
+}
+
+extern "C" int b200_bn_apply(const BnApplyParams* p, cudaStream_t s) {
+  dim3 g, b;
+  bn_launch_dims(p->C, p->rows, g, b);
+  bn_apply_kernel<<<g, b, 0, s>>>(*p);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_bn_stats(const void* y, long long rows, int C, long long ldy, float* stats, cudaStream_t s) {
+  dim3 g, b;
+  bn_launch_dims(C, rows, g, b);
+  bn_stats_kernel<<<g, b, b.x * b.y * 16 * sizeof(float), s>>>((const __nv_bfloat16*)y, rows, C, ldy, stats);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_bn_bwd_reduce(const BnBwdParams* p, cudaStream_t s) {
+  dim3 g, b;
+  bn_launch_dims(p->C, p->rows, g, b);
+  bn_bwd_reduce_kernel<<<g, b, b.x * b.y * 16 * sizeof(float), s>>>(*p);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_bn_bwd_apply(const BnBwdParams* p, cudaStream_t s) {
+  dim3 g, b;
+  bn_launch_dims(p->C, p->rows, g, b);
+  bn_bwd_apply_kernel<<<g, b, 0, s>>>(*p);
+  return (int)cudaGetLastError();
+}
+static inline int ew_grid(long long total, int block) {
+  long long g = (total + block - 1) / block;
+  long long cap = 148 * 16;
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+extern "C" int b200_maxpool_fwd(const void* x, void* out, void* argmax, int N, int H, int W, int C, int P, int Q, int k,
+                                int stride, int pad, cudaStream_t s) {
+  const long long total = (long long)N * P * Q * (C / VEC);
+  maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, (uint8_t*)argmax,
+                                                         N, H, W, C, P, Q, k, stride, pad);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_maxpool_bwd(const void* dout, const void* argmax, void* dx, int N, int H, int W, int C, int P, int Q,
+                                int k, int stride, int pad, cudaStream_t s) {
+  const long long total = (long long)N * H * W * (C / VEC);
+  maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (const uint8_t*)argmax,
+                                                         (__nv_bfloat16*)dx, N, H, W, C, P, Q, k, stride, pad);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_gap_fwd(const void* x, void* out, int N, int HW, int C, cudaStream_t s) {
+  gap_fwd_kernel<<<ew_grid((long long)N * (C / VEC), 128), 128, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, HW, C);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_gap_bwd(const void* dout, void* dx, int N, int HW, int C, cudaStream_t s) {
+  gap_bwd_kernel<<<ew_grid((long long)N * HW * (C / VEC), 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, HW, C);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_avgpool2_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s) {
+  avgpool2_fwd_kernel<<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / VEC), 256), 256, 0, s>>>(
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, C);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_avgpool2_bwd(const void* dout, void* dx, int N, int H, int W, int C, cudaStream_t s) {
+  avgpool2_bwd_kernel<<<ew_grid((long long)N * H * W * (C / VEC), 256), 256, 0, s>>>(
+      (const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, H, W, C);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_ce_topk(const void* logits, const long long* target, void* dlogits, float* accum, int rows, int ncls,
+                            long long ld, int topk, float grad_scale, cudaStream_t s) {
+  ce_topk_kernel<<<rows, 256, 0, s>>>((const __nv_bfloat16*)logits, target, (__nv_bfloat16*)dlogits, accum, ncls, ld, topk, grad_scale);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, cudaStream_t s) {
+  nchw_to_nhwc_bf16_kernel<<<ew_grid((long long)N * C * H * W, 256), 256, 0, s>>>(x, (__nv_bfloat16*)out, N, C, H, W);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_stem_im2col(const float* x, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S,
+                                int stride, int pad, int Kpad, cudaStream_t s) {
+  stem_im2col_kernel<<<ew_grid((long long)N * P * Q * (R + 1), 256), 256, 0, s>>>(x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_pad_rows(const void* src, void* dst, int rows, int cols, int cols_pad, cudaStream_t s) {
+  pad_rows_kernel<<<ew_grid((long long)rows * cols_pad, 256), 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, rows, cols, cols_pad);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_unpad_add(const float* src, float* dst, int rows, int cols, int cols_pad, cudaStream_t s) {
+  unpad_add_kernel<<<ew_grid((long long)rows * cols, 256), 256, 0, s>>>(src, dst, rows, cols, cols_pad);
+  return (int)cudaGetLastError();
+}

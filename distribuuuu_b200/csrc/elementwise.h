@@ -1,0 +1,72 @@
+// Parameter blocks of the memory-bound kernels (elementwise.cu), shared with the host bindings.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+enum ActKind { ACT_NONE = 0, ACT_RELU = 1, ACT_SILU = 2 };
+
+constexpr int kMaxPeers = 8;
+
+// Peer-memory context for SyncBN-style statistic exchanges (all pointers are device addresses; peers' buffers
+// are mapped into this process through symmetric memory, so plain loads/stores on them travel over NVLink).
+struct PeerCtx {
+  int world;                        // 1 => purely local
+  int rank;
+  uint32_t epoch;                   // monotonically increasing exchange counter
+  int slot_base;                    // first signal-pad slot used by this exchange stream
+  uint32_t* signal_pads[kMaxPeers]; // signal pad of every rank
+  float* sym_bufs[kMaxPeers];       // statistics buffer of every rank
+  int* ticket;                      // [2] local ints: arrival ticket / departure counter
+};
+
+struct BnApplyParams {
+  const __nv_bfloat16* y; long long ldy;        // conv output [rows][C]
+  const __nv_bfloat16* residual; long long ldr; // optional
+  __nv_bfloat16* out; long long ldo;
+  long long rows; int C;
+  const float* stats;        // local [2][C] sum / sumsq (== sym_bufs[rank] + sym_offset when world > 1)
+  long long sym_offset;      // float offset of this layer's statistics inside the symmetric buffer
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var;
+  float* save_mean; float* save_invstd;
+  float count;               // elements per channel over ALL ranks
+  float eps, momentum;
+  int act, training;
+  PeerCtx peer;
+};
+
+struct BnBwdParams {
+  const __nv_bfloat16* y; long long ldy;
+  const __nv_bfloat16* dout; long long ldd;
+  const __nv_bfloat16* residual; long long ldr;  // forward residual (needed to recompute act'(z)); optional
+  __nv_bfloat16* dy;                              // gradient wrt the conv output (pitch ldy)
+  __nv_bfloat16* dresidual;                       // optional gradient wrt the residual input (pitch ldr)
+  long long rows; int C;
+  float* sums;               // local [2][C]: sum(dz), sum(dz*xhat)
+  long long sym_offset;
+  const float* gamma; const float* beta;
+  const float* save_mean; const float* save_invstd;
+  float* dgamma; float* dbeta; // fp32 gradient slots (accumulated)
+  float count;
+  int act;
+  PeerCtx peer;
+};
+
+extern "C" {
+int b200_bn_apply(const BnApplyParams* p, cudaStream_t s);
+int b200_bn_stats(const void* y, long long rows, int C, long long ldy, float* stats, cudaStream_t s);
+int b200_bn_bwd_reduce(const BnBwdParams* p, cudaStream_t s);
+int b200_bn_bwd_apply(const BnBwdParams* p, cudaStream_t s);
+int b200_maxpool_fwd(const void* x, void* out, void* argmax, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, cudaStream_t s);
+int b200_maxpool_bwd(const void* dout, const void* argmax, void* dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, cudaStream_t s);
+int b200_gap_fwd(const void* x, void* out, int N, int HW, int C, cudaStream_t s);
+int b200_gap_bwd(const void* dout, void* dx, int N, int HW, int C, cudaStream_t s);
+int b200_avgpool2_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s);
+int b200_avgpool2_bwd(const void* dout, void* dx, int N, int H, int W, int C, cudaStream_t s);
+int b200_ce_topk(const void* logits, const long long* target, void* dlogits, float* accum, int rows, int ncls, long long ld, int topk, float grad_scale, cudaStream_t s);
+int b200_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, cudaStream_t s);
+int b200_stem_im2col(const float* x, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad, cudaStream_t s);
+int b200_pad_rows(const void* src, void* dst, int rows, int cols, int cols_pad, cudaStream_t s);
+int b200_unpad_add(const float* src, float* dst, int rows, int cols, int cols_pad, cudaStream_t s);
+}

@@ -1,0 +1,411 @@
+"""Autograd wrappers around the sm_100a kernels (``csrc/``) -- the *native* implementation of
+``ops.functional``.
+
+Conventions on this path: activations are logical ``[N, C, H, W]`` bf16 tensors in
+``channels_last`` memory format (physically NHWC, which is what the kernels index); weights
+come from the engine's flat bf16 buffer as contiguous ``[Cout, R, S, Cin]`` views; weight
+gradients are written by the kernels *directly* into the engine's flat fp32 gradient buffer
+(no ``.grad`` tensors, no bucket copies -- SURVEY G19) and the engine is told when a parameter
+is ready so the fused all-reduce + SGD kernel can start while backward is still running.
+
+Layers the kernels do not cover yet (grouped / depthwise convs, strided dgrad, SE, attention)
+run as plain torch ops on the same bf16 NHWC tensors, with their parameter gradients routed
+into the same flat buffer by a hook (see ``NativeEngine._make_leaf``).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+ACT = {None: 0, "relu": 1, "silu": 2}
+
+
+def _nhwc(x: torch.Tensor) -> torch.Tensor:
+    """Contiguous [N,H,W,C] view (copy only if the tensor is not channels_last already)."""
+    v = x.permute(0, 2, 3, 1)
+    return v if v.is_contiguous() else v.contiguous()
+
+
+def _nchw_view(x_nhwc: torch.Tensor) -> torch.Tensor:
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+class ConvFn(torch.autograd.Function):
+    """Implicit-GEMM convolution (fprop / dgrad / wgrad on tcgen05), optional BN-statistics epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, eng, conv, stats):
+        K = eng.K
+        xh = _nhwc(x)
+        w = eng.w16_krsc(conv.weight)
+        N, H, W, C = xh.shape
+        Kc, R, S, _ = w.shape
+        s, p, d = conv.stride[0], conv.padding[0], conv.dilation[0]
+        P = (H + 2 * p - d * (R - 1) - 1) // s + 1
+        Q = (W + 2 * p - d * (S - 1) - 1) // s + 1
+        y = torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
+        K.conv_fprop(xh, w, y, stats, None, s, p, d)
+        ctx.eng, ctx.conv = eng, conv
+        ctx.save_for_backward(xh)
+        ctx.x_needs_grad = x.requires_grad
+        return _nchw_view(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng, conv = ctx.eng, ctx.conv
+        K = eng.K
+        (xh,) = ctx.saved_tensors
+        dyh = _nhwc(dy)
+        s, p, d = conv.stride[0], conv.padding[0], conv.dilation[0]
+        K.conv_wgrad(dyh, xh, eng.grad_krsc(conv.weight), s, p, d)
+        dx = None
+        if ctx.x_needs_grad:
+            w = eng.w16_krsc(conv.weight)
+            if s == 1:
+                dxh = torch.empty_like(xh)
+                K.conv_dgrad(dyh, w, dxh, 1, p, d)
+            else:
+                dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d)
+            dx = _nchw_view(dxh)
+        # only now: the bucket's fused update overwrites the bf16 weights the dgrad above still reads
+        eng.mark_ready(conv.weight)
+        return dx, None, None, None
+
+
+def _strided_dgrad(K, dyh, w, x_shape, s, p, d):
+    """Data gradient of a strided conv: scatter dy onto a zero-filled stride-1 grid, then run the stride-1
+    tcgen05 dgrad (costs s^2 x the FLOPs of the few strided layers; a parity-decomposed kernel is future work)."""
+    N, H, W, C = x_shape
+    Kc, R, S, _ = w.shape
+    P1 = H + 2 * p - d * (R - 1)
+    Q1 = W + 2 * p - d * (S - 1)
+    up = torch.zeros((N, P1, Q1, Kc), dtype=dyh.dtype, device=dyh.device)
+    up[:, ::s, ::s, :][:, : dyh.shape[1], : dyh.shape[2]] = dyh
+    dxh = torch.empty((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
+    K.conv_dgrad(up, w, dxh, 1, p, d)
+    return dxh
+
+
+class StemConvFn(torch.autograd.Function):
+    """7x7/2 stem on the raw NCHW fp32 batch: explicit im2col to [pixels, 160] bf16 (K = 147 padded), then the
+    tcgen05 GEMM; wgrad is the same GEMM transposed.  The input needs no gradient."""
+
+    @staticmethod
+    def forward(ctx, x_nchw_f32, eng, conv, stats):
+        K = eng.K
+        N, C, H, W = x_nchw_f32.shape
+        Kc, _, R, S = conv.weight.shape
+        s, p = conv.stride[0], conv.padding[0]
+        P = (H + 2 * p - (R - 1) - 1) // s + 1
+        Q = (W + 2 * p - (S - 1) - 1) // s + 1
+        kdim = R * S * C
+        kpad = (kdim + 15) // 16 * 16
+        patches = torch.empty((N * P * Q, 1, 1, kpad), dtype=torch.bfloat16, device=x_nchw_f32.device)
+        K.stem_im2col(x_nchw_f32.contiguous(), patches, R, S, s, p, P, Q)
+        wpad = eng.scratch("stem_w", (Kc, 1, 1, kpad), torch.bfloat16)
+        K.pad_rows(eng.w16_krsc(conv.weight), wpad, Kc, kdim, kpad)
+        y = torch.empty((N * P * Q, 1, 1, Kc), dtype=torch.bfloat16, device=x_nchw_f32.device)
+        K.conv_fprop(patches, wpad, y, stats, None, 1, 0, 1)
+        ctx.eng, ctx.conv, ctx.dims = eng, conv, (Kc, kdim, kpad)
+        ctx.save_for_backward(patches)
+        return _nchw_view(y.view(N, P, Q, Kc))
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng, conv = ctx.eng, ctx.conv
+        K = eng.K
+        Kc, kdim, kpad = ctx.dims
+        (patches,) = ctx.saved_tensors
+        dyh = _nhwc(dy).reshape(-1, 1, 1, Kc)
+        dwp = eng.scratch("stem_dw", (Kc, 1, 1, kpad), torch.float32)
+        dwp.zero_()
+        K.conv_wgrad(dyh, patches, dwp, 1, 0, 1)
+        K.unpad_add(dwp, eng.grad_flat_view(conv.weight), Kc, kdim, kpad)
+        eng.mark_ready(conv.weight)
+        return None, None, None, None
+
+
+class BnActFn(torch.autograd.Function):
+    """act(BN(y) + residual): one pass forward (statistics come from the conv epilogue or ``bn_stats``), two
+    passes backward; SyncBN statistics are exchanged through peer memory inside the same kernels."""
+
+    @staticmethod
+    def forward(ctx, y, residual, eng, bn, act, stats_slot, training):
+        K = eng.K
+        yh = _nhwc(y)
+        N, H, W, C = yh.shape
+        y2 = yh.view(-1, C)
+        res2 = _nhwc(residual).view(-1, C) if residual is not None else None
+        out = torch.empty_like(yh)
+        save = torch.empty((2, C), dtype=torch.float32, device=y.device)
+        peer = eng.peer_state if (training and eng.sync_bn) else None
+        count = float(y2.shape[0] * (eng.world if peer is not None else 1))
+        stats = stats_slot.tensor if stats_slot is not None else save  # eval: unused
+        K.bn_apply(y2, res2, out.view(-1, C), stats, stats_slot.sym_offset if stats_slot is not None else 0,
+                   eng.master_view(bn.weight) if bn.affine else None, eng.master_view(bn.bias) if bn.affine else None,
+                   bn.running_mean, bn.running_var, save[0], save[1], count, bn.eps,
+                   bn.momentum if bn.momentum is not None else 0.1, ACT[act], training, peer)
+        if training and bn.track_running_stats:
+            eng.note_bn_step(bn)
+        ctx.eng, ctx.bn, ctx.act, ctx.count = eng, bn, act, count
+        ctx.has_res = residual is not None
+        ctx.res_needs_grad = residual is not None and residual.requires_grad
+        need_res = residual is not None and act is not None
+        ctx.save_for_backward(y2, res2 if need_res else None, save)
+        ctx.shape = (N, H, W, C)
+        return _nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng, bn = ctx.eng, ctx.bn
+        K = eng.K
+        y2, res2, save = ctx.saved_tensors
+        N, H, W, C = ctx.shape
+        d2 = _nhwc(dout).view(-1, C)
+        dy = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dout.device)
+        dres = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dout.device) if ctx.res_needs_grad else None
+        slot = eng.bwd_slot(bn)
+        peer = eng.peer_state if eng.sync_bn else None
+        K.bn_backward(y2, d2, res2, dy.view(-1, C), dres.view(-1, C) if dres is not None else None, slot.tensor,
+                      slot.sym_offset, eng.master_view(bn.weight) if bn.affine else None,
+                      eng.master_view(bn.bias) if bn.affine else None, save[0], save[1],
+                      eng.grad_flat_view(bn.weight) if bn.affine else None,
+                      eng.grad_flat_view(bn.bias) if bn.affine else None, ctx.count, ACT[ctx.act], peer)
+        if bn.affine:
+            eng.mark_ready(bn.weight)
+            eng.mark_ready(bn.bias)
+        return _nchw_view(dy), (_nchw_view(dres) if dres is not None else None), None, None, None, None, None
+
+
+class LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng, fc):
+        K = eng.K
+        x2 = x.contiguous()
+        B, Cin = x2.shape
+        w = eng.w16_view(fc.weight)  # [out, in]
+        out = torch.empty((B, 1, 1, w.shape[0]), dtype=torch.bfloat16, device=x.device)
+        K.conv_fprop(x2.view(B, 1, 1, Cin), w.view(w.shape[0], 1, 1, Cin), out, None,
+                     eng.master_view(fc.bias) if fc.bias is not None else None, 1, 0, 1)
+        ctx.eng, ctx.fc = eng, fc
+        ctx.save_for_backward(x2)
+        return out.view(B, -1)
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng, fc = ctx.eng, ctx.fc
+        K = eng.K
+        (x2,) = ctx.saved_tensors
+        B, Cin = x2.shape
+        d2 = dout.contiguous()
+        Kc = d2.shape[1]
+        K.conv_wgrad(d2.view(B, 1, 1, Kc), x2.view(B, 1, 1, Cin), eng.grad_flat_view(fc.weight).view(Kc, 1, 1, Cin), 1, 0, 1)
+        if fc.bias is not None:
+            eng.grad_flat_view(fc.bias).add_(d2.float().sum(0))
+        dx = torch.empty((B, 1, 1, Cin), dtype=torch.bfloat16, device=dout.device)
+        K.conv_dgrad(d2.view(B, 1, 1, Kc), eng.w16_view(fc.weight).view(Kc, 1, 1, Cin), dx, 1, 0, 1)
+        eng.mark_ready(fc.weight)
+        if fc.bias is not None:
+            eng.mark_ready(fc.bias)
+        return dx.view(B, Cin), None, None
+
+
+class MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng, k, s, p):
+        xh = _nhwc(x)
+        N, H, W, C = xh.shape
+        P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        out = torch.empty((N, P, Q, C), dtype=xh.dtype, device=x.device)
+        arg = torch.empty((N, P, Q, C), dtype=torch.uint8, device=x.device) if x.requires_grad else None
+        eng.K.maxpool_fwd(xh, out, arg, k, s, p)
+        ctx.eng, ctx.cfg, ctx.in_shape = eng, (k, s, p), xh.shape
+        ctx.save_for_backward(arg)
+        return _nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        (arg,) = ctx.saved_tensors
+        dx = torch.empty(ctx.in_shape, dtype=torch.bfloat16, device=dout.device)
+        ctx.eng.K.maxpool_bwd(_nhwc(dout), arg, dx, *ctx.cfg)
+        return _nchw_view(dx), None, None, None, None
+
+
+class AvgPool2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng):
+        xh = _nhwc(x)
+        N, H, W, C = xh.shape
+        out = torch.empty((N, H // 2, W // 2, C), dtype=xh.dtype, device=x.device)
+        eng.K.avgpool2_fwd(xh, out)
+        ctx.eng, ctx.in_shape = eng, xh.shape
+        return _nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx = torch.empty(ctx.in_shape, dtype=torch.bfloat16, device=dout.device)
+        ctx.eng.K.avgpool2_bwd(_nhwc(dout), dx)
+        return _nchw_view(dx), None
+
+
+class GapFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, eng):
+        xh = _nhwc(x)
+        N, H, W, C = xh.shape
+        out = torch.empty((N, C), dtype=xh.dtype, device=x.device)
+        eng.K.gap_fwd(xh, out)
+        ctx.eng, ctx.in_shape = eng, xh.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dx = torch.empty(ctx.in_shape, dtype=torch.bfloat16, device=dout.device)
+        ctx.eng.K.gap_bwd(dout.contiguous(), dx)
+        return _nchw_view(dx), None
+
+
+class CeTopkFn(torch.autograd.Function):
+    """softmax-CE + top-1/top-k counts + dlogits in one kernel (reference trainer.py:43,50 + utils.py:265-277)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, eng, topk):
+        lg = logits.contiguous()
+        B = lg.shape[0]
+        accum = torch.zeros(3, dtype=torch.float32, device=lg.device)
+        dl = torch.empty_like(lg) if logits.requires_grad else None
+        eng.K.ce_topk(lg, target.contiguous(), dl, accum, topk, 1.0 / B)
+        ctx.save_for_backward(dl)
+        ctx.mark_non_differentiable(accum)
+        return accum[0] / B, accum
+
+    @staticmethod
+    def backward(ctx, dloss, _daccum):
+        (dl,) = ctx.saved_tensors
+        return dl * dloss.to(dl.dtype), None, None, None
+
+
+class NativeOps:
+    """Implements the ``ops.functional`` surface for one ``NativeEngine``."""
+
+    def __init__(self, engine):
+        self.eng = engine
+
+    # ---- helpers -------------------------------------------------------------------------------
+    @staticmethod
+    def _native_conv_ok(conv: nn.Conv2d, x) -> bool:
+        kh, kw = conv.kernel_size
+        return (conv.groups == 1 and conv.bias is None and kh == kw and conv.stride[0] == conv.stride[1]
+                and conv.padding[0] == conv.padding[1] and conv.dilation[0] == conv.dilation[1]
+                and isinstance(conv.padding, tuple) and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0
+                and x.dtype == torch.bfloat16 and conv.padding_mode == "zeros")
+
+    @staticmethod
+    def _is_stem(conv: nn.Conv2d, x) -> bool:
+        return (conv.in_channels < 8 and conv.groups == 1 and conv.bias is None and x.dtype == torch.float32
+                and conv.out_channels % 8 == 0 and conv.dilation[0] == 1)
+
+    def _as_act(self, x):
+        """Bring an arbitrary input (fp32 NCHW batch) onto the activation convention."""
+        if x.dtype == torch.bfloat16:
+            return x
+        N, C, H, W = x.shape
+        out = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device)
+        self.eng.K.nchw_to_nhwc(x.contiguous(), out)
+        return _nchw_view(out)
+
+    def _torch_conv(self, x, conv):
+        x = self._as_act(x)
+        w = self.eng.w16_leaf(conv.weight)
+        b = self.eng.w16_leaf(conv.bias) if conv.bias is not None else None
+        return F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+
+    # ---- functional surface ----------------------------------------------------------------------
+    def conv_bn_act(self, x, conv, bn, act, residual):
+        eng = self.eng
+        training = bn is not None and bn.training
+        slot = eng.fwd_slot(bn) if training else None
+        stats = slot.tensor if slot is not None else None
+        if self._is_stem(conv, x):
+            y = StemConvFn.apply(x, eng, conv, stats)
+        elif self._native_conv_ok(conv, x):
+            y = ConvFn.apply(x, eng, conv, stats)
+        else:
+            y = self._torch_conv(x, conv)
+            if stats is not None:
+                yh = _nhwc(y)
+                eng.K.bn_stats(yh.view(-1, yh.shape[-1]), stats)
+        if bn is None:
+            if residual is not None:
+                y = y + residual
+            return _torch_act(y, act)
+        return BnActFn.apply(y, residual, eng, bn, act, slot, training)
+
+    def bn_act(self, x, bn, act):
+        eng = self.eng
+        x = self._as_act(x)
+        training = bn.training
+        slot = eng.fwd_slot(bn) if training else None
+        if slot is not None:
+            xh = _nhwc(x)
+            eng.K.bn_stats(xh.view(-1, xh.shape[-1]), slot.tensor)
+        return BnActFn.apply(x, None, eng, bn, act, slot, training)
+
+    def linear(self, x, fc):
+        if x.dtype == torch.bfloat16 and fc.in_features % 8 == 0 and fc.out_features % 8 == 0:
+            return LinearFn.apply(x, self.eng, fc)
+        w = self.eng.w16_leaf(fc.weight)
+        b = self.eng.w16_leaf(fc.bias) if fc.bias is not None else None
+        return F.linear(x.to(torch.bfloat16), w, b)
+
+    def max_pool2d(self, x, k, s, p):
+        if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+            return MaxPoolFn.apply(x, self.eng, k, s, p)
+        return F.max_pool2d(x, k, s, p)
+
+    def avg_pool2d(self, x, k, s):
+        if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and k == 2 and s == 2 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
+            return AvgPool2Fn.apply(x, self.eng)
+        return F.avg_pool2d(x, k, s)
+
+    def global_avg_pool(self, x):
+        if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
+            return GapFn.apply(x, self.eng)
+        return x.mean(dim=(2, 3))
+
+    def squeeze_excite(self, x, fc1, fc2, act):
+        s = self.global_avg_pool(x)[:, :, None, None]
+        s = _torch_act(self._torch_conv(s, fc1), act)
+        return x * torch.sigmoid(self._torch_conv(s, fc2))
+
+    def concat_channels(self, tensors):
+        tensors = [self._as_act(t) for t in tensors]
+        if len(tensors) == 1:
+            return tensors[0]
+        return torch.cat(tensors, dim=1).contiguous(memory_format=torch.channels_last)
+
+    def relpos_attention(self, q, k, v, rel_h, rel_w, height, width, scale):
+        from . import functional as Fn
+        from . import runtime
+        with runtime.native_scope(None):  # composite torch ops on bf16; positional tables via leaf views
+            return Fn.relpos_attention(q, k, v, self.eng.w16_leaf(rel_h), self.eng.w16_leaf(rel_w), height, width, scale)
+
+    def cross_entropy_topk(self, logits, target, topk):
+        if logits.dtype == torch.bfloat16:
+            loss, accum = CeTopkFn.apply(logits, target, self.eng, topk)
+            return loss, accum[1], accum[2]
+        from . import functional as Fn
+        from . import runtime
+        with runtime.native_scope(None):
+            return Fn.cross_entropy_topk(logits, target, topk)
+
+
+def _torch_act(x, act):
+    if act is None:
+        return x
+    if act == "relu":
+        return F.relu(x)
+    if act == "silu":
+        return F.silu(x)
+    raise ValueError(act)

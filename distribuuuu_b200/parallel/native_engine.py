@@ -1,0 +1,440 @@
+"""Native data-parallel engine: flat parameter storage, fused peer-memory all-reduce + SGD,
+peer-memory SyncBN, CUDA-stream overlap.
+
+What replaces what (reference call sites -> here):
+
+* ``DDP(net)`` ctor broadcast (trainer.py:134)      -> one broadcast of the flat fp32 master.
+* C++ Reducer bucket copies + ``ncclAllReduce`` per bucket + ``optimizer.step()`` foreach kernels
+  (trainer.py:46-47)                        -> ``csrc/comm.cu::allreduce_sgd_kernel`` per
+  bucket on a side stream, started as soon as the bucket's last gradient kernel is enqueued: gradients are
+  produced by the wgrad kernels directly into the flat fp32 buffer, reduced through NVLink peer memory
+  (multimem.ld_reduce in the switch, or P2P loads), the Nesterov update runs on the owner's shard of the
+  fp32 master weights (optimizer state is sharded ZeRO-1 style) and the new bf16 weights are multicast
+  back to every rank.
+* ``optimizer.zero_grad()`` (trainer.py:45; G14)                 -> folded into the same kernel.
+* ``nn.SyncBatchNorm`` all_gather / all_reduce per layer (K5/K6) -> statistics exchanged by P2P loads inside
+  the BN kernels (``csrc/elementwise.cu``), one flag exchange per layer per direction.
+* per-iteration DDP buffer broadcast (K3)                        -> dropped: running statistics stay local.
+
+Checkpoints stay reference-compatible: ``module.state_dict()`` reads fp32 views of the flat master and
+``FusedSGD.state_dict()`` emits ``torch.optim.SGD`` format (sharded state is gathered first).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List
+
+import torch
+import torch.distributed as dist
+import torch.nn as nn
+from loguru import logger
+
+from ..ops import build, runtime
+from ..ops.native import NativeOps
+
+_ALIGN = 64           # parameter offsets are multiples of 64 elements (128 B of bf16: TMA-friendly)
+_ONE_SHOT_BYTES = 512 * 1024
+
+
+@dataclass
+class _Slot:
+    tensor: torch.Tensor
+    sym_offset: int
+
+
+@dataclass
+class _Bucket:
+    off: int
+    n: int
+    params: list
+    pending: int = 0
+    one_shot: bool = False
+
+
+class FusedSGD:
+    """Optimizer facade over the engine's flat buffers (same surface the trainer and checkpoint code use on
+    ``torch.optim.SGD``: ``param_groups``, ``state_dict``, ``load_state_dict``, ``zero_grad``, ``step``)."""
+
+    def __init__(self, engine, lr, momentum=0.0, dampening=0.0, weight_decay=0.0, nesterov=False):
+        if nesterov and (momentum <= 0 or dampening != 0):
+            raise ValueError("Nesterov momentum requires a momentum and zero dampening")
+        self.engine = engine
+        self.param_groups = [dict(lr=lr, momentum=momentum, dampening=dampening, weight_decay=weight_decay,
+                                  nesterov=nesterov, maximize=False, foreach=None, differentiable=False, fused=None,
+                                  params=list(range(len(engine.params))))]
+        self.steps = 0
+        self.has_momentum_state = False
+
+    def zero_grad(self, set_to_none: bool = True):  # gradients are zeroed by the fused update itself
+        pass
+
+    def step(self):  # the update is fused into the engine's train_step; kept for API compatibility
+        pass
+
+    def hyper(self):
+        g = self.param_groups[0]
+        return (float(g["lr"]), float(g["momentum"]), float(g["dampening"]), float(g["weight_decay"]),
+                bool(g["nesterov"]), not self.has_momentum_state)
+
+    def state_dict(self):
+        eng = self.engine
+        eng.sync_masters()
+        state = {}
+        if self.has_momentum_state and self.param_groups[0]["momentum"] != 0:
+            for i, p in enumerate(eng.params):
+                state[i] = {"momentum_buffer": eng.logical_view(eng.flat_mom, p).detach().clone().contiguous()}
+        groups = [dict(g) for g in self.param_groups]
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        eng = self.engine
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(eng.params):
+            raise ValueError("optimizer state does not match the model (parameter count differs)")
+        for k in ("lr", "momentum", "dampening", "weight_decay", "nesterov"):
+            if k in groups[0]:
+                self.param_groups[0][k] = groups[0][k]
+        eng.flat_mom.zero_()
+        loaded = 0
+        for i, p in enumerate(eng.params):
+            st = sd["state"].get(i, sd["state"].get(str(i)))
+            if st is not None and st.get("momentum_buffer") is not None:
+                eng.logical_view(eng.flat_mom, p).copy_(st["momentum_buffer"])
+                loaded += 1
+        self.has_momentum_state = loaded > 0
+
+
+class NativeEngine(nn.Module):
+    def __init__(self, module: nn.Module, device: torch.device, precision: str = "bf16", comm: str = "peer",
+                 bucket_cap_mb: float = 25, sync_bn: bool = False):
+        super().__init__()
+        if precision != "bf16":
+            raise ValueError("the native engine computes in bf16 (fp32 master weights); use B200.ENGINE=torch for fp32")
+        self.module = module
+        self.device = device
+        self.K = build.load()
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.sync_bn = bool(sync_bn) and self.world > 1
+        self.ops = NativeOps(self)
+        self.optimizer: FusedSGD | None = None
+        self.comm_mode = comm if self.world > 1 else "local"
+        self._scratch: Dict[str, torch.Tensor] = {}
+        self._leaves: Dict[nn.Parameter, torch.Tensor] = {}
+        self._bn_stepped: List[torch.Tensor] = []
+        self._step_parity = 0
+        self.comm_stream = torch.cuda.Stream(device)
+        self._build_flat_storage()
+        self._build_bn_slots()
+        self._setup_comm()
+        self._plan_buckets(int(bucket_cap_mb * 1024 * 1024))
+        self._sync_initial_state()
+
+    # ------------------------------------------------------------------------------ storage
+    def _build_flat_storage(self):
+        self.params = [p for p in self.module.parameters()]
+        self.index: Dict[nn.Parameter, tuple] = {}
+        off = 0
+        for p in self.params:
+            self.index[p] = (off, p.numel())
+            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+        self.total = off
+        dev = self.device
+        self.flat_master = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.flat_mom = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        self.flat_grad = torch.zeros(self.total, dtype=torch.float32, device=dev)
+        for p in self.params:  # rebind every parameter to a view of the flat master (conv weights physically KRSC)
+            view = self.logical_view(self.flat_master, p)
+            view.copy_(p.data)
+            p.data = view
+
+    def logical_view(self, flat: torch.Tensor, p: nn.Parameter) -> torch.Tensor:
+        """View of ``flat`` with the parameter's logical shape; 4-D weights are stored [O,H,W,I]."""
+        off, n = self.index[p]
+        if p.dim() == 4:
+            O, I, H, W = p.shape
+            return flat[off:off + n].view(O, H, W, I).permute(0, 3, 1, 2)
+        return flat[off:off + n].view(p.shape)
+
+    def master_view(self, p):
+        return p.data
+
+    def grad_flat_view(self, p):
+        off, n = self.index[p]
+        return self.flat_grad[off:off + n]
+
+    def grad_krsc(self, p):
+        O, I, H, W = p.shape
+        return self.grad_flat_view(p).view(O, H, W, I)
+
+    def w16_view(self, p):
+        off, n = self.index[p]
+        return self.flat_w16[off:off + n].view(p.shape)
+
+    def w16_krsc(self, p):
+        off, n = self.index[p]
+        O, I, H, W = p.shape
+        return self.flat_w16[off:off + n].view(O, H, W, I)
+
+    def w16_leaf(self, p):
+        """bf16 leaf (logical shape) for torch fallback ops; its gradient is folded into the flat buffer."""
+        leaf = self._leaves.get(p)
+        if leaf is None:
+            leaf = self.logical_view(self.flat_w16, p).detach().requires_grad_(True)
+            gview = self.logical_view(self.flat_grad, p)
+
+            def hook(t, gview=gview, p=p):
+                gview.add_(t.grad)
+                t.grad = None
+                self.mark_ready(p)
+
+            leaf.register_post_accumulate_grad_hook(hook)
+            self._leaves[p] = leaf
+        return leaf
+
+    def scratch(self, name, shape, dtype):
+        t = self._scratch.get(name)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = torch.zeros(shape, dtype=dtype, device=self.device)
+            self._scratch[name] = t
+        return t
+
+    # ------------------------------------------------------------------------------ BN statistics slots
+    def _build_bn_slots(self):
+        self.bn_offsets: Dict[nn.Module, int] = {}
+        off = 0
+        for m in self.module.modules():
+            if isinstance(m, nn.modules.batchnorm._BatchNorm):
+                self.bn_offsets[m] = off
+                off += 2 * m.num_features          # forward: sum, sumsq
+                off += 2 * m.num_features          # backward: sum(dz), sum(dz*xhat)
+        self.stats_len = (off + 63) // 64 * 64
+
+    def fwd_slot(self, bn) -> _Slot:
+        base = self._step_parity * self.stats_len + self.bn_offsets[bn]
+        n = 2 * bn.num_features
+        return _Slot(self.stats_buf[base:base + n], self.stats_sym_base + base)
+
+    def bwd_slot(self, bn) -> _Slot:
+        base = self._step_parity * self.stats_len + self.bn_offsets[bn] + 2 * bn.num_features
+        n = 2 * bn.num_features
+        return _Slot(self.stats_buf[base:base + n], self.stats_sym_base + base)
+
+    def note_bn_step(self, bn):
+        if bn.num_batches_tracked is not None:
+            self._bn_stepped.append(bn.num_batches_tracked)
+
+    # ------------------------------------------------------------------------------ communication setup
+    def _setup_comm(self):
+        """Allocate w16 / gradient staging / BN statistics / flags -- in symmetric memory when world > 1."""
+        dev = self.device
+        n16 = self.total * 2                     # bytes of one bf16 flat buffer
+        stats_bytes = 2 * self.stats_len * 4
+        flag_bytes = 4096
+        layout = {"w16": 0, "stage": n16, "stats": 2 * n16, "flags": 2 * n16 + stats_bytes}
+        nbytes = 2 * n16 + stats_bytes + flag_bytes
+        self.peer_state = None
+        self.comm_state = None
+        self.symm_handle = None
+        raw = None
+        if self.world > 1 and self.comm_mode == "peer":
+            try:
+                import torch.distributed._symmetric_memory as symm
+                raw = symm.empty(nbytes, dtype=torch.uint8, device=dev)
+                raw.zero_()
+                torch.cuda.synchronize(dev)
+                self.symm_handle = symm.rendezvous(raw, group=dist.group.WORLD)
+            except Exception as exc:  # loud, not silent: the run continues on the NCCL baseline path
+                logger.warning(f"[b200] symmetric memory unavailable ({type(exc).__name__}: {exc}); "
+                               "falling back to B200.COMM=nccl (baseline path, NOT the fused peer kernel)")
+                self.comm_mode = "nccl"
+                self.symm_handle = None
+                raw = None
+        if raw is None:
+            raw = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        self._raw = raw
+        self.flat_w16 = raw[layout["w16"]:layout["w16"] + n16].view(torch.bfloat16)
+        self.flat_stage = raw[layout["stage"]:layout["stage"] + n16].view(torch.bfloat16)
+        self.stats_buf = raw[layout["stats"]:layout["stats"] + stats_bytes].view(torch.float32)
+        self.stats_sym_base = 0  # offsets handed to kernels are relative to the per-rank statistics base pointer
+        self._local_sync = torch.zeros(16, dtype=torch.int32, device=dev)
+        if self.sync_bn and self.comm_mode != "peer":
+            raise RuntimeError("MODEL.SYNCBN on the native engine needs the peer-memory path (B200.COMM=peer); "
+                               "use B200.ENGINE=torch for SyncBN over NCCL")
+        if self.symm_handle is not None:
+            h = self.symm_handle
+            ptrs = [int(p) for p in h.buffer_ptrs]
+            mc = int(h.multicast_ptr) if getattr(h, "multicast_ptr", 0) else 0
+            cs = self.K.CommState()
+            cs.world, cs.rank, cs.slot_base = self.world, self.rank, 0
+            cs.signal_pads = [p + layout["flags"] for p in ptrs]
+            cs.stage = [p + layout["stage"] for p in ptrs]
+            cs.w16 = [p + layout["w16"] for p in ptrs]
+            cs.mc_stage = mc + layout["stage"] if mc else 0
+            cs.mc_w16 = mc + layout["w16"] if mc else 0
+            cs.local_counter = self._local_sync[0:].data_ptr()
+            cs.local_release = self._local_sync[4:].data_ptr()
+            self.comm_state = cs
+            ps = self.K.PeerState()
+            ps.world, ps.rank, ps.slot_base = self.world, self.rank, 64   # flag slots 64.. belong to SyncBN
+            ps.signal_pads = [p + layout["flags"] for p in ptrs]
+            ps.sym_bufs = [p + layout["stats"] for p in ptrs]
+            ps.ticket = self._local_sync[8:].data_ptr()
+            self.peer_state = ps
+            self.has_multicast = bool(mc)
+            dist.barrier()
+            if self.rank == 0:
+                logger.info(f"[b200] peer-memory comm ready: world={self.world} multicast={'yes' if mc else 'no'} "
+                            f"symmetric bytes={nbytes}")
+
+    def _plan_buckets(self, cap_bytes: int):
+        """Contiguous flat ranges in reverse parameter order (the order gradients become ready); first bucket 1 MiB."""
+        self.buckets: List[_Bucket] = []
+        self.bucket_of: Dict[nn.Parameter, _Bucket] = {}
+        cap = 1 << 20
+        cur: List[nn.Parameter] = []
+        cur_bytes = 0
+
+        def close():
+            nonlocal cur, cur_bytes, cap
+            if not cur:
+                return
+            lo = self.index[cur[-1]][0]
+            last_off, last_n = self.index[cur[0]]
+            hi = (last_off + last_n + _ALIGN - 1) // _ALIGN * _ALIGN
+            b = _Bucket(off=lo, n=hi - lo, params=list(cur), one_shot=(hi - lo) * 2 <= _ONE_SHOT_BYTES)
+            for p in cur:
+                self.bucket_of[p] = b
+            self.buckets.append(b)
+            cur, cur_bytes, cap = [], 0, cap_bytes
+
+        for p in reversed(self.params):
+            nbytes = p.numel() * 4
+            if cur and cur_bytes + nbytes > cap:
+                close()
+            cur.append(p)
+            cur_bytes += nbytes
+        close()
+        self._reset_pending()
+
+    def _reset_pending(self):
+        for b in self.buckets:
+            b.pending = sum(1 for p in b.params if p.requires_grad)
+
+    def _sync_initial_state(self):
+        if self.world > 1:
+            dist.broadcast(self.flat_master, src=0)
+            for buf in self.module.buffers():
+                dist.broadcast(buf, src=0)
+        self.refresh_compute_weights()
+
+    def refresh_compute_weights(self):
+        self.K.cast_bf16(self.flat_master, self.flat_w16)
+        torch.cuda.synchronize(self.device)
+        if self.world > 1:
+            dist.barrier()
+
+    def on_weights_loaded(self):
+        self.refresh_compute_weights()
+
+    # ------------------------------------------------------------------------------ optimizer plumbing
+    def make_optimizer(self, **hparams):
+        self.optimizer = FusedSGD(self, **hparams)
+        return self.optimizer
+
+    def _owned_mask_apply(self, flat):
+        """Zero the regions of ``flat`` this rank does not own (see sync_masters)."""
+        if self.comm_mode != "peer":
+            return
+        for b in self.buckets:
+            if b.one_shot:
+                if self.rank != 0:
+                    flat[b.off:b.off + b.n].zero_()
+                continue
+            n8 = b.n // 8
+            per = (n8 + self.world - 1) // self.world
+            lo = min(per * self.rank, n8) * 8
+            hi = min(lo // 8 + per, n8) * 8
+            flat[b.off:b.off + lo].zero_()
+            flat[b.off + hi:b.off + b.n].zero_()
+
+    def sync_masters(self):
+        """Make every rank's fp32 master weights and momentum complete (two-shot buckets keep only the owner's
+        shard up to date).  Collective; called before checkpointing."""
+        if self.world == 1 or self.comm_mode != "peer":
+            return
+        torch.cuda.synchronize(self.device)
+        for flat in (self.flat_master, self.flat_mom):
+            self._owned_mask_apply(flat)
+            dist.all_reduce(flat)
+
+    def mark_ready(self, p):
+        b = self.bucket_of.get(p)
+        if b is None:
+            return
+        b.pending -= 1
+        if b.pending == 0 and self.world > 1 and self._in_train_step:
+            self._launch_bucket(b)
+
+    def _launch_bucket(self, b: _Bucket):
+        lr, mom, damp, wd, nest, first = self.optimizer.hyper()
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self.comm_stream.wait_event(ev)
+        with torch.cuda.stream(self.comm_stream):
+            if self.comm_mode == "peer":
+                grid = 8 if b.one_shot else 32
+                self.K.allreduce_sgd(self.comm_state, self.flat_master, self.flat_mom, self.flat_grad, b.off, b.n,
+                                     lr, mom, damp, wd, nest, first, b.one_shot, grid)
+            else:  # NCCL baseline: library all-reduce, then the local fused update
+                g = self.flat_grad[b.off:b.off + b.n]
+                dist.all_reduce(g)
+                self.K.sgd_local(self.flat_master, self.flat_mom, self.flat_grad, self.flat_w16, b.off, b.n,
+                                 lr, mom, damp, wd, nest, first, 1.0 / self.world, True)
+
+    _in_train_step = False
+
+    # ------------------------------------------------------------------------------ steps
+    def forward(self, x):
+        with runtime.native_scope(self):
+            return self.module(x)
+
+    def _begin_step(self):
+        self._step_parity ^= 1
+        base = self._step_parity * self.stats_len
+        self.stats_buf[base:base + self.stats_len].zero_()
+        self._bn_stepped.clear()
+
+    def train_step(self, inputs, targets, optimizer, topk: int):
+        assert optimizer is self.optimizer, "the native engine steps its own FusedSGD (utils.construct_optimizer)"
+        self._begin_step()
+        self._reset_pending()
+        self._in_train_step = True
+        try:
+            with runtime.native_scope(self):
+                logits = self.module(inputs)
+                loss, hits1, hitsk = self.ops.cross_entropy_topk(logits, targets, topk)
+            loss.backward()
+        finally:
+            self._in_train_step = False
+        if self._bn_stepped:
+            torch._foreach_add_(self._bn_stepped, 1)
+        lr, mom, damp, wd, nest, first = optimizer.hyper()
+        if self.world == 1:
+            self.K.sgd_local(self.flat_master, self.flat_mom, self.flat_grad, self.flat_w16, 0, self.total,
+                             lr, mom, damp, wd, nest, first, 1.0, True)
+        else:
+            for b in self.buckets:  # parameters that produced no gradient this step still take part
+                if b.pending > 0:
+                    b.pending = 0
+                    self._launch_bucket(b)
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        optimizer.has_momentum_state = True
+        optimizer.steps += 1
+        return loss.detach(), hits1, hitsk
+
+    @torch.no_grad()
+    def eval_step(self, inputs, targets, topk: int):
+        with runtime.native_scope(self):
+            logits = self.module(inputs)
+            return self.ops.cross_entropy_topk(logits, targets, topk)

@@ -1,0 +1,291 @@
+"""Numerical self-tests of the sm_100a kernels against plain PyTorch fp32 references.
+
+Each ``check_*`` function raises ``AssertionError`` on mismatch and returns a dict of error metrics.  They are
+used by ``tests/test_gpu_*.py`` (in-process, ``@pytest.mark.gpu``) and by ``tools/gpu_selftest.py`` (one
+subprocess per check with a timeout, so a hung or trapping kernel cannot take the other checks down).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+
+def _K():
+    from .ops import build
+    return build.load()
+
+
+def _rel_err(got: torch.Tensor, want: torch.Tensor) -> float:
+    got, want = got.float(), want.float()
+    return float((got - want).abs().max() / want.abs().max().clamp_min(1e-6))
+
+
+def _bf16(*shape, scale=1.0, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(torch.bfloat16)
+
+
+# ---------------------------------------------------------------------------------------------- conv / GEMM
+def _ref_conv(x_nhwc, w_krsc, stride, pad, dil):
+    x = x_nhwc.float().permute(0, 3, 1, 2)
+    w = w_krsc.float().permute(0, 3, 1, 2)
+    return F.conv2d(x, w, None, stride, pad, dil).permute(0, 2, 3, 1).contiguous()
+
+
+def check_conv_fprop(N=4, H=14, W=14, C=64, K=128, R=3, stride=1, pad=1, dil=1, stats=True, tol=2e-2):
+    Kmod = _K()
+    x = _bf16(N, H, W, C, seed=1)
+    w = _bf16(K, R, R, C, scale=(C * R * R) ** -0.5, seed=2)
+    P = (H + 2 * pad - dil * (R - 1) - 1) // stride + 1
+    Q = (W + 2 * pad - dil * (R - 1) - 1) // stride + 1
+    y = torch.full((N, P, Q, K), float("nan"), dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2 * K, dtype=torch.float32, device="cuda") if stats else None
+    Kmod.conv_fprop(x, w, y, st, None, stride, pad, dil)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, stride, pad, dil)
+    err = _rel_err(y, ref)
+    out = {"rel_err": err}
+    assert err < tol, f"conv_fprop mismatch rel_err={err}"
+    if stats:
+        yf = y.float().view(-1, K)
+        e1 = _rel_err(st[:K], yf.sum(0))
+        e2 = _rel_err(st[K:], (yf * yf).sum(0))
+        out.update(stats_sum_err=e1, stats_sq_err=e2)
+        assert e1 < 2e-3 and e2 < 2e-3, f"BN-statistics epilogue mismatch {e1} {e2}"
+    return out
+
+
+def check_conv_dgrad(N=4, H=14, W=14, C=64, K=128, R=3, pad=1, dil=1, tol=2e-2):
+    Kmod = _K()
+    P, Q = H + 2 * pad - dil * (R - 1), W + 2 * pad - dil * (R - 1)
+    dy = _bf16(N, P, Q, K, seed=3)
+    w = _bf16(K, R, R, C, scale=(K * R * R) ** -0.5, seed=4)
+    dx = torch.full((N, H, W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    Kmod.conv_dgrad(dy, w, dx, 1, pad, dil)
+    torch.cuda.synchronize()
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, 1, pad, 0, 1, dil)
+    err = _rel_err(dx, ref.permute(0, 2, 3, 1))
+    assert err < tol, f"conv_dgrad mismatch rel_err={err}"
+    return {"rel_err": err}
+
+
+def check_conv_wgrad(N=4, H=14, W=14, C=64, K=128, R=3, stride=1, pad=1, dil=1, tol=2e-2):
+    Kmod = _K()
+    P = (H + 2 * pad - dil * (R - 1) - 1) // stride + 1
+    Q = (W + 2 * pad - dil * (R - 1) - 1) // stride + 1
+    x = _bf16(N, H, W, C, seed=5)
+    dy = _bf16(N, P, Q, K, seed=6)
+    dw = torch.zeros((K, R, R, C), dtype=torch.float32, device="cuda")
+    Kmod.conv_wgrad(dy, x, dw, stride, pad, dil)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(False)
+    wr = torch.zeros((K, C, R, R), device="cuda", requires_grad=True)
+    F.conv2d(xr, wr, None, stride, pad, dil).backward(dy.float().permute(0, 3, 1, 2))
+    err = _rel_err(dw, wr.grad.permute(0, 2, 3, 1))
+    assert err < tol, f"conv_wgrad mismatch rel_err={err}"
+    return {"rel_err": err}
+
+
+CONV_CASES = {
+    # name: (kind, kwargs)
+    "fprop_1x1_k64": ("fprop", dict(N=2, H=28, W=28, C=64, K=64, R=1, pad=0)),
+    "fprop_1x1_k256_tail": ("fprop", dict(N=3, H=7, W=7, C=256, K=1024, R=1, pad=0)),
+    "fprop_1x1_c24": ("fprop", dict(N=2, H=8, W=8, C=24, K=72, R=1, pad=0)),
+    "fprop_3x3": ("fprop", dict(N=4, H=14, W=14, C=64, K=128, R=3, pad=1)),
+    "fprop_3x3_56": ("fprop", dict(N=2, H=56, W=56, C=64, K=64, R=3, pad=1)),
+    "fprop_3x3_s2": ("fprop", dict(N=2, H=28, W=28, C=128, K=128, R=3, stride=2, pad=1)),
+    "fprop_1x1_s2": ("fprop", dict(N=2, H=28, W=28, C=256, K=512, R=1, stride=2, pad=0)),
+    "fprop_3x3_small": ("fprop", dict(N=1, H=7, W=7, C=64, K=64, R=3, pad=1)),
+    "fprop_5x5_dil": ("fprop", dict(N=2, H=12, W=12, C=64, K=64, R=3, pad=2, dil=2)),
+    "dgrad_1x1": ("dgrad", dict(N=2, H=28, W=28, C=64, K=256, R=1, pad=0)),
+    "dgrad_1x1_wide": ("dgrad", dict(N=2, H=7, W=7, C=512, K=2048, R=1, pad=0)),
+    "dgrad_3x3": ("dgrad", dict(N=4, H=14, W=14, C=256, K=256, R=3, pad=1)),
+    "dgrad_3x3_56": ("dgrad", dict(N=2, H=56, W=56, C=64, K=64, R=3, pad=1)),
+    "wgrad_1x1": ("wgrad", dict(N=4, H=14, W=14, C=256, K=1024, R=1, pad=0)),
+    "wgrad_1x1_k64": ("wgrad", dict(N=2, H=56, W=56, C=64, K=64, R=1, pad=0)),
+    "wgrad_3x3": ("wgrad", dict(N=4, H=14, W=14, C=256, K=256, R=3, pad=1)),
+    "wgrad_3x3_s2": ("wgrad", dict(N=2, H=28, W=28, C=128, K=128, R=3, stride=2, pad=1)),
+    "wgrad_1x1_s2": ("wgrad", dict(N=2, H=28, W=28, C=256, K=512, R=1, stride=2, pad=0)),
+}
+
+
+def check_conv_case(name: str):
+    kind, kw = CONV_CASES[name]
+    return {"fprop": check_conv_fprop, "dgrad": check_conv_dgrad, "wgrad": check_conv_wgrad}[kind](**kw)
+
+
+# ---------------------------------------------------------------------------------------------- BN / pools / CE / SGD
+def check_bn(N=8, H=14, W=14, C=64, act="relu", residual=True):
+    Kmod = _K()
+    from .ops.native import ACT
+    y = _bf16(N * H * W, C, seed=7)
+    res = _bf16(N * H * W, C, seed=8) if residual else None
+    gamma = torch.rand(C, device="cuda") + 0.5
+    beta = torch.randn(C, device="cuda") * 0.1
+    rm, rv = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    stats = torch.zeros(2 * C, device="cuda")
+    Kmod.bn_stats(y, stats)
+    out = torch.empty_like(y)
+    save = torch.empty(2, C, device="cuda")
+    rows = y.shape[0]
+    Kmod.bn_apply(y, res, out, stats, 0, gamma, beta, rm, rv, save[0], save[1], float(rows), 1e-5, 0.1, ACT[act], True, None)
+    # reference
+    yr = y.float().clone().requires_grad_(True)
+    rr = res.float().clone().requires_grad_(True) if residual else None
+    g_ref, b_ref = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device="cuda"), torch.ones(C, device="cuda")
+    z = F.batch_norm(yr, rm2, rv2, g_ref, b_ref, True, 0.1, 1e-5)
+    if residual:
+        z = z + rr
+    o_ref = F.relu(z) if act == "relu" else (F.silu(z) if act == "silu" else z)
+    e_out = _rel_err(out, o_ref)
+    assert e_out < 2e-2, f"bn_apply mismatch {e_out}"
+    assert _rel_err(rm, rm2) < 1e-3 and _rel_err(rv, rv2) < 1e-3, "running statistics mismatch"
+    # backward
+    dout = _bf16(rows, C, seed=9)
+    o_ref.backward(dout.float())
+    dy = torch.empty_like(y)
+    dres = torch.empty_like(y) if residual else None
+    sums = torch.zeros(2 * C, device="cuda")
+    dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    Kmod.bn_backward(y, dout, res, dy, dres, sums, 0, gamma, beta, save[0], save[1], dgamma, dbeta, float(rows), ACT[act], None)
+    torch.cuda.synchronize()
+    errs = {"out": e_out, "dy": _rel_err(dy, yr.grad), "dgamma": _rel_err(dgamma, g_ref.grad), "dbeta": _rel_err(dbeta, b_ref.grad)}
+    if residual:
+        errs["dres"] = _rel_err(dres, rr.grad)
+    assert all(v < 3e-2 for v in errs.values()), f"bn backward mismatch {errs}"
+    return errs
+
+
+def check_pools():
+    Kmod = _K()
+    x = _bf16(4, 16, 16, 64, seed=10)
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    # maxpool 3x3/2
+    out = torch.empty((4, 8, 8, 64), dtype=torch.bfloat16, device="cuda")
+    arg = torch.empty((4, 8, 8, 64), dtype=torch.uint8, device="cuda")
+    Kmod.maxpool_fwd(x, out, arg, 3, 2, 1)
+    ref = F.max_pool2d(xr, 3, 2, 1)
+    assert _rel_err(out, ref.permute(0, 2, 3, 1)) < 1e-6, "maxpool fwd"
+    dout = _bf16(4, 8, 8, 64, seed=11)
+    ref.backward(dout.float().permute(0, 3, 1, 2))
+    dx = torch.empty_like(x)
+    Kmod.maxpool_bwd(dout, arg, dx, 3, 2, 1)
+    e_mp = _rel_err(dx, xr.grad.permute(0, 2, 3, 1))
+    assert e_mp < 1e-2, f"maxpool bwd {e_mp}"
+    # global average pool
+    g = torch.empty((4, 64), dtype=torch.bfloat16, device="cuda")
+    Kmod.gap_fwd(x, g)
+    e_gap = _rel_err(g, x.float().mean((1, 2)))
+    dxg = torch.empty_like(x)
+    Kmod.gap_bwd(g, dxg)
+    e_gapb = _rel_err(dxg, (g.float() / 256)[:, None, None, :].expand(4, 16, 16, 64))
+    # 2x2 average pool
+    a = torch.empty((4, 8, 8, 64), dtype=torch.bfloat16, device="cuda")
+    Kmod.avgpool2_fwd(x, a)
+    e_ap = _rel_err(a, F.avg_pool2d(x.float().permute(0, 3, 1, 2), 2).permute(0, 2, 3, 1))
+    dxa = torch.empty_like(x)
+    Kmod.avgpool2_bwd(a, dxa)
+    e_apb = _rel_err(dxa, (a.float() / 4).repeat_interleave(2, 1).repeat_interleave(2, 2))
+    torch.cuda.synchronize()
+    errs = dict(maxpool_bwd=e_mp, gap=e_gap, gap_bwd=e_gapb, avgpool=e_ap, avgpool_bwd=e_apb)
+    assert all(v < 1e-2 for v in errs.values()), errs
+    return errs
+
+
+def check_ce_topk(B=64, ncls=1000, topk=5):
+    Kmod = _K()
+    logits = _bf16(B, ncls, scale=2.0, seed=12)
+    target = torch.randint(0, ncls, (B,), device="cuda")
+    logits[0, target[0]] = 50.0  # a certain top-1 hit
+    accum = torch.zeros(3, device="cuda")
+    dl = torch.empty_like(logits)
+    Kmod.ce_topk(logits, target, dl, accum, topk, 1.0 / B)
+    lr = logits.float().clone().requires_grad_(True)
+    loss = F.cross_entropy(lr, target)
+    loss.backward()
+    top = lr.topk(topk, 1).indices
+    h1 = (top[:, 0] == target).sum().item()
+    hk = (top == target[:, None]).any(1).sum().item()
+    torch.cuda.synchronize()
+    e_loss = abs(accum[0].item() / B - loss.item()) / abs(loss.item())
+    e_grad = _rel_err(dl, lr.grad)
+    assert e_loss < 1e-3 and e_grad < 2e-2, (e_loss, e_grad)
+    assert int(accum[1].item()) == h1 and int(accum[2].item()) == hk, (accum.tolist(), h1, hk)
+    return {"loss_err": e_loss, "grad_err": e_grad, "top1": h1, "topk": hk}
+
+
+def check_sgd(n=4096 * 8 + 64, steps=3):
+    Kmod = _K()
+    torch.manual_seed(0)
+    w = torch.randn(n, device="cuda")
+    ref = torch.nn.Parameter(w.clone())
+    opt = torch.optim.SGD([ref], lr=0.1, momentum=0.9, nesterov=True, weight_decay=5e-5)
+    master, mom = w.clone(), torch.zeros(n, device="cuda")
+    w16 = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    for s in range(steps):
+        g = torch.randn(n, device="cuda")
+        ref.grad = g.clone()
+        opt.step()
+        grad = g.clone()
+        Kmod.sgd_local(master, mom, grad, w16, 0, n, 0.1, 0.9, 0.0, 5e-5, True, s == 0, 1.0, True)
+        assert float(grad.abs().max()) == 0.0, "gradient buffer was not zeroed"
+    torch.cuda.synchronize()
+    e_w = _rel_err(master, ref.data)
+    e_m = _rel_err(mom, opt.state[ref]["momentum_buffer"])
+    e_16 = _rel_err(w16, ref.data)
+    assert e_w < 1e-6 and e_m < 1e-6 and e_16 < 1e-2, (e_w, e_m, e_16)
+    return {"master": e_w, "momentum": e_m, "bf16": e_16}
+
+
+def check_stem():
+    Kmod = _K()
+    x = torch.randn(2, 3, 32, 32, device="cuda")
+    P = Q = 16
+    patches = torch.empty((2 * P * Q, 1, 1, 160), dtype=torch.bfloat16, device="cuda")
+    Kmod.stem_im2col(x, patches, 7, 7, 2, 3, P, Q)
+    ref = F.unfold(x, 7, padding=3, stride=2)  # [N, C*49, L] ordered (c, r, s)
+    ref = ref.view(2, 3, 49, P * Q).permute(0, 3, 2, 1).reshape(2 * P * Q, 147)  # -> (r,s,c)
+    torch.cuda.synchronize()
+    e = _rel_err(patches.view(-1, 160)[:, :147], ref.to(torch.bfloat16))
+    assert e < 1e-6 and float(patches.view(-1, 160)[:, 147:].float().abs().max()) == 0.0, e
+    out = torch.empty((2, 32, 32, 3), dtype=torch.bfloat16, device="cuda")
+    Kmod.nchw_to_nhwc(x, out)
+    assert _rel_err(out, x.permute(0, 2, 3, 1).to(torch.bfloat16)) < 1e-6
+    return {"im2col": e}
+
+
+# ---------------------------------------------------------------------------------------------- end to end
+def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_classes=16, tol=0.08):
+    """Same weights, same data: the native engine's loss trajectory must track the fp32 torch path."""
+    import copy
+    from . import models
+    from .parallel.native_engine import NativeEngine
+    from .trainer import TorchEngine
+    torch.manual_seed(0)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    net_a = models.build_model(arch, num_classes=num_classes).to(dev)
+    net_b = copy.deepcopy(net_a)
+    eng = NativeEngine(net_a, dev)
+    opt = eng.make_optimizer(lr=0.05, momentum=0.9, weight_decay=5e-5, dampening=0.0, nesterov=True)
+    ref = TorchEngine(net_b)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-5, nesterov=True)
+    eng.train(), ref.train()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    losses = []
+    for _ in range(steps):
+        x = torch.randn(batch, 3, size, size, device=dev, generator=g)
+        y = torch.randint(0, num_classes, (batch,), device=dev, generator=g)
+        la, _, _ = eng.train_step(x, y, opt, 5)
+        lb, _, _ = ref.train_step(x, y, ropt, 5)
+        losses.append((float(la), float(lb)))
+    torch.cuda.synchronize()
+    rel = max(abs(a - b) / max(abs(b), 1e-3) for a, b in losses)
+    # parameters after the steps (bf16 compute vs fp32): compare the stem-far fc weight loosely
+    pa = dict(net_a.named_parameters())
+    pb = dict(net_b.named_parameters())
+    last = [k for k in pa if k.endswith("weight")][-1]
+    drift = _rel_err(pa[last].data, pb[last].data)
+    assert all(l[0] == l[0] for l in losses), f"NaN loss {losses}"
+    assert rel < tol, f"loss trajectories diverge: {losses}"
+    return {"losses": losses, "max_rel_loss_diff": rel, "last_weight_drift": drift}

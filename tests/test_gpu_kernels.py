@@ -1,0 +1,59 @@
+"""GPU numerics: every sm_100a kernel against a plain PyTorch fp32 reference of the same op (run on the B200 box)."""
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def test_extension_loads_and_is_in_tree():
+    import os
+    from distribuuuu_b200.ops import build
+    mod = build.load()
+    assert os.path.dirname(os.path.abspath(mod.__file__)).endswith(os.path.join("distribuuuu_b200", "_ext"))
+
+
+def _cases():
+    from distribuuuu_b200.selftest import CONV_CASES
+    return sorted(CONV_CASES)
+
+
+@pytest.mark.parametrize("name", _cases())
+def test_conv_gemm_tcgen05(name):
+    from distribuuuu_b200 import selftest
+    selftest.check_conv_case(name)
+
+
+@pytest.mark.parametrize("act,residual,C", [("relu", True, 64), (None, False, 256), ("silu", False, 24), ("relu", False, 2048)])
+def test_batchnorm_kernels(act, residual, C):
+    from distribuuuu_b200 import selftest
+    selftest.check_bn(act=act, residual=residual, C=C)
+
+
+def test_pool_kernels():
+    from distribuuuu_b200 import selftest
+    selftest.check_pools()
+
+
+def test_softmax_ce_topk_kernel():
+    from distribuuuu_b200 import selftest
+    selftest.check_ce_topk()
+
+
+def test_fused_sgd_matches_torch_optim():
+    from distribuuuu_b200 import selftest
+    selftest.check_sgd()
+
+
+def test_stem_im2col_and_layout_conversion():
+    from distribuuuu_b200 import selftest
+    selftest.check_stem()
+
+
+@pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
+def test_native_engine_tracks_fp32_reference(arch):
+    from distribuuuu_b200 import selftest
+    selftest.check_engine_vs_torch(arch, batch=8, size=64)
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()

@@ -1,0 +1,72 @@
+#!/usr/bin/env python
+"""Run every kernel self-test in its own subprocess (timeout each) and write gpurun_out/selftest.json.
+A trapping / hanging kernel therefore costs one check, not the whole GPU session.
+
+    python tools/gpu_selftest.py            # all checks
+    python tools/gpu_selftest.py --only fprop_3x3 bn_relu_res
+    python tools/gpu_selftest.py --run NAME  # (internal) run one check in this process
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def registry():
+    from distribuuuu_b200 import selftest as st
+    checks = {name: (lambda n=name: st.check_conv_case(n)) for name in st.CONV_CASES}
+    checks.update({
+        "bn_relu_res": lambda: st.check_bn(act="relu", residual=True),
+        "bn_none": lambda: st.check_bn(act=None, residual=False, C=256),
+        "bn_silu_c24": lambda: st.check_bn(act="silu", residual=False, C=24),
+        "pools": st.check_pools,
+        "ce_topk": st.check_ce_topk,
+        "sgd": st.check_sgd,
+        "stem": st.check_stem,
+        "engine_resnet18": lambda: st.check_engine_vs_torch("resnet18", batch=16, size=64),
+        "engine_resnet50": lambda: st.check_engine_vs_torch("resnet50", batch=8, size=64),
+    })
+    return checks
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--run")
+    ap.add_argument("--only", nargs="*")
+    ap.add_argument("--timeout", type=int, default=180)
+    ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "selftest.json"))
+    a = ap.parse_args()
+    if a.run:
+        res = registry()[a.run]()
+        print("RESULT " + json.dumps(res))
+        return
+    names = a.only or list(registry())
+    os.makedirs(os.path.dirname(a.out), exist_ok=True)
+    results = {}
+    for name in names:
+        t0 = time.time()
+        try:
+            p = subprocess.run([sys.executable, __file__, "--run", name], capture_output=True, text=True, timeout=a.timeout)
+            ok = p.returncode == 0
+            line = [l for l in p.stdout.splitlines() if l.startswith("RESULT ")]
+            results[name] = {"ok": ok, "sec": round(time.time() - t0, 1),
+                             "result": json.loads(line[-1][7:]) if line else None,
+                             "err": None if ok else (p.stderr[-1500:] + p.stdout[-500:])}
+        except subprocess.TimeoutExpired:
+            results[name] = {"ok": False, "sec": a.timeout, "err": "timeout"}
+        print(f"{'PASS' if results[name]['ok'] else 'FAIL'} {name} {results[name].get('result')}", flush=True)
+        if not results[name]["ok"]:
+            print("   " + (results[name]["err"] or "").replace("\n", "\n   ")[-1200:], flush=True)
+        with open(a.out, "w") as f:
+            json.dump(results, f, indent=1)
+    n_ok = sum(r["ok"] for r in results.values())
+    print(f"{n_ok}/{len(results)} checks passed")
+
+
+if __name__ == "__main__":
+    main()
