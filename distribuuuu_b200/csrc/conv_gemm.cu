@@ -122,7 +122,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             else
               tma_load_3d(dst_a, &map_a, bar, kb * BK, 0, w.m0);
             const int btap = p.b_flip_taps ? (p.taps - 1 - tap) : tap;
-            if (p.b_nbox == 1) {
+            if (p.kind == KIND_FPROP) {
               tma_load_3d(dst_b, &map_b, bar, kb * BK, btap, w.n0);          // K-major weights [N][tap][K]
             } else {
               for (int j = 0; j < p.b_nbox; ++j)                              // MN-major weights [K][tap][N]

@@ -35,7 +35,7 @@ class ConvFn(torch.autograd.Function):
     """Implicit-GEMM convolution (fprop / dgrad / wgrad on tcgen05), optional BN-statistics epilogue."""
 
     @staticmethod
-    def forward(ctx, x, eng, conv, stats):
+    def forward(ctx, x, eng, conv, stats, anchor):
         K = eng.K
         xh = _nhwc(x)
         w = eng.w16_krsc(conv.weight)
@@ -70,7 +70,7 @@ class ConvFn(torch.autograd.Function):
             dx = _nchw_view(dxh)
         # only now: the bucket's fused update overwrites the bf16 weights the dgrad above still reads
         eng.mark_ready(conv.weight)
-        return dx, None, None, None
+        return dx, None, None, None, None
 
 
 def _strided_dgrad(K, dyh, w, x_shape, s, p, d):
@@ -92,7 +92,7 @@ class StemConvFn(torch.autograd.Function):
     tcgen05 GEMM; wgrad is the same GEMM transposed.  The input needs no gradient."""
 
     @staticmethod
-    def forward(ctx, x_nchw_f32, eng, conv, stats):
+    def forward(ctx, x_nchw_f32, eng, conv, stats, anchor):
         K = eng.K
         N, C, H, W = x_nchw_f32.shape
         Kc, _, R, S = conv.weight.shape
@@ -123,7 +123,7 @@ class StemConvFn(torch.autograd.Function):
         K.conv_wgrad(dyh, patches, dwp, 1, 0, 1)
         K.unpad_add(dwp, eng.grad_flat_view(conv.weight), Kc, kdim, kpad)
         eng.mark_ready(conv.weight)
-        return None, None, None, None
+        return None, None, None, None, None
 
 
 class BnActFn(torch.autograd.Function):
@@ -131,7 +131,7 @@ class BnActFn(torch.autograd.Function):
     passes backward; SyncBN statistics are exchanged through peer memory inside the same kernels."""
 
     @staticmethod
-    def forward(ctx, y, residual, eng, bn, act, stats_slot, training):
+    def forward(ctx, y, residual, eng, bn, act, stats_slot, training, anchor):
         K = eng.K
         yh = _nhwc(y)
         N, H, W, C = yh.shape
@@ -175,12 +175,12 @@ class BnActFn(torch.autograd.Function):
         if bn.affine:
             eng.mark_ready(bn.weight)
             eng.mark_ready(bn.bias)
-        return _nchw_view(dy), (_nchw_view(dres) if dres is not None else None), None, None, None, None, None
+        return _nchw_view(dy), (_nchw_view(dres) if dres is not None else None), None, None, None, None, None, None
 
 
 class LinearFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, eng, fc):
+    def forward(ctx, x, eng, fc, anchor):
         K = eng.K
         x2 = x.contiguous()
         B, Cin = x2.shape
@@ -208,7 +208,7 @@ class LinearFn(torch.autograd.Function):
         eng.mark_ready(fc.weight)
         if fc.bias is not None:
             eng.mark_ready(fc.bias)
-        return dx.view(B, Cin), None, None
+        return dx.view(B, Cin), None, None, None
 
 
 class MaxPoolFn(torch.autograd.Function):
@@ -328,9 +328,9 @@ class NativeOps:
         slot = eng.fwd_slot(bn) if training else None
         stats = slot.tensor if slot is not None else None
         if self._is_stem(conv, x):
-            y = StemConvFn.apply(x, eng, conv, stats)
+            y = StemConvFn.apply(x, eng, conv, stats, eng.anchor)
         elif self._native_conv_ok(conv, x):
-            y = ConvFn.apply(x, eng, conv, stats)
+            y = ConvFn.apply(x, eng, conv, stats, eng.anchor)
         else:
             y = self._torch_conv(x, conv)
             if stats is not None:
@@ -340,7 +340,7 @@ class NativeOps:
             if residual is not None:
                 y = y + residual
             return _torch_act(y, act)
-        return BnActFn.apply(y, residual, eng, bn, act, slot, training)
+        return BnActFn.apply(y, residual, eng, bn, act, slot, training, eng.anchor)
 
     def bn_act(self, x, bn, act):
         eng = self.eng
@@ -350,11 +350,11 @@ class NativeOps:
         if slot is not None:
             xh = _nhwc(x)
             eng.K.bn_stats(xh.view(-1, xh.shape[-1]), slot.tensor)
-        return BnActFn.apply(x, None, eng, bn, act, slot, training)
+        return BnActFn.apply(x, None, eng, bn, act, slot, training, eng.anchor)
 
     def linear(self, x, fc):
         if x.dtype == torch.bfloat16 and fc.in_features % 8 == 0 and fc.out_features % 8 == 0:
-            return LinearFn.apply(x, self.eng, fc)
+            return LinearFn.apply(x, self.eng, fc, self.eng.anchor)
         w = self.eng.w16_leaf(fc.weight)
         b = self.eng.w16_leaf(fc.bias) if fc.bias is not None else None
         return F.linear(x.to(torch.bfloat16), w, b)

@@ -124,6 +124,8 @@ class NativeEngine(nn.Module):
         self._bn_stepped: List[torch.Tensor] = []
         self._step_parity = 0
         self.comm_stream = torch.cuda.Stream(device)
+        # autograd anchor: lets Functions whose tensor inputs carry no grad (first layer) still get a backward call
+        self.anchor = torch.zeros((), device=device, requires_grad=True)
         self._build_flat_storage()
         self._build_bn_slots()
         self._setup_comm()

@@ -98,6 +98,8 @@ CONV_CASES = {
     "fprop_3x3_small": ("fprop", dict(N=1, H=7, W=7, C=64, K=64, R=3, pad=1)),
     "fprop_5x5_dil": ("fprop", dict(N=2, H=12, W=12, C=64, K=64, R=3, pad=2, dil=2)),
     "dgrad_1x1": ("dgrad", dict(N=2, H=28, W=28, C=64, K=256, R=1, pad=0)),
+    "dgrad_1x1_c64_k512": ("dgrad", dict(N=2, H=14, W=14, C=64, K=512, R=1, pad=0)),
+    "dgrad_3x3_c128": ("dgrad", dict(N=2, H=14, W=14, C=128, K=192, R=3, pad=1)),
     "dgrad_1x1_wide": ("dgrad", dict(N=2, H=7, W=7, C=512, K=2048, R=1, pad=0)),
     "dgrad_3x3": ("dgrad", dict(N=4, H=14, W=14, C=256, K=256, R=3, pad=1)),
     "dgrad_3x3_56": ("dgrad", dict(N=2, H=56, W=56, C=64, K=64, R=3, pad=1)),
