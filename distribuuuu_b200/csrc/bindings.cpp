@@ -191,8 +191,9 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
                        : im2col_map_4d(x.data_ptr(), g.N, g.H, g.W, g.C, -pad, -pad, pad - (g.S - 1) * dil,
                                        pad - (g.R - 1) * dil, stride, 64, 128);
   CUtensorMap mb = tiled_map_3d(w.data_ptr(), g.C, p.taps, g.K, g.C, (uint64_t)p.taps * g.C, 64, 1, bn);
+  CUtensorMap mo = tiled_map_3d(out.data_ptr(), g.K, M, 1, g.K, (uint64_t)g.K * M, 64, 32, 1);
   const int grid = std::min(p.total_items, num_sms());
-  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &p, bn, grid, cur_stream()));
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &p, bn, grid, cur_stream()));
 }
 
 // ---------------------------------------------------------------------------------------------- conv dgrad (stride 1)
@@ -229,8 +230,9 @@ void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64
                                              padp_h - (R - 1) * dil, 1, 64, 128);
   // weights viewed as (C inner, taps, K): MN-major B boxes of [64 k-rows (Cout)][64 n (Cin)]
   CUtensorMap mb = tiled_map_3d(w.data_ptr(), C, p.taps, K, C, (uint64_t)p.taps * C, 64, 1, 64);
+  CUtensorMap mo = tiled_map_3d(dx.data_ptr(), C, M, 1, C, (uint64_t)C * M, 64, 32, 1);
   const int grid = std::min(p.total_items, num_sms());
-  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &p, bn, grid, cur_stream()));
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &p, bn, grid, cur_stream()));
 }
 
 // ---------------------------------------------------------------------------------------------- conv wgrad
@@ -269,7 +271,7 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
                              : im2col_map_4d(x.data_ptr(), N, H, W, C, -pad, -pad, pad - (S - 1) * dil,
                                              pad - (R - 1) * dil, stride, 64, 64);
   const int grid = std::min(p.total_items, num_sms());
-  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &p, bn, grid, cur_stream()));
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &ma, &p, bn, grid, cur_stream()));
 }
 
 // ---------------------------------------------------------------------------------------------- peer contexts

@@ -28,7 +28,8 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages; 128/256/512 are all legal allocations
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 4 /*epilogue warps*/ * 2 /*double buffer*/ * 4096;  // 32 rows x 128 B each
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
 struct PixelCoord { int w, h, n; };
@@ -66,14 +67,15 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + C::kStages * kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kStages * C::kStageBytes);
+  uint8_t* smem_stage_out = smem + C::kStages * C::kStageBytes;  // epilogue staging (1024-aligned)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage_out + C::kStagingBytes);
   uint64_t* full_bar = bars;                       // [kStages] TMA -> MMA
   uint64_t* empty_bar = bars + C::kStages;         // [kStages] MMA -> TMA
   uint64_t* tmem_full = bars + 2 * C::kStages;     // [2] MMA -> epilogue
@@ -86,6 +88,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
+    if (EPI == EPI_BF16) tma_prefetch_desc(&map_out);
     for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiThreads); }
     fence_barrier_init();
@@ -176,96 +179,118 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int quarter = warp & 3;                 // TMEM lanes [32*quarter, 32*quarter+32)
     const int row_in_tile = quarter * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
-    float st_sum[BN / 32], st_sq[BN / 32];
-#pragma unroll
-    for (int c = 0; c < BN / 32; ++c) { st_sum[c] = 0.f; st_sq[c] = 0.f; }
-    int st_nb = -1;
-    const bool want_stats = (EPI == EPI_BF16) && (p.stats != nullptr);
 
-    auto flush_stats = [&](int nb) {
-      if (nb < 0) return;
+    if constexpr (EPI == EPI_BF16) {
+      // TMEM -> registers -> bf16 -> 128B-swizzled smem (32 rows x 64 cols per warp) -> TMA store (coalesced,
+      // clipped at the M/N edges).  The BN statistics are column sums read back from that same smem tile:
+      // lane l owns columns 2l, 2l+1 of the 64-column chunk, 32 conflict-free LDS.32 per chunk.
+      constexpr int NCH = BN / 64;
+      uint8_t* my_stage = smem_stage_out + (warp - 2) * 8192;
+      float st_sum[NCH][2], st_sq[NCH][2];
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        const int col = nb * BN + c * 32 + lane;
-        if (col < p.N) {
-          atomicAdd(p.stats + col, st_sum[c]);
-          atomicAdd(p.stats + p.N + col, st_sq[c]);
-        }
-        st_sum[c] = 0.f; st_sq[c] = 0.f;
-      }
-    };
+      for (int c = 0; c < NCH; ++c) { st_sum[c][0] = st_sum[c][1] = 0.f; st_sq[c][0] = st_sq[c][1] = 0.f; }
+      int st_nb = -1;
+      const bool want_stats = (p.stats != nullptr);
+      int buf = 0;
 
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-      const WorkItem w = decode_item(p, item, BN);
-      if (want_stats && w.nb != st_nb) { flush_stats(st_nb); st_nb = w.nb; }
-      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
-      tc_fence_after();
-      const int row = w.m0 + row_in_tile;
-      const bool row_ok = row < p.M;
-      const bool has_k = w.it_end > w.it_begin;
+      auto flush_stats = [&](int nb) {
+        if (nb < 0) return;
 #pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = w.n0 + c * 32;
-        if (!has_k) {
+        for (int c = 0; c < NCH; ++c) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = 0u;
+          for (int h = 0; h < 2; ++h) {
+            const int col = nb * BN + c * 64 + 2 * lane + h;
+            if (col < p.N) {
+              atomicAdd(p.stats + col, st_sum[c][h]);
+              atomicAdd(p.stats + p.N + col, st_sq[c][h]);
+            }
+            st_sum[c][h] = 0.f; st_sq[c][h] = 0.f;
+          }
         }
-        if constexpr (EPI == EPI_BF16) {
+      };
+
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const WorkItem w = decode_item(p, item, BN);
+        if (want_stats && w.nb != st_nb) { flush_stats(st_nb); st_nb = w.nb; }
+        mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < NCH; ++c) {
+          const int col0 = w.n0 + c * 64;
+          if (col0 >= p.N) continue;                 // warp-uniform: chunk entirely past the N edge
+          uint8_t* sbuf = my_stage + buf * 4096;
+          if (lane == 0) bulk_wait_group_read<1>();   // the TMA store that last read this buffer has drained
+          __syncwarp();
+          uint32_t v[64];
+          {
+            uint32_t lo[32], hi[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 64;
+            tmem_ld_32x32b_x32(taddr, lo);
+            tmem_ld_32x32b_x32(taddr + 32, hi);
+            tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
+          }
           if (p.bias != nullptr) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 64; ++j) {
               const int col = col0 + j;
               const float b = (col < p.N) ? __ldg(p.bias + col) : 0.f;
               v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
             }
           }
-          if (row_ok && col0 < p.N) {
-            __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)row * p.ldo + col0;
-            if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 pk;
-                pk.x = pack_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
-                pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
-                pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
-                pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-                reinterpret_cast<uint4*>(dst)[g] = pk;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) dst[j] = __float2bfloat16_rn(__uint_as_float(v[j]));
-            }
+          for (int g = 0; g < 8; ++g) {               // 8 x 16-byte pieces of this thread's 128-byte row
+            uint4 pk;
+            pk.x = pack_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
+            pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+            pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+            pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((g ^ (lane & 7)) << 4)) = pk;
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_3d(&map_out, smem_u32(sbuf), col0, w.m0 + quarter * 32, 0);
+            bulk_commit_group();
           }
           if (want_stats) {
-            // statistics of the values the next layer will actually read (bf16-rounded); rows past M are zero
-            float s1[32], s2[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float f = row_ok ? __bfloat162float(__float2bfloat16_rn(__uint_as_float(v[j]))) : 0.f;
-              s1[j] = f; s2[j] = f * f;
+            float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+            const int rows_valid = min(32, p.M - (w.m0 + quarter * 32));   // rows past M hold conv-of-zero-padding junk? no: zeros, but be exact
+#pragma unroll 8
+            for (int r = 0; r < 32; ++r) {
+              const uint32_t wd = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+              const float f0 = (r < rows_valid) ? __uint_as_float(wd << 16) : 0.f;
+              const float f1 = (r < rows_valid) ? __uint_as_float(wd & 0xffff0000u) : 0.f;
+              a0 += f0; q0 = fmaf(f0, f0, q0);
+              a1 += f1; q1 = fmaf(f1, f1, q1);
             }
-            // butterfly transpose-reduce: afterwards lane l holds the column-(c*32+l) sum over the warp's 32 rows
-#pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) {
-              const bool upper = (lane & off) != 0;
-#pragma unroll
-              for (int i = 0; i < off; ++i) {
-                const float send1 = upper ? s1[i] : s1[i + off];
-                const float keep1 = upper ? s1[i + off] : s1[i];
-                s1[i] = keep1 + __shfl_xor_sync(0xffffffffu, send1, off);
-                const float send2 = upper ? s2[i] : s2[i + off];
-                const float keep2 = upper ? s2[i + off] : s2[i];
-                s2[i] = keep2 + __shfl_xor_sync(0xffffffffu, send2, off);
-              }
-            }
-            st_sum[c] += s1[0];
-            st_sq[c] += s2[0];
+            st_sum[c][0] += a0; st_sum[c][1] += a1; st_sq[c][0] += q0; st_sq[c][1] += q1;
           }
-        } else {  // EPI_F32_RED: split-K partial sums into fp32 dW[M][taps][N]
+          buf ^= 1;
+        }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+      if (want_stats) flush_stats(st_nb);
+      if (lane == 0) bulk_wait_group<0>();            // all stores complete before the CTA may exit
+      __syncwarp();
+    } else {
+      // EPI_F32_RED: split-K partial sums into fp32 dW[M][taps][N]
+      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const WorkItem w = decode_item(p, item, BN);
+        mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+        tc_fence_after();
+        const int row = w.m0 + row_in_tile;
+        const bool row_ok = row < p.M;
+        const bool has_k = w.it_end > w.it_begin;
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
+          tmem_ld_wait();
+          const int col0 = w.n0 + c * 32;
           if (row_ok && col0 < p.N && has_k) {
             float* dst = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + (long long)w.tap * p.tap_stride + col0;
             if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
@@ -282,12 +307,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             }
           }
         }
+        tc_fence_before();
+        mbar_arrive(smem_u32(&tmem_empty[acc]));
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      tc_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty[acc]));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (want_stats) flush_stats(st_nb);
   }
 
   tc_fence_before();
@@ -296,8 +320,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 template <int BN, int EPI>
-static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const ConvGemmParams& p, int grid,
-                              cudaStream_t stream) {
+static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+                              const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   auto kern = conv_gemm_kernel<BN, EPI>;
   static bool configured = false;
@@ -306,24 +330,24 @@ static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, cons
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ma, mb, p);
+  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ma, mb, mo, p);
   return cudaGetLastError();
 }
 
 }  // namespace b200
 
-extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap* map_b, const ConvGemmParams* p,
-                                     int bn, int grid, cudaStream_t stream) {
+extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap* map_b, const CUtensorMap* map_out,
+                                     const ConvGemmParams* p, int bn, int grid, cudaStream_t stream) {
   using namespace b200;
   cudaError_t e = cudaErrorInvalidValue;
   if (p->epi == EPI_BF16) {
-    if (bn == 64) e = launch_one<64, EPI_BF16>(*map_a, *map_b, *p, grid, stream);
-    else if (bn == 128) e = launch_one<128, EPI_BF16>(*map_a, *map_b, *p, grid, stream);
-    else if (bn == 256) e = launch_one<256, EPI_BF16>(*map_a, *map_b, *p, grid, stream);
+    if (bn == 64) e = launch_one<64, EPI_BF16>(*map_a, *map_b, *map_out, *p, grid, stream);
+    else if (bn == 128) e = launch_one<128, EPI_BF16>(*map_a, *map_b, *map_out, *p, grid, stream);
+    else if (bn == 256) e = launch_one<256, EPI_BF16>(*map_a, *map_b, *map_out, *p, grid, stream);
   } else {
-    if (bn == 64) e = launch_one<64, EPI_F32_RED>(*map_a, *map_b, *p, grid, stream);
-    else if (bn == 128) e = launch_one<128, EPI_F32_RED>(*map_a, *map_b, *p, grid, stream);
-    else if (bn == 256) e = launch_one<256, EPI_F32_RED>(*map_a, *map_b, *p, grid, stream);
+    if (bn == 64) e = launch_one<64, EPI_F32_RED>(*map_a, *map_b, *map_out, *p, grid, stream);
+    else if (bn == 128) e = launch_one<128, EPI_F32_RED>(*map_a, *map_b, *map_out, *p, grid, stream);
+    else if (bn == 256) e = launch_one<256, EPI_F32_RED>(*map_a, *map_b, *map_out, *p, grid, stream);
   }
   return (int)e;
 }

@@ -33,5 +33,7 @@ struct ConvGemmParams {
   int total_items;
 };
 
-extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap* map_b, const ConvGemmParams* p,
-                                     int bn, int grid, cudaStream_t stream);
+// map_out: 2-D tiled map over the bf16 output [M][N] (box 64 cols x 32 rows, 128B swizzle) for the TMA-store
+// epilogue; ignored (pass any valid map) for EPI_F32_RED.
+extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap* map_b, const CUtensorMap* map_out,
+                                     const ConvGemmParams* p, int bn, int grid, cudaStream_t stream);

@@ -16,6 +16,17 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(raw.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
+// raw 16-byte streaming load (kept in registers until all loads of an unrolled batch are issued)
+__device__ __forceinline__ uint4 ldg_stream(const __nv_bfloat16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
+}
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   BF8 raw;
 #pragma unroll
@@ -103,7 +114,7 @@ __device__ __forceinline__ void gather_stats(const PeerCtx& pc, const float* loc
 // (+ residual) + activation in ONE pass over the conv output.
 // grid: (ceil(C/8 / blockDim.x), row_chunks); block: (cvx, rows_per_block)
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_apply_kernel(BnApplyParams p) {
+__global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyParams p) {
   if (p.peer.world > 1 && p.training) peer_exchange_wait(p.peer);
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = cv * VEC;
@@ -143,19 +154,36 @@ __global__ void bn_apply_kernel(BnApplyParams p) {
       shift[i] = b - p.running_mean[c0 + i] * scale[i];
     }
   }
-  for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += (long long)gridDim.y * blockDim.y) {
-    float x[8];
-    load8(p.y + row * p.ldy + c0, x);
-    if (p.residual) {
-      float r[8];
-      load8(p.residual + row * p.ldr + c0, r);
+  constexpr int U = 4;  // rows in flight per thread: all loads of a batch are issued before any use
+  const long long rstride = (long long)gridDim.y * blockDim.y;
+  for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += U * rstride) {
+    uint4 ry[U], rr[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]) + r[i], p.act);
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]), p.act);
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + u * rstride;
+      if (r < p.rows) {
+        ry[u] = ldg_stream(p.y + r * p.ldy + c0);
+        if (p.residual) rr[u] = ldg_stream(p.residual + r * p.ldr + c0);
+      }
     }
-    store8(p.out + row * p.ldo + c0, x);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long r = row + u * rstride;
+      if (r < p.rows) {
+        float x[8];
+        unpack8f(ry[u], x);
+        if (p.residual) {
+          float q[8];
+          unpack8f(rr[u], q);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]) + q[i], p.act);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]), p.act);
+        }
+        store8(p.out + r * p.ldo + c0, x);
+      }
+    }
   }
 }
 
@@ -167,11 +195,21 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long r
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
   if (c0 < C) {
-    for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < rows; row += (long long)gridDim.y * blockDim.y) {
-      float x[8];
-      load8(y + row * ldy + c0, x);
+    constexpr int U = 4;
+    const long long rstride = (long long)gridDim.y * blockDim.y;
+    for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < rows; row += U * rstride) {
+      uint4 ry[U];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] += x[i]; b[i] = fmaf(x[i], x[i], b[i]); }
+      for (int u = 0; u < U; ++u) if (row + u * rstride < rows) ry[u] = ldg_stream(y + (row + u * rstride) * ldy + c0);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (row + u * rstride < rows) {
+          float x[8];
+          unpack8f(ry[u], x);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { a[i] += x[i]; b[i] = fmaf(x[i], x[i], b[i]); }
+        }
+      }
     }
   }
   // reduce over threadIdx.y through shared memory
@@ -196,45 +234,53 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long r
 // ------------------------------------------------------------------------------------------------
 // BN backward, pass 1: per-channel sum(dz) and sum(dz * xhat), dz = dout * act'(z), z recomputed from y.
 // ------------------------------------------------------------------------------------------------
-__global__ void bn_bwd_reduce_kernel(BnBwdParams p) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdParams p) {
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = cv * VEC;
   float a[8], b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
   if (c0 < p.C) {
-    float mean[8], invstd[8], g[8], be[8];
+    // xhat = y*invstd + nmi ;  z = y*scale + shift  (z only needed for the activation derivative)
+    float invstd[8], nmi[8], scale[8], shift[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      mean[i] = p.save_mean[c0 + i]; invstd[i] = p.save_invstd[c0 + i];
-      g[i] = p.gamma ? p.gamma[c0 + i] : 1.f; be[i] = p.beta ? p.beta[c0 + i] : 0.f;
+      const float mean = p.save_mean[c0 + i];
+      invstd[i] = p.save_invstd[c0 + i];
+      nmi[i] = -mean * invstd[i];
+      const float g = p.gamma ? p.gamma[c0 + i] : 1.f, be = p.beta ? p.beta[c0 + i] : 0.f;
+      scale[i] = g * invstd[i];
+      shift[i] = be - mean * scale[i];
     }
-    for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += (long long)gridDim.y * blockDim.y) {
-      float y[8], d[8];
-      load8(p.y + row * p.ldy + c0, y);
-      load8(p.dout + row * p.ldd + c0, d);
-      if (p.act != ACT_NONE) {
-        if (p.residual) {
-          float r[8];
-          load8(p.residual + row * p.ldr + c0, r);
+    constexpr int U = 4;
+    const long long rstride = (long long)gridDim.y * blockDim.y;
+    const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr);
+    for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += U * rstride) {
+      uint4 ry[U], rd[U], rr[U];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xh = (y[i] - mean[i]) * invstd[i];
-            d[i] *= act_bwd(fmaf(xh, g[i], be[i]) + r[i], p.act);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float xh = (y[i] - mean[i]) * invstd[i];
-            d[i] *= act_bwd(fmaf(xh, g[i], be[i]), p.act);
-          }
+      for (int u = 0; u < U; ++u) {
+        const long long r = row + u * rstride;
+        if (r < p.rows) {
+          ry[u] = ldg_stream(p.y + r * p.ldy + c0);
+          rd[u] = ldg_stream(p.dout + r * p.ldd + c0);
+          if (need_res) rr[u] = ldg_stream(p.residual + r * p.ldr + c0);
         }
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float xh = (y[i] - mean[i]) * invstd[i];
-        a[i] += d[i];
-        b[i] = fmaf(d[i], xh, b[i]);
+      for (int u = 0; u < U; ++u) {
+        if (row + u * rstride < p.rows) {
+          float y[8], d[8];
+          unpack8f(ry[u], y);
+          unpack8f(rd[u], d);
+          float q[8];
+          if (need_res) unpack8f(rr[u], q);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
+            a[i] += d[i];
+            b[i] = fmaf(d[i], fmaf(y[i], invstd[i], nmi[i]), b[i]);
+          }
+        }
       }
     }
   }
@@ -256,12 +302,13 @@ __global__ void bn_bwd_reduce_kernel(BnBwdParams p) {
 
 // BN backward, pass 2: dy = (dz - mean(dz) - xhat * mean(dz*xhat)) * gamma * invstd (means over all ranks for SyncBN);
 // also emits d(residual) = dz and the local dgamma / dbeta.
-__global__ void bn_bwd_apply_kernel(BnBwdParams p) {
+__global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdParams p) {
   if (p.peer.world > 1) peer_exchange_wait(p.peer);
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = cv * VEC;
   if (c0 >= p.C) return;
-  float mean[8], invstd[8], g[8], be[8], m_dz[8], m_dzx[8];
+  // dy = (dz - mean(dz) - xhat*mean(dz*xhat)) * gamma*invstd  ==  dz*scale + y*ca + cb
+  float scale[8], shift[8], ca[8], cb[8];
   {
     float s0[8], s1[8];
     gather_stats(p.peer, p.sums, p.sym_offset, p.C, c0, s0, s1);
@@ -269,9 +316,13 @@ __global__ void bn_bwd_apply_kernel(BnBwdParams p) {
     const bool writer = (blockIdx.y == 0 && threadIdx.y == 0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      mean[i] = p.save_mean[c0 + i]; invstd[i] = p.save_invstd[c0 + i];
-      g[i] = p.gamma ? p.gamma[c0 + i] : 1.f; be[i] = p.beta ? p.beta[c0 + i] : 0.f;
-      m_dz[i] = s0[i] * inv_n; m_dzx[i] = s1[i] * inv_n;
+      const float mean = p.save_mean[c0 + i], invstd = p.save_invstd[c0 + i];
+      const float g = p.gamma ? p.gamma[c0 + i] : 1.f, be = p.beta ? p.beta[c0 + i] : 0.f;
+      const float m_dz = s0[i] * inv_n, m_dzx = s1[i] * inv_n;
+      scale[i] = g * invstd;
+      shift[i] = be - mean * scale[i];
+      ca[i] = -invstd * m_dzx * scale[i];
+      cb[i] = -m_dz * scale[i] - mean * ca[i];
     }
     if (writer && p.dgamma) {
       // parameter gradients use the LOCAL sums (the gradient all-reduce averages them afterwards, as DDP does)
@@ -283,29 +334,41 @@ __global__ void bn_bwd_apply_kernel(BnBwdParams p) {
       }
     }
   }
-  for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += (long long)gridDim.y * blockDim.y) {
-    float y[8], d[8];
-    load8(p.y + row * p.ldy + c0, y);
-    load8(p.dout + row * p.ldd + c0, d);
-    float xh[8];
+  constexpr int U = 4;
+  const long long rstride = (long long)gridDim.y * blockDim.y;
+  const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr);
+  // iterate from the END of the tensor: the reduce pass finished there, so those lines are the likeliest L2 hits
+  for (long long k = (long long)blockIdx.y * blockDim.y + threadIdx.y; k < p.rows; k += U * rstride) {
+    uint4 ry[U], rd[U], rr[U];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) xh[i] = (y[i] - mean[i]) * invstd[i];
-    if (p.act != ACT_NONE) {
-      if (p.residual) {
-        float r[8];
-        load8(p.residual + row * p.ldr + c0, r);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] *= act_bwd(fmaf(xh[i], g[i], be[i]) + r[i], p.act);
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) d[i] *= act_bwd(fmaf(xh[i], g[i], be[i]), p.act);
+    for (int u = 0; u < U; ++u) {
+      const long long kk = k + u * rstride;
+      if (kk < p.rows) {
+        const long long r = p.rows - 1 - kk;
+        ry[u] = ldg_stream(p.y + r * p.ldy + c0);
+        rd[u] = ldg_stream(p.dout + r * p.ldd + c0);
+        if (need_res) rr[u] = ldg_stream(p.residual + r * p.ldr + c0);
       }
     }
-    if (p.dresidual) store8(p.dresidual + row * p.ldr + c0, d);
-    float o[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) o[i] = (d[i] - m_dz[i] - xh[i] * m_dzx[i]) * (g[i] * invstd[i]);
-    store8(p.dy + row * p.ldy + c0, o);
+    for (int u = 0; u < U; ++u) {
+      const long long kk = k + u * rstride;
+      if (kk < p.rows) {
+        const long long r = p.rows - 1 - kk;
+        float y[8], d[8], q[8];
+        unpack8f(ry[u], y);
+        unpack8f(rd[u], d);
+        if (need_res) unpack8f(rr[u], q);
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
+          o[i] = fmaf(d[i], scale[i], fmaf(y[i], ca[i], cb[i]));
+        }
+        if (p.dresidual) store8(p.dresidual + r * p.ldr + c0, d);
+        store8(p.dy + r * p.ldy + c0, o);
+      }
+    }
   }
 }
 
@@ -540,26 +603,30 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloa
 
 __global__ void stem_im2col_kernel(const float* __restrict__ x /*NCHW fp32*/, __nv_bfloat16* __restrict__ patches,
                                    int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad) {
-  // one thread per (pixel, r): writes S*C contiguous bf16 (row layout [r][s][c], matching weights [Cout][R][S][C])
-  const long long total = (long long)N * P * Q * (R + 1);  // the extra "r == R" slot zero-fills the K padding
+  // one thread per 8 consecutive patch elements (one 16-byte store): row layout [r][s][c] (+ zero padding to Kpad),
+  // matching weights [Cout][R][S][C].  Stores are fully coalesced; the fp32 image is re-read through L1/L2.
+  const int vec_per_row = Kpad / 8;
+  const long long total = (long long)N * P * Q * vec_per_row;
+  const int kdim = R * S * C;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int r = idx % (R + 1);
-    long long pix = idx / (R + 1);
-    __nv_bfloat16* dst = patches + pix * Kpad;
-    if (r == R) {
-      for (int k = R * S * C; k < Kpad; ++k) dst[k] = __float2bfloat16_rn(0.f);
-      continue;
-    }
-    const int q = pix % Q; long long t = pix / Q;
+    const int j8 = idx % vec_per_row;
+    const long long pix = idx / vec_per_row;
+    const int q = pix % Q; const long long t = pix / Q;
     const int ph = t % P; const int n = t / P;
-    const int h = ph * stride - pad + r;
-    dst += r * S * C;
-    for (int s = 0; s < S; ++s) {
-      const int w = q * stride - pad + s;
-      const bool ok = (h >= 0 && h < H && w >= 0 && w < W);
-      for (int c = 0; c < C; ++c)
-        dst[s * C + c] = __float2bfloat16_rn(ok ? x[(((long long)n * C + c) * H + h) * W + w] : 0.f);
+    float v[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = j8 * 8 + i;
+      float val = 0.f;
+      if (k < kdim) {
+        const int c = k % C; const int rs = k / C;
+        const int s = rs % S, r = rs / S;
+        const int h = ph * stride - pad + r, w = q * stride - pad + s;
+        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((long long)n * C + c) * H + h) * W + w);
+      }
+      v[i] = val;
     }
+    store8(patches + pix * Kpad + j8 * 8, v);
   }
 }
 
@@ -673,7 +740,7 @@ extern "C" int b200_nchw_to_nhwc(const float* x, void* out, int N, int C, int H,
 }
 extern "C" int b200_stem_im2col(const float* x, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S,
                                 int stride, int pad, int Kpad, cudaStream_t s) {
-  stem_im2col_kernel<<<ew_grid((long long)N * P * Q * (R + 1), 256), 256, 0, s>>>(x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad);
+  stem_im2col_kernel<<<ew_grid((long long)N * P * Q * (Kpad / 8), 256), 256, 0, s>>>(x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_pad_rows(const void* src, void* dst, int rows, int cols, int cols_pad, cudaStream_t s) {

@@ -43,6 +43,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=7)
+    ap.add_argument("--shapes", type=int, nargs="*", help="indices into SHAPES (default: all)")
+    ap.add_argument("--no-cudnn", action="store_true")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "conv_shapes.json"))
     a = ap.parse_args()
     from distribuuuu_b200.ops import build
@@ -56,7 +58,8 @@ def main():
         pass
     rows, tot = [], {"ours": 0.0, "cudnn": 0.0}
     B = a.batch
-    for cin, cout, k, s, h, cnt in SHAPES:
+    shapes = [SHAPES[i] for i in a.shapes] if a.shapes else SHAPES
+    for cin, cout, k, s, h, cnt in shapes:
         pad = k // 2
         p = (h + 2 * pad - k) // s + 1
         x = torch.randn(B, h, h, cin, device="cuda").to(torch.bfloat16)
@@ -70,6 +73,9 @@ def main():
         xc, wc, dyc = x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), dy.permute(0, 3, 1, 2)
         r = {"shape": f"{cin}->{cout} k{k} s{s} {h}->{p}", "count": cnt, "gflop": flops / 1e9}
         r["fprop_ours_ms"] = timeit(lambda: K.conv_fprop(x, w, y, st, None, s, pad, 1), a.iters, flush)
+        if a.no_cudnn:
+            rows.append(r)
+            continue
         r["fprop_cudnn_ms"] = timeit(lambda: F.conv2d(xc, wc, None, s, pad), a.iters, flush)
         r["wgrad_ours_ms"] = timeit(lambda: K.conv_wgrad(dy, x, dw, s, pad, 1), a.iters, flush)
         r["wgrad_cudnn_ms"] = timeit(lambda: torch.ops.aten.convolution_backward(
