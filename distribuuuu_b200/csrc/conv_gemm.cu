@@ -7,8 +7,8 @@
 //
 // Replaces what the reference reaches through cuDNN/cuBLAS (reference resnet.py:36-54 convs, :211 fc; SURVEY G1-G3,G10).
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-5 = epilogue
-// (TMEM lane quarter = warp_idx % 4).  smem ring of kStages {A 128x64, B BNx64} bf16 tiles; TMEM holds two
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2-9 = epilogue
+// (TMEM lane quarter = warp_idx % 4, two warps per quarter splitting the columns).  smem ring of kStages {A 128x64, B BNx64} bf16 tiles; TMEM holds two
 // accumulator stages of BN fp32 columns so the epilogue of tile i overlaps the MMAs of tile i+1.
 #include "common.cuh"
 #include "conv_gemm.h"
@@ -19,16 +19,17 @@ constexpr int BM = 128;
 constexpr int BK = 64;                       // reduction elements per smem stage (128 bytes of bf16)
 constexpr int kABytes = BM * BK * 2;         // 16 KB
 constexpr int kBoxBytes = 64 * BK * 2;       // one 64x64 MN-major box = 8 KB
-constexpr int kNumThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;                 // two per TMEM lane quarter: latency of one hides behind the other
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kNumThreads = 64 + kEpiThreads;
 
 template <int BN>
 struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages; 128/256/512 are all legal allocations
-  static constexpr int kStagingBytes = 4 /*epilogue warps*/ * 2 /*double buffer*/ * 4096;  // 32 rows x 128 B each
+  static constexpr int kStagingBytes = kEpiWarps * 2 /*double buffer*/ * 4096;  // 32 rows x 128 B each
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
@@ -181,22 +182,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     int acc = 0; uint32_t acc_phase = 0;
 
     if constexpr (EPI == EPI_BF16) {
-      // TMEM -> registers -> bf16 -> 128B-swizzled smem (32 rows x 64 cols per warp) -> TMA store (coalesced,
-      // clipped at the M/N edges).  The BN statistics are column sums read back from that same smem tile:
-      // lane l owns columns 2l, 2l+1 of the 64-column chunk, 32 conflict-free LDS.32 per chunk.
+      // TMEM -> registers -> bf16 -> 128B-swizzled smem (32 rows x 64 cols) -> TMA store (coalesced, clipped at the
+      // M/N edges).  The BN statistics are column sums read back from that same smem tile: lane l owns columns
+      // 2l, 2l+1 of the 64-column chunk (conflict-free LDS.32).  Two warps serve each TMEM lane quarter: with
+      // >= 2 chunks per tile they take alternate chunks; with a single chunk (BN = 64) they split its columns and
+      // its statistics rows and meet on a named barrier.
       constexpr int NCH = BN / 64;
-      uint8_t* my_stage = smem_stage_out + (warp - 2) * 8192;
+      const int half = (warp - 2) >> 2;
       float st_sum[NCH][2], st_sq[NCH][2];
 #pragma unroll
       for (int c = 0; c < NCH; ++c) { st_sum[c][0] = st_sum[c][1] = 0.f; st_sq[c][0] = st_sq[c][1] = 0.f; }
       int st_nb = -1;
       const bool want_stats = (p.stats != nullptr);
       int buf = 0;
+      // staging: own double buffer per warp; in the cooperative (NCH == 1) case both warps of a quarter use half 0's
+      uint8_t* my_stage = smem_stage_out + ((NCH == 1 ? 0 : half) * 4 + quarter) * 8192;
+      const uint32_t pair_bar = 1 + quarter;      // named barrier id shared by the two warps of a quarter
 
       auto flush_stats = [&](int nb) {
         if (nb < 0) return;
 #pragma unroll
         for (int c = 0; c < NCH; ++c) {
+          if (NCH > 1 && (c & 1) != half) continue;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             const int col = nb * BN + c * 64 + 2 * lane + h;
@@ -208,66 +215,83 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       };
+      // 32 accumulator columns -> four swizzled 16-byte pieces (g0..g0+3) of this thread's staging row
+      auto stage_32cols = [&](uint8_t* sbuf, uint32_t taddr, int col_first, int g0) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr, v);
+        tmem_ld_wait();
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int col = col_first + j;
+            const float b = (col < p.N) ? __ldg(p.bias + col) : 0.f;
+            v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
+          }
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+          *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((g0 + g) ^ (lane & 7)) << 4)) = pk;
+        }
+      };
+      auto column_stats = [&](const uint8_t* sbuf, int r0, int r1, int rows_valid, int c) {
+        float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+        for (int r = r0; r < r1; ++r) {
+          const uint32_t wd = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+          const float f0 = (r < rows_valid) ? __uint_as_float(wd << 16) : 0.f;
+          const float f1 = (r < rows_valid) ? __uint_as_float(wd & 0xffff0000u) : 0.f;
+          a0 += f0; q0 = fmaf(f0, f0, q0);
+          a1 += f1; q1 = fmaf(f1, f1, q1);
+        }
+        st_sum[c][0] += a0; st_sum[c][1] += a1; st_sq[c][0] += q0; st_sq[c][1] += q1;
+      };
 
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const WorkItem w = decode_item(p, item, BN);
         if (want_stats && w.nb != st_nb) { flush_stats(st_nb); st_nb = w.nb; }
         mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
         tc_fence_after();
-#pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          const int col0 = w.n0 + c * 64;
-          if (col0 >= p.N) continue;                 // warp-uniform: chunk entirely past the N edge
+        const int row_base = w.m0 + quarter * 32;
+        const int rows_valid = min(32, p.M - row_base);
+        const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
+        if constexpr (NCH == 1) {
           uint8_t* sbuf = my_stage + buf * 4096;
-          if (lane == 0) bulk_wait_group_read<1>();   // the TMA store that last read this buffer has drained
-          __syncwarp();
-          uint32_t v[64];
-          {
-            uint32_t lo[32], hi[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 64;
-            tmem_ld_32x32b_x32(taddr, lo);
-            tmem_ld_32x32b_x32(taddr + 32, hi);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { v[j] = lo[j]; v[32 + j] = hi[j]; }
-          }
-          if (p.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 64; ++j) {
-              const int col = col0 + j;
-              const float b = (col < p.N) ? __ldg(p.bias + col) : 0.f;
-              v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
-            }
-          }
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {               // 8 x 16-byte pieces of this thread's 128-byte row
-            uint4 pk;
-            pk.x = pack_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
-            pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
-            pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
-            pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-            *reinterpret_cast<uint4*>(sbuf + lane * 128 + ((g ^ (lane & 7)) << 4)) = pk;
-          }
+          if (half == 0 && lane == 0) bulk_wait_group_read<1>();
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // buffer is free, both warps present
+          stage_32cols(sbuf, tacc + half * 32, w.n0 + half * 32, half * 4);
           fence_proxy_async_smem();
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_3d(&map_out, smem_u32(sbuf), col0, w.m0 + quarter * 32, 0);
+          asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // whole 32x64 tile staged
+          if (half == 0 && lane == 0) {
+            tma_store_3d(&map_out, smem_u32(sbuf), w.n0, row_base, 0);
             bulk_commit_group();
           }
-          if (want_stats) {
-            float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
-            const int rows_valid = min(32, p.M - (w.m0 + quarter * 32));   // rows past M hold conv-of-zero-padding junk? no: zeros, but be exact
-#pragma unroll 8
-            for (int r = 0; r < 32; ++r) {
-              const uint32_t wd = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
-              const float f0 = (r < rows_valid) ? __uint_as_float(wd << 16) : 0.f;
-              const float f1 = (r < rows_valid) ? __uint_as_float(wd & 0xffff0000u) : 0.f;
-              a0 += f0; q0 = fmaf(f0, f0, q0);
-              a1 += f1; q1 = fmaf(f1, f1, q1);
-            }
-            st_sum[c][0] += a0; st_sum[c][1] += a1; st_sq[c][0] += q0; st_sq[c][1] += q1;
-          }
+          if (want_stats) column_stats(sbuf, half * 16, half * 16 + 16, rows_valid, 0);
           buf ^= 1;
+        } else {
+#pragma unroll
+          for (int c = 0; c < NCH; ++c) {
+            if ((c & 1) != half) continue;               // the sibling warp of this quarter takes these chunks
+            const int col0 = w.n0 + c * 64;
+            if (col0 >= p.N) continue;                   // chunk entirely past the N edge
+            uint8_t* sbuf = my_stage + buf * 4096;
+            if (lane == 0) bulk_wait_group_read<1>();     // the TMA store that last read this buffer has drained
+            __syncwarp();
+            stage_32cols(sbuf, tacc + c * 64, col0, 0);
+            stage_32cols(sbuf, tacc + c * 64 + 32, col0 + 32, 4);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_3d(&map_out, smem_u32(sbuf), col0, row_base, 0);
+              bulk_commit_group();
+            }
+            if (want_stats) column_stats(sbuf, 0, 32, rows_valid, c);
+            buf ^= 1;
+          }
         }
         tc_fence_before();
         mbar_arrive(smem_u32(&tmem_empty[acc]));
@@ -285,8 +309,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const int row = w.m0 + row_in_tile;
         const bool row_ok = row < p.M;
         const bool has_k = w.it_end > w.it_begin;
+        const int half = (warp - 2) >> 2;            // the two warps of a lane quarter take alternate 32-col chunks
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
+          if ((c & 1) != half) continue;
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
           tmem_ld_wait();

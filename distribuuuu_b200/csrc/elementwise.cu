@@ -27,6 +27,15 @@ __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) { f[2 * i] = __uint_as_float(w[i] << 16); f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u); }
 }
+// cp.async ring: global -> shared without holding registers, so many rows per thread can be in flight
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+constexpr int kRing = 4;        // ring depth (stages); kRing-1 rows per thread are in flight
+constexpr int kBnThreads = 256;
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   BF8 raw;
 #pragma unroll
@@ -154,37 +163,42 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyParams p) {
       shift[i] = b - p.running_mean[c0 + i] * scale[i];
     }
   }
-  constexpr int U = 4;  // rows in flight per thread: all loads of a batch are issued before any use
+  extern __shared__ __align__(16) unsigned char dyn_raw[];
+  uint4* ring = reinterpret_cast<uint4*>(dyn_raw);  // [kRing][2][256]
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const long long rstride = (long long)gridDim.y * blockDim.y;
-  for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += U * rstride) {
-    uint4 ry[U], rr[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long r = row + u * rstride;
-      if (r < p.rows) {
-        ry[u] = ldg_stream(p.y + r * p.ldy + c0);
-        if (p.residual) rr[u] = ldg_stream(p.residual + r * p.ldr + c0);
-      }
+  const long long row0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+  const bool has_res = p.residual != nullptr;
+  auto issue = [&](int stage, long long r) {
+    if (r < p.rows) {
+      cp_async16(&ring[(stage * 2 + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
+      if (has_res) cp_async16(&ring[(stage * 2 + 1) * kBnThreads + tid], p.residual + r * p.ldr + c0);
     }
+    cp_async_commit();
+  };
+  long long r_issue = row0;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long r = row + u * rstride;
-      if (r < p.rows) {
-        float x[8];
-        unpack8f(ry[u], x);
-        if (p.residual) {
-          float q[8];
-          unpack8f(rr[u], q);
+  for (int st = 0; st < kRing - 1; ++st) { issue(st, r_issue); r_issue += rstride; }
+  int st = 0;
+  for (long long r = row0; r < p.rows; r += rstride) {
+    issue((st + kRing - 1) % kRing, r_issue);
+    r_issue += rstride;
+    cp_async_wait<kRing - 1>();
+    float x[8];
+    unpack8f(ring[(st * 2 + 0) * kBnThreads + tid], x);
+    if (has_res) {
+      float q[8];
+      unpack8f(ring[(st * 2 + 1) * kBnThreads + tid], q);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]) + q[i], p.act);
-        } else {
+      for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]) + q[i], p.act);
+    } else {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]), p.act);
-        }
-        store8(p.out + r * p.ldo + c0, x);
-      }
+      for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]), p.act);
     }
+    store8(p.out + r * p.ldo + c0, x);
+    st = (st + 1) % kRing;
   }
+  cp_async_wait<0>();
 }
 
 // Per-channel sum / sum-of-squares of a [rows][C] bf16 tensor (used when the producer is not our conv kernel).
@@ -235,6 +249,7 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long r
 // BN backward, pass 1: per-channel sum(dz) and sum(dz * xhat), dz = dout * act'(z), z recomputed from y.
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdParams p) {
+  extern __shared__ __align__(16) float dyn[];
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = cv * VEC;
   float a[8], b[8];
@@ -252,39 +267,42 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdParams p) {
       scale[i] = g * invstd[i];
       shift[i] = be - mean * scale[i];
     }
-    constexpr int U = 4;
+    uint4* ring = reinterpret_cast<uint4*>(dyn);  // [kRing][3][256]
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const long long rstride = (long long)gridDim.y * blockDim.y;
+    const long long row0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
     const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr);
-    for (long long row = (long long)blockIdx.y * blockDim.y + threadIdx.y; row < p.rows; row += U * rstride) {
-      uint4 ry[U], rd[U], rr[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const long long r = row + u * rstride;
-        if (r < p.rows) {
-          ry[u] = ldg_stream(p.y + r * p.ldy + c0);
-          rd[u] = ldg_stream(p.dout + r * p.ldd + c0);
-          if (need_res) rr[u] = ldg_stream(p.residual + r * p.ldr + c0);
-        }
+    auto issue = [&](int stage, long long r) {
+      if (r < p.rows) {
+        cp_async16(&ring[(stage * 3 + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
+        cp_async16(&ring[(stage * 3 + 1) * kBnThreads + tid], p.dout + r * p.ldd + c0);
+        if (need_res) cp_async16(&ring[(stage * 3 + 2) * kBnThreads + tid], p.residual + r * p.ldr + c0);
       }
+      cp_async_commit();
+    };
+    long long r_issue = row0;
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (row + u * rstride < p.rows) {
-          float y[8], d[8];
-          unpack8f(ry[u], y);
-          unpack8f(rd[u], d);
-          float q[8];
-          if (need_res) unpack8f(rr[u], q);
+    for (int st = 0; st < kRing - 1; ++st) { issue(st, r_issue); r_issue += rstride; }
+    int st = 0;
+    for (long long r = row0; r < p.rows; r += rstride) {
+      issue((st + kRing - 1) % kRing, r_issue);
+      r_issue += rstride;
+      cp_async_wait<kRing - 1>();
+      float y[8], d[8], q[8];
+      unpack8f(ring[(st * 3 + 0) * kBnThreads + tid], y);
+      unpack8f(ring[(st * 3 + 1) * kBnThreads + tid], d);
+      if (need_res) unpack8f(ring[(st * 3 + 2) * kBnThreads + tid], q);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
-            a[i] += d[i];
-            b[i] = fmaf(d[i], fmaf(y[i], invstd[i], nmi[i]), b[i]);
-          }
-        }
+      for (int i = 0; i < 8; ++i) {
+        if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
+        a[i] += d[i];
+        b[i] = fmaf(d[i], fmaf(y[i], invstd[i], nmi[i]), b[i]);
       }
+      st = (st + 1) % kRing;
     }
+    cp_async_wait<0>();
   }
-  extern __shared__ float dyn[];
+  __syncthreads();  // the ring memory is reused for the cross-row reduction below
   float* mine = dyn + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 16;
 #pragma unroll
   for (int i = 0; i < 8; ++i) { mine[i] = a[i]; mine[8 + i] = b[i]; }
@@ -334,42 +352,45 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdParams p) {
       }
     }
   }
-  constexpr int U = 4;
+  extern __shared__ __align__(16) unsigned char dyn_raw[];
+  uint4* ring = reinterpret_cast<uint4*>(dyn_raw);  // [kRing][3][256]
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const long long rstride = (long long)gridDim.y * blockDim.y;
+  const long long k0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
   const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr);
-  // iterate from the END of the tensor: the reduce pass finished there, so those lines are the likeliest L2 hits
-  for (long long k = (long long)blockIdx.y * blockDim.y + threadIdx.y; k < p.rows; k += U * rstride) {
-    uint4 ry[U], rd[U], rr[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long kk = k + u * rstride;
-      if (kk < p.rows) {
-        const long long r = p.rows - 1 - kk;
-        ry[u] = ldg_stream(p.y + r * p.ldy + c0);
-        rd[u] = ldg_stream(p.dout + r * p.ldd + c0);
-        if (need_res) rr[u] = ldg_stream(p.residual + r * p.ldr + c0);
-      }
+  // rows are visited from the END of the tensor: the reduce pass finished there, so those lines are the likeliest L2 hits
+  auto issue = [&](int stage, long long kk) {
+    if (kk < p.rows) {
+      const long long r = p.rows - 1 - kk;
+      cp_async16(&ring[(stage * 3 + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
+      cp_async16(&ring[(stage * 3 + 1) * kBnThreads + tid], p.dout + r * p.ldd + c0);
+      if (need_res) cp_async16(&ring[(stage * 3 + 2) * kBnThreads + tid], p.residual + r * p.ldr + c0);
     }
+    cp_async_commit();
+  };
+  long long k_issue = k0;
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const long long kk = k + u * rstride;
-      if (kk < p.rows) {
-        const long long r = p.rows - 1 - kk;
-        float y[8], d[8], q[8];
-        unpack8f(ry[u], y);
-        unpack8f(rd[u], d);
-        if (need_res) unpack8f(rr[u], q);
-        float o[8];
+  for (int st = 0; st < kRing - 1; ++st) { issue(st, k_issue); k_issue += rstride; }
+  int st = 0;
+  for (long long kk = k0; kk < p.rows; kk += rstride) {
+    issue((st + kRing - 1) % kRing, k_issue);
+    k_issue += rstride;
+    cp_async_wait<kRing - 1>();
+    const long long r = p.rows - 1 - kk;
+    float y[8], d[8], q[8], o[8];
+    unpack8f(ring[(st * 3 + 0) * kBnThreads + tid], y);
+    unpack8f(ring[(st * 3 + 1) * kBnThreads + tid], d);
+    if (need_res) unpack8f(ring[(st * 3 + 2) * kBnThreads + tid], q);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
-          o[i] = fmaf(d[i], scale[i], fmaf(y[i], ca[i], cb[i]));
-        }
-        if (p.dresidual) store8(p.dresidual + r * p.ldr + c0, d);
-        store8(p.dy + r * p.ldy + c0, o);
-      }
+    for (int i = 0; i < 8; ++i) {
+      if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
+      o[i] = fmaf(d[i], scale[i], fmaf(y[i], ca[i], cb[i]));
     }
+    if (p.dresidual) store8(p.dresidual + r * p.ldr + c0, d);
+    store8(p.dy + r * p.ldy + c0, o);
+    st = (st + 1) % kRing;
   }
+  cp_async_wait<0>();
 }
 
 // Plain activation backward when there is no BN (conv + bias + act): dz = dout * act'(z) with z the stored output.
@@ -661,7 +682,7 @@ static inline void bn_launch_dims(int C, long long rows, dim3& grid, dim3& block
   const int by = 256 / bx;
   const int gx = (cvs + bx - 1) / bx;
   long long want = (rows + by - 1) / by;
-  long long cap = (148 * 8 + gx - 1) / gx;   // ~8 CTAs per SM in total
+  long long cap = (148 * 4 + gx - 1) / gx;   // ~4 CTAs per SM in total (2-3 resident: ring smem + registers)
   int gy = (int)(want < cap ? want : cap);
   if (gy < 1) gy = 1;
   grid = dim3(gx, gy);
@@ -671,7 +692,7 @@ static inline void bn_launch_dims(int C, long long rows, dim3& grid, dim3& block
 extern "C" int b200_bn_apply(const BnApplyParams* p, cudaStream_t s) {
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
-  bn_apply_kernel<<<g, b, 0, s>>>(*p);
+  bn_apply_kernel<<<g, b, kRing * 2 * kBnThreads * 16, s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_stats(const void* y, long long rows, int C, long long ldy, float* stats, cudaStream_t s) {
@@ -683,13 +704,13 @@ extern "C" int b200_bn_stats(const void* y, long long rows, int C, long long ldy
 extern "C" int b200_bn_bwd_reduce(const BnBwdParams* p, cudaStream_t s) {
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
-  bn_bwd_reduce_kernel<<<g, b, b.x * b.y * 16 * sizeof(float), s>>>(*p);
+  bn_bwd_reduce_kernel<<<g, b, kRing * 3 * kBnThreads * 16, s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_bwd_apply(const BnBwdParams* p, cudaStream_t s) {
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
-  bn_bwd_apply_kernel<<<g, b, 0, s>>>(*p);
+  bn_bwd_apply_kernel<<<g, b, kRing * 3 * kBnThreads * 16, s>>>(*p);
   return (int)cudaGetLastError();
 }
 static inline int ew_grid(long long total, int block) {
