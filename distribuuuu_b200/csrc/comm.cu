@@ -139,7 +139,9 @@ __global__ void cast_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* _
 
 // ---- fused peer-memory all-reduce + SGD -----------------------------------------------------------
 // All offsets / lengths are in units of 8 elements (16 bytes of bf16).
-__global__ void __launch_bounds__(512, 1) allreduce_sgd_kernel(AllreduceSgdParams p) {
+// 256 threads x <= 64 registers: a CTA of this kernel must fit on an SM next to a resident conv / BN CTA of the
+// backward pass it overlaps with (the persistent conv kernel keeps ~48k of the 64k registers of every SM).
+__global__ void __launch_bounds__(256, 4) allreduce_sgd_kernel(AllreduceSgdParams p) {
   const CommCtx& c = p.comm;
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
@@ -219,7 +221,7 @@ extern "C" int b200_cast_bf16(const float* src, void* dst, long long n, cudaStre
   return (int)cudaGetLastError();
 }
 extern "C" int b200_allreduce_sgd(const AllreduceSgdParams* p, int grid, cudaStream_t s) {
-  allreduce_sgd_kernel<<<grid, 512, 0, s>>>(*p);
+  allreduce_sgd_kernel<<<grid, 256, 0, s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_rank_barrier(const CommCtx* c, uint32_t epoch, cudaStream_t s) {

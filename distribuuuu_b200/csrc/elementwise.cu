@@ -689,10 +689,20 @@ static inline void bn_launch_dims(int C, long long rows, dim3& grid, dim3& block
   block = dim3(bx, by);
 }
 
+// The ring buffers plus the few bytes of static shared memory exceed the default 48 KB limit: opt in once.
+template <typename Kern>
+static inline cudaError_t allow_big_smem(Kern kern, int bytes) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+}
+constexpr int kRingBytes2 = kRing * 2 * kBnThreads * 16;  // 32 KB
+constexpr int kRingBytes3 = kRing * 3 * kBnThreads * 16;  // 48 KB
+
 extern "C" int b200_bn_apply(const BnApplyParams* p, cudaStream_t s) {
+  static cudaError_t once = allow_big_smem(bn_apply_kernel, kRingBytes2);
+  if (once != cudaSuccess) return (int)once;
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
-  bn_apply_kernel<<<g, b, kRing * 2 * kBnThreads * 16, s>>>(*p);
+  bn_apply_kernel<<<g, b, kRingBytes2, s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_stats(const void* y, long long rows, int C, long long ldy, float* stats, cudaStream_t s) {
@@ -702,15 +712,19 @@ extern "C" int b200_bn_stats(const void* y, long long rows, int C, long long ldy
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_bwd_reduce(const BnBwdParams* p, cudaStream_t s) {
+  static cudaError_t once = allow_big_smem(bn_bwd_reduce_kernel, kRingBytes3);
+  if (once != cudaSuccess) return (int)once;
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
-  bn_bwd_reduce_kernel<<<g, b, kRing * 3 * kBnThreads * 16, s>>>(*p);
+  bn_bwd_reduce_kernel<<<g, b, kRingBytes3, s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_bwd_apply(const BnBwdParams* p, cudaStream_t s) {
+  static cudaError_t once = allow_big_smem(bn_bwd_apply_kernel, kRingBytes3);
+  if (once != cudaSuccess) return (int)once;
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
-  bn_bwd_apply_kernel<<<g, b, kRing * 3 * kBnThreads * 16, s>>>(*p);
+  bn_bwd_apply_kernel<<<g, b, kRingBytes3, s>>>(*p);
   return (int)cudaGetLastError();
 }
 static inline int ew_grid(long long total, int block) {
