@@ -261,7 +261,12 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   p.im_P = P; p.im_Q = Q; p.im_stride = stride; p.im_low_w = -pad; p.im_low_h = -pad;
   p.k_blocks_total = (int)((pixels + 63) / 64);
   const int base_items = p.m_blocks * p.n_blocks * p.taps;
-  int splits = (2 * num_sms() + base_items - 1) / base_items;
+  // split-K so that the item count is just UNDER a whole number of waves (an extra partial wave costs a full
+  // item time): aim at 2 waves, fall back to 1 wave / no split for shapes that already have many items
+  const int sms = num_sms();
+  int splits = (2 * sms) / base_items;
+  if (splits < 1) splits = 1;
+  if (base_items > 2 * sms) splits = 1;
   splits = std::max(1, std::min(splits, std::max(1, p.k_blocks_total / 8)));
   p.splits = splits;
   p.out = dw.data_ptr(); p.ldo = (long long)p.taps * C; p.tap_stride = C;
