@@ -622,18 +622,26 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloa
   }
 }
 
-__global__ void stem_im2col_kernel(const float* __restrict__ x /*NCHW fp32*/, __nv_bfloat16* __restrict__ patches,
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x /*NCHW fp32*/, __nv_bfloat16* __restrict__ patches,
                                    int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad) {
-  // one thread per 8 consecutive patch elements (one 16-byte store): row layout [r][s][c] (+ zero padding to Kpad),
-  // matching weights [Cout][R][S][C].  Stores are fully coalesced; the fp32 image is re-read through L1/L2.
+  // One CTA per output row (n, p): the R input rows it needs are staged in shared memory once (coalesced reads of the
+  // NCHW image, zero-filled borders), then every thread emits 16-byte patch pieces (row layout [r][s][c] + zero
+  // padding to Kpad, matching weights [Cout][R][S][C]) with fully coalesced stores.
+  extern __shared__ float tile[];                    // [C][R][W + 2*pad]
+  const int Wp = W + 2 * pad;
+  const int n = blockIdx.x / P, ph = blockIdx.x % P;
+  for (int i = threadIdx.x; i < C * R * Wp; i += blockDim.x) {
+    const int wp = i % Wp; const int cr = i / Wp;
+    const int r = cr % R, c = cr / R;
+    const int h = ph * stride - pad + r, w = wp - pad;
+    tile[i] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(x + (((long long)n * C + c) * H + h) * W + w) : 0.f;
+  }
+  __syncthreads();
   const int vec_per_row = Kpad / 8;
-  const long long total = (long long)N * P * Q * vec_per_row;
   const int kdim = R * S * C;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int j8 = idx % vec_per_row;
-    const long long pix = idx / vec_per_row;
-    const int q = pix % Q; const long long t = pix / Q;
-    const int ph = t % P; const int n = t / P;
+  __nv_bfloat16* out_row = patches + ((long long)n * P + ph) * Q * Kpad;
+  for (int item = threadIdx.x; item < Q * vec_per_row; item += blockDim.x) {
+    const int j8 = item % vec_per_row, q = item / vec_per_row;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
@@ -642,12 +650,11 @@ __global__ void stem_im2col_kernel(const float* __restrict__ x /*NCHW fp32*/, __
       if (k < kdim) {
         const int c = k % C; const int rs = k / C;
         const int s = rs % S, r = rs / S;
-        const int h = ph * stride - pad + r, w = q * stride - pad + s;
-        if (h >= 0 && h < H && w >= 0 && w < W) val = __ldg(x + (((long long)n * C + c) * H + h) * W + w);
+        val = tile[(c * R + r) * Wp + q * stride + s];
       }
       v[i] = val;
     }
-    store8(patches + pix * Kpad + j8 * 8, v);
+    store8(out_row + (long long)q * Kpad + j8 * 8, v);
   }
 }
 
@@ -775,7 +782,7 @@ extern "C" int b200_nchw_to_nhwc(const float* x, void* out, int N, int C, int H,
 }
 extern "C" int b200_stem_im2col(const float* x, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S,
                                 int stride, int pad, int Kpad, cudaStream_t s) {
-  stem_im2col_kernel<<<ew_grid((long long)N * P * Q * (Kpad / 8), 256), 256, 0, s>>>(x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad);
+  stem_im2col_kernel<<<N * P, 256, (size_t)C * R * (W + 2 * pad) * sizeof(float), s>>>(x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_pad_rows(const void* src, void* dst, int rows, int cols, int cols_pad, cudaStream_t s) {

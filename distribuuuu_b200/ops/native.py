@@ -325,7 +325,7 @@ class NativeOps:
     def conv_bn_act(self, x, conv, bn, act, residual):
         eng = self.eng
         training = bn is not None and bn.training
-        slot = eng.fwd_slot(bn) if training else None
+        slot = eng.fwd_slot(bn) if (training and conv.out_channels % 8 == 0) else None
         stats = slot.tensor if slot is not None else None
         if self._is_stem(conv, x):
             y = StemConvFn.apply(x, eng, conv, stats, eng.anchor)
@@ -340,11 +340,23 @@ class NativeOps:
             if residual is not None:
                 y = y + residual
             return _torch_act(y, act)
+        if y.shape[1] % 8 != 0:
+            w = eng.w16_leaf(bn.weight) if bn.affine else None
+            b = eng.w16_leaf(bn.bias) if bn.affine else None
+            y = F.batch_norm(y, bn.running_mean, bn.running_var, w, b, bn.training, bn.momentum or 0.1, bn.eps)
+            if residual is not None:
+                y = y + residual
+            return _torch_act(y, act)
         return BnActFn.apply(y, residual, eng, bn, act, slot, training, eng.anchor)
 
     def bn_act(self, x, bn, act):
         eng = self.eng
         x = self._as_act(x)
+        if x.shape[1] % 8 != 0:  # kernels are 8-channel vectorised; odd widths take the ATen path
+            w = eng.w16_leaf(bn.weight) if bn.affine else None
+            b = eng.w16_leaf(bn.bias) if bn.affine else None
+            y = F.batch_norm(x, bn.running_mean, bn.running_var, w, b, bn.training, bn.momentum or 0.1, bn.eps)
+            return _torch_act(y, act)
         training = bn.training
         slot = eng.fwd_slot(bn) if training else None
         if slot is not None:

@@ -258,6 +258,51 @@ def check_stem():
 
 
 # ---------------------------------------------------------------------------------------------- end to end
+def check_checkpoint_interop(tmpdir="/tmp/b200_ckpt_test"):
+    """A checkpoint written from the native engine (flat / fused optimizer) loads into a plain model with
+    ``torch.optim.SGD`` and back (reference layout: utils.py:366-410)."""
+    import os
+    import shutil
+    from . import models, utils
+    from .config import cfg
+    from .parallel.native_engine import NativeEngine
+    dev = torch.device("cuda", torch.cuda.current_device())
+    shutil.rmtree(tmpdir, ignore_errors=True)
+    cfg.defrost()
+    cfg.OUT_DIR = tmpdir
+    net = models.build_model("resnet18", num_classes=16).to(dev)
+    eng = NativeEngine(net, dev)
+    opt = eng.make_optimizer(lr=0.05, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    eng.train()
+    x, y = torch.randn(8, 3, 64, 64, device=dev), torch.randint(0, 16, (8,), device=dev)
+    for _ in range(2):
+        eng.train_step(x, y, opt, 5)
+    path = utils.save_checkpoint(eng, opt, 0, 1.0, True)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"epoch", "state_dict", "optimizer", "best_acc1"}
+    plain = models.build_model("resnet18", num_classes=16)
+    popt = torch.optim.SGD(plain.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+    start, best = utils.load_checkpoint(path, plain, popt)
+    assert (start, best) == (1, 1.0)
+    mom_ref = popt.state[next(iter(plain.parameters()))]["momentum_buffer"]
+    assert mom_ref.shape == next(iter(plain.parameters())).shape and float(mom_ref.abs().sum()) > 0
+    # and back into a fresh native engine
+    net2 = models.build_model("resnet18", num_classes=16).to(dev)
+    eng2 = NativeEngine(net2, dev)
+    opt2 = eng2.make_optimizer(lr=0.05, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    torch.save({"epoch": 0, "state_dict": plain.state_dict(), "optimizer": popt.state_dict(), "best_acc1": 1.0}, path)
+    utils.load_checkpoint(path, eng2, opt2)
+    e_w = _rel_err(eng2.flat_master, eng.flat_master)
+    e_m = _rel_err(eng2.flat_mom, eng.flat_mom)
+    e_16 = _rel_err(eng2.flat_w16.float(), eng.flat_w16.float())
+    assert e_w < 1e-6 and e_m < 1e-6 and e_16 < 1e-6, (e_w, e_m, e_16)
+    # evaluation path on the native engine
+    eng2.eval()
+    loss, h1, hk = eng2.eval_step(x, y, 5)
+    assert loss == loss
+    return {"master": e_w, "momentum": e_m, "eval_loss": float(loss)}
+
+
 def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_classes=16, tol=0.08):
     """Same weights, same data: the native engine's loss trajectory must track the fp32 torch path."""
     import copy

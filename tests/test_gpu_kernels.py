@@ -54,6 +54,18 @@ def test_native_engine_tracks_fp32_reference(arch):
     selftest.check_engine_vs_torch(arch, batch=8, size=64)
 
 
+@pytest.mark.parametrize("arch,batch,size", [("resnext50_32x4d", 8, 64), ("densenet121", 8, 64), ("efficientnet_b0", 8, 64),
+                                             ("regnety_160", 4, 64), ("regnetx_160", 4, 64), ("botnet50", 4, 224)])
+def test_every_model_family_trains_on_native_engine(arch, batch, size):
+    from distribuuuu_b200 import selftest
+    selftest.check_engine_vs_torch(arch, batch=batch, size=size, tol=0.15)
+
+
+def test_checkpoint_interop_native_vs_torch_optim():
+    from distribuuuu_b200 import selftest
+    selftest.check_checkpoint_interop()
+
+
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
