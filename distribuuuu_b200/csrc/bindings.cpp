@@ -247,26 +247,34 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   TORCH_CHECK(dy.size(3) == K && dw.size(3) == C && dy.size(0) == N, "wgrad shape mismatch");
   TORCH_CHECK(C % 8 == 0 && K % 8 == 0, "channels must be multiples of 8");
   const long long pixels = (long long)N * P * Q;
-  const int bn = pick_bn(C);
   const bool pointwise = (R == 1 && S == 1 && stride == 1 && pad == 0);
+  // B operand = "virtual boxes": (tap, 64-channel slice of Cin).  One work item accumulates up to 4 of them
+  // (N = 64..256 TMEM columns) against a single load of the dY^T tile, so dY is re-read taps*Cin/(64*vpi) times
+  // instead of taps*Cin/64 times.
+  const int cin_boxes = (C + 63) / 64;
+  const int vboxes = R * S * cin_boxes;
+  int vpi = 1;
+  for (int cand = 4; cand >= 1; --cand) if (vboxes % cand == 0) { vpi = cand; break; }
+  if (vpi == 1 && vboxes > 4) vpi = 4;            // no nice divisor: groups of 4 with a short tail group
+  const int bn = vpi > 2 ? 256 : (vpi == 2 ? 128 : 64);
   ConvGemmParams p{};
   p.kind = KIND_WGRAD; p.epi = EPI_F32_RED;
   p.M = K; p.N = C;
-  p.m_blocks = (K + 127) / 128; p.n_blocks = (C + bn - 1) / bn;
+  p.m_blocks = (K + 127) / 128; p.n_blocks = (vboxes + vpi - 1) / vpi;
+  p.vb_per_item = vpi; p.cin_boxes = cin_boxes; p.vboxes_total = vboxes;
   p.taps = R * S; p.S = S; p.kb_per_tap = 0; p.dil = dil;
   p.a_im2col = 0; p.a_nbox = 2; p.a_kstep16 = kMnMajorStep16; p.a_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
-  p.b_im2col = pointwise ? 0 : 1; p.b_nbox = bn / 64; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
+  p.b_im2col = pointwise ? 0 : 1; p.b_nbox = vpi; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
   p.b_flip_taps = 0;
-  p.idesc = idesc_bf16(128, bn, 1, 1);
+  p.idesc = idesc_bf16(128, 64 * vpi, 1, 1);
   p.im_P = P; p.im_Q = Q; p.im_stride = stride; p.im_low_w = -pad; p.im_low_h = -pad;
   p.k_blocks_total = (int)((pixels + 63) / 64);
-  const int base_items = p.m_blocks * p.n_blocks * p.taps;
+  const int base_items = p.m_blocks * p.n_blocks;
   // split-K so that the item count is just UNDER a whole number of waves (an extra partial wave costs a full
-  // item time): aim at 2 waves, fall back to 1 wave / no split for shapes that already have many items
+  // item time): aim at 2 waves, fall back to no split for shapes that already have many items
   const int sms = num_sms();
   int splits = (2 * sms) / base_items;
   if (splits < 1) splits = 1;
-  if (base_items > 2 * sms) splits = 1;
   splits = std::max(1, std::min(splits, std::max(1, p.k_blocks_total / 8)));
   p.splits = splits;
   p.out = dw.data_ptr(); p.ldo = (long long)p.taps * C; p.tap_stride = C;

@@ -45,20 +45,22 @@ __device__ __forceinline__ PixelCoord decode_pixel(const ConvGemmParams& p, int 
   return {q * p.im_stride + p.im_low_w, ph * p.im_stride + p.im_low_h, n};
 }
 
-struct WorkItem { int m0, n0, nb, tap, it_begin, it_end; };
+struct WorkItem { int m0, n0, nb, tap, it_begin, it_end, vb0, nbox; };
 
 __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn) {
   WorkItem w;
   if (p.kind != KIND_WGRAD) {
     int nb = item % p.n_blocks;
     int mb = item / p.n_blocks;
-    w.m0 = mb * BM; w.n0 = nb * bn; w.nb = nb; w.tap = 0;
+    w.m0 = mb * BM; w.n0 = nb * bn; w.nb = nb; w.tap = 0; w.vb0 = 0; w.nbox = 0;
     w.it_begin = 0; w.it_end = p.taps * p.kb_per_tap;
   } else {
+    // wgrad: an item owns `nbox` consecutive virtual B boxes (tap, 64-channel slice of Cin) -> N = 64*nbox columns
     int split = item % p.splits; int rest = item / p.splits;
-    int tap = rest % p.taps; rest /= p.taps;
-    int nb = rest % p.n_blocks; int mb = rest / p.n_blocks;
-    w.m0 = mb * BM; w.n0 = nb * bn; w.nb = nb; w.tap = tap;
+    int group = rest % p.n_blocks; int mb = rest / p.n_blocks;
+    w.m0 = mb * BM; w.n0 = 0; w.nb = group; w.tap = 0;
+    w.vb0 = group * p.vb_per_item;
+    w.nbox = min(p.vb_per_item, p.vboxes_total - w.vb0);
     w.it_begin = (int)(((long long)p.k_blocks_total * split) / p.splits);
     w.it_end = (int)(((long long)p.k_blocks_total * (split + 1)) / p.splits);
   }
@@ -116,7 +118,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t bar = smem_u32(&full_bar[stage]);
           const uint32_t dst_a = smem_u32(smem_a + stage * kABytes);
           const uint32_t dst_b = smem_u32(smem_b + stage * C::kBBytes);
-          mbar_expect_tx(bar, C::kStageBytes);
+          mbar_expect_tx(bar, p.kind == KIND_WGRAD ? (uint32_t)(kABytes + w.nbox * kBoxBytes) : (uint32_t)C::kStageBytes);
           if (p.kind != KIND_WGRAD) {
             const int tap = it / p.kb_per_tap;
             const int kb = it - tap * p.kb_per_tap;
@@ -135,14 +137,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           } else {
             const int k0 = it * BK;  // first reduction pixel of this block
             for (int j = 0; j < p.a_nbox; ++j) tma_load_3d(dst_a + j * kBoxBytes, &map_a, bar, w.m0 + 64 * j, 0, k0);
-            if (p.b_im2col) {
-              const PixelCoord pb = decode_pixel(p, k0);
-              const int r = w.tap / p.S, s = w.tap - r * p.S;
-              for (int j = 0; j < p.b_nbox; ++j)
-                tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + 64 * j, pb.w, pb.h, pb.n,
+            PixelCoord pb{0, 0, 0};
+            if (p.b_im2col) pb = decode_pixel(p, k0);
+            for (int j = 0; j < w.nbox; ++j) {
+              const int vb = w.vb0 + j;
+              const int tap = vb / p.cin_boxes, cbox = vb - tap * p.cin_boxes;
+              if (p.b_im2col) {
+                const int r = tap / p.S, s = tap - r * p.S;
+                tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, cbox * 64, pb.w, pb.h, pb.n,
                                    (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
-            } else {
-              for (int j = 0; j < p.b_nbox; ++j) tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + 64 * j, 0, k0);
+              } else {
+                tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, cbox * 64, 0, k0);
+              }
             }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -159,6 +165,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t idesc = (p.kind == KIND_WGRAD) ? ((p.idesc & ~(0x3fu << 17)) | ((uint32_t)(w.nbox * 64 >> 3) << 17)) : p.idesc;
         for (int it = w.it_begin; it < w.it_end; ++it) {
           mbar_wait(smem_u32(&full_bar[stage]), phase);          // TMA bytes have landed
           tc_fence_after();
@@ -166,7 +173,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint64_t b_desc = p.b_desc_hi | (uint64_t)((smem_u32(smem_b + stage * C::kBBytes) >> 4) & 0x3fff);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_d, a_desc + (uint64_t)(k * p.a_kstep16), b_desc + (uint64_t)(k * p.b_kstep16), p.idesc,
+            umma_bf16(tmem_d, a_desc + (uint64_t)(k * p.a_kstep16), b_desc + (uint64_t)(k * p.b_kstep16), idesc,
                       (it > w.it_begin || k > 0) ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when the MMAs retire
           if (++stage == C::kStages) { stage = 0; phase ^= 1; }
@@ -316,9 +323,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           uint32_t v[32];
           tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + c * 32, v);
           tmem_ld_wait();
-          const int col0 = w.n0 + c * 32;
+          const int j = c >> 1;                         // which B box of this item
+          if (j >= w.nbox) continue;
+          const int vb = w.vb0 + j;
+          const int tap = vb / p.cin_boxes, cbox = vb - tap * p.cin_boxes;
+          const int col0 = cbox * 64 + (c & 1) * 32;    // channel offset inside the tap
           if (row_ok && col0 < p.N && has_k) {
-            float* dst = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + (long long)w.tap * p.tap_stride + col0;
+            float* dst = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + (long long)tap * p.tap_stride + col0;
             if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int g = 0; g < 8; ++g)
@@ -328,8 +339,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
                              : "memory");
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) atomicAdd(dst + j, __uint_as_float(v[j]));
+              for (int jj = 0; jj < 32; ++jj)
+                if (col0 + jj < p.N) atomicAdd(dst + jj, __uint_as_float(v[jj]));
             }
           }
         }

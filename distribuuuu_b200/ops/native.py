@@ -78,6 +78,14 @@ def _strided_dgrad(K, dyh, w, x_shape, s, p, d):
     tcgen05 dgrad (costs s^2 x the FLOPs of the few strided layers; a parity-decomposed kernel is future work)."""
     N, H, W, C = x_shape
     Kc, R, S, _ = w.shape
+    if R == 1 and S == 1 and p == 0:
+        # 1x1 strided conv: only the sampled pixels receive gradient -> compact pointwise dgrad + strided scatter
+        Pc, Qc = dyh.shape[1], dyh.shape[2]
+        compact = torch.empty((N, Pc, Qc, C), dtype=dyh.dtype, device=dyh.device)
+        K.conv_dgrad(dyh, w, compact, 1, 0, 1)
+        dxh = torch.zeros((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
+        dxh[:, ::s, ::s, :][:, :Pc, :Qc] = compact
+        return dxh
     P1 = H + 2 * p - d * (R - 1)
     Q1 = W + 2 * p - d * (S - 1)
     up = torch.zeros((N, P1, Q1, Kc), dtype=dyh.dtype, device=dyh.device)
