@@ -12,6 +12,7 @@
 
 #include "comm.h"
 #include "conv_gemm.h"
+#include "dwconv.h"
 #include "elementwise.h"
 
 namespace {
@@ -193,12 +194,13 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   CUtensorMap mb = tiled_map_3d(w.data_ptr(), g.C, p.taps, g.K, g.C, (uint64_t)p.taps * g.C, 64, 1, bn);
   CUtensorMap mo = tiled_map_3d(out.data_ptr(), g.K, M, 1, g.K, (uint64_t)g.K * M, 64, 32, 1);
   const int grid = std::min(p.total_items, num_sms());
-  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &p, bn, grid, cur_stream()));
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &mo, &p, bn, grid, cur_stream()));
 }
 
 // ---------------------------------------------------------------------------------------------- conv dgrad (stride 1)
 // dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C].
-void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64_t stride, int64_t pad, int64_t dil) {
+void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64_t stride, int64_t pad, int64_t dil,
+                const c10::optional<at::Tensor>& addend) {
   check_bf16_contig(dy, "dy"); check_bf16_contig(w, "w"); check_bf16_contig(dx, "dx");
   TORCH_CHECK(stride == 1, "tcgen05 dgrad handles stride 1 (strided layers use the zero-insertion path)");
   c10::cuda::CUDAGuard guard(dy.device());
@@ -231,8 +233,15 @@ void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64
   // weights viewed as (C inner, taps, K): MN-major B boxes of [64 k-rows (Cout)][64 n (Cin)]
   CUtensorMap mb = tiled_map_3d(w.data_ptr(), C, p.taps, K, C, (uint64_t)p.taps * C, 64, 1, 64);
   CUtensorMap mo = tiled_map_3d(dx.data_ptr(), C, M, 1, C, (uint64_t)C * M, 64, 32, 1);
+  CUtensorMap md = mo;
+  if (addend.has_value()) {
+    check_bf16_contig(*addend, "addend");
+    TORCH_CHECK(addend->numel() == dx.numel(), "addend must have dx's shape");
+    p.addend = 1;
+    md = tiled_map_3d(addend->data_ptr(), C, M, 1, C, (uint64_t)C * M, 64, 32, 1);
+  }
   const int grid = std::min(p.total_items, num_sms());
-  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &p, bn, grid, cur_stream()));
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &md, &p, bn, grid, cur_stream()));
 }
 
 // ---------------------------------------------------------------------------------------------- conv wgrad
@@ -284,7 +293,44 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
                              : im2col_map_4d(x.data_ptr(), N, H, W, C, -pad, -pad, pad - (S - 1) * dil,
                                              pad - (R - 1) * dil, stride, 64, 64);
   const int grid = std::min(p.total_items, num_sms());
-  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &ma, &p, bn, grid, cur_stream()));
+  B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &ma, &ma, &p, bn, grid, cur_stream()));
+}
+
+// ---------------------------------------------------------------------------------------------- depthwise conv
+const float* fptr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+float* fptr_mut(c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
+const __nv_bfloat16* bptr(const at::Tensor& t) { return reinterpret_cast<const __nv_bfloat16*>(t.data_ptr()); }
+__nv_bfloat16* bptr_mut(at::Tensor& t) { return reinterpret_cast<__nv_bfloat16*>(t.data_ptr()); }
+DwParams dw_params(const at::Tensor& x_like, int64_t k, int64_t stride, int64_t pad, int P, int Q) {
+  DwParams p{};
+  p.N = x_like.size(0); p.H = x_like.size(1); p.W = x_like.size(2); p.C = x_like.size(3);
+  p.P = P; p.Q = Q; p.k = k; p.stride = stride; p.pad = pad;
+  TORCH_CHECK(p.C % 8 == 0 && k <= 5, "depthwise kernels need C % 8 == 0 and k <= 5");
+  return p;
+}
+void dw_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& y, const c10::optional<at::Tensor>& stats, int64_t k,
+              int64_t stride, int64_t pad) {
+  check_bf16_contig(x, "x"); check_bf16_contig(w, "w"); check_bf16_contig(y, "y");
+  c10::cuda::CUDAGuard guard(x.device());
+  DwParams p = dw_params(x, k, stride, pad, y.size(1), y.size(2));
+  p.x = bptr(x); p.w = bptr(w); p.y = bptr_mut(y);
+  p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;
+  B200_CUDA_OK(b200_dw_fprop(&p, cur_stream()));
+}
+void dw_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64_t k, int64_t stride, int64_t pad) {
+  check_bf16_contig(dy, "dy"); check_bf16_contig(w, "w"); check_bf16_contig(dx, "dx");
+  c10::cuda::CUDAGuard guard(dy.device());
+  DwParams p = dw_params(dx, k, stride, pad, dy.size(1), dy.size(2));
+  p.w = bptr(w); p.y = const_cast<__nv_bfloat16*>(bptr(dy)); p.dx = bptr_mut(dx);
+  B200_CUDA_OK(b200_dw_dgrad(&p, cur_stream()));
+}
+void dw_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64_t k, int64_t stride, int64_t pad) {
+  check_bf16_contig(dy, "dy"); check_bf16_contig(x, "x");
+  TORCH_CHECK(dw.scalar_type() == at::kFloat && dw.is_contiguous(), "dw must be contiguous fp32");
+  c10::cuda::CUDAGuard guard(dy.device());
+  DwParams p = dw_params(x, k, stride, pad, dy.size(1), dy.size(2));
+  p.x = bptr(x); p.y = const_cast<__nv_bfloat16*>(bptr(dy)); p.dw = dw.data_ptr<float>();
+  B200_CUDA_OK(b200_dw_wgrad(&p, cur_stream()));
 }
 
 // ---------------------------------------------------------------------------------------------- peer contexts
@@ -309,10 +355,6 @@ struct PeerState {
   }
 };
 
-const float* fptr(const c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
-float* fptr_mut(c10::optional<at::Tensor>& t) { return t.has_value() ? t->data_ptr<float>() : nullptr; }
-const __nv_bfloat16* bptr(const at::Tensor& t) { return reinterpret_cast<const __nv_bfloat16*>(t.data_ptr()); }
-__nv_bfloat16* bptr_mut(at::Tensor& t) { return reinterpret_cast<__nv_bfloat16*>(t.data_ptr()); }
 
 // y/out/residual are [rows, C] views (last dim contiguous, arbitrary row pitch).
 void bn_apply(const at::Tensor& y, const c10::optional<at::Tensor>& residual, at::Tensor& out, const at::Tensor& stats,
@@ -501,7 +543,8 @@ void rank_barrier(CommState* cs) {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "distribuuuu_b200 sm_100a kernels";
   m.def("conv_fprop", &conv_fprop, "tcgen05 implicit-GEMM convolution forward (NHWC bf16)");
-  m.def("conv_dgrad", &conv_dgrad, "tcgen05 implicit-GEMM data gradient (stride 1)");
+  m.def("conv_dgrad", &conv_dgrad, "tcgen05 implicit-GEMM data gradient (stride 1), optional fused addend",
+        py::arg("dy"), py::arg("w"), py::arg("dx"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("addend") = py::none());
   m.def("conv_wgrad", &conv_wgrad, "tcgen05 split-K weight gradient (fp32 accumulate)");
   py::class_<PeerState>(m, "PeerState")
       .def(py::init<>())
@@ -517,6 +560,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("mc_stage", &CommState::mc_stage).def_readwrite("mc_w16", &CommState::mc_w16)
       .def_readwrite("local_counter", &CommState::local_counter).def_readwrite("local_release", &CommState::local_release)
       .def_readwrite("epoch", &CommState::epoch);
+  m.def("dw_fprop", &dw_fprop, "depthwise conv forward (+BN statistics)");
+  m.def("dw_dgrad", &dw_dgrad);
+  m.def("dw_wgrad", &dw_wgrad);
   m.def("bn_apply", &bn_apply);
   m.def("bn_stats", &bn_stats);
   m.def("bn_backward", &bn_backward);

@@ -70,7 +70,8 @@ __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int ite
 template <int BN, int EPI>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_add,
+                 const __grid_constant__ ConvGemmParams p) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
@@ -83,7 +84,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   uint64_t* empty_bar = bars + C::kStages;         // [kStages] MMA -> TMA
   uint64_t* tmem_full = bars + 2 * C::kStages;     // [2] MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;            // [2] epilogue -> MMA
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* add_bar = tmem_empty + 2;              // [kEpiWarps] addend-tile loads (epilogue only)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(add_bar + kEpiWarps);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -94,6 +96,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (EPI == EPI_BF16) tma_prefetch_desc(&map_out);
     for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiThreads); }
+    for (int i = 0; i < kEpiWarps; ++i) mbar_init(smem_u32(&add_bar[i]), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -205,6 +208,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // staging: own double buffer per warp; in the cooperative (NCH == 1) case both warps of a quarter use half 0's
       uint8_t* my_stage = smem_stage_out + ((NCH == 1 ? 0 : half) * 4 + quarter) * 8192;
       const uint32_t pair_bar = 1 + quarter;      // named barrier id shared by the two warps of a quarter
+      // optional addend (e.g. the residual-branch gradient in a dgrad): its tile is TMA-loaded into the staging
+      // buffer first and summed in registers, which removes a separate elementwise add pass
+      const bool has_add = (p.addend != 0);
+      const uint32_t my_add_bar = smem_u32(&add_bar[(NCH == 1 ? 0 : half) * 4 + quarter]);
+      uint32_t add_phase = 0;
 
       auto flush_stats = [&](int nb) {
         if (nb < 0) return;
@@ -233,6 +241,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int col = col_first + j;
             const float b = (col < p.N) ? __ldg(p.bias + col) : 0.f;
             v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
+          }
+        }
+        if (has_add) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const uint4 ad = *reinterpret_cast<const uint4*>(sbuf + lane * 128 + (((g0 + g) ^ (lane & 7)) << 4));
+            const uint32_t aw[4] = {ad.x, ad.y, ad.z, ad.w};
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              v[8 * g + 2 * t] = __float_as_uint(__uint_as_float(v[8 * g + 2 * t]) + __uint_as_float(aw[t] << 16));
+              v[8 * g + 2 * t + 1] = __float_as_uint(__uint_as_float(v[8 * g + 2 * t + 1]) + __uint_as_float(aw[t] & 0xffff0000u));
+            }
           }
         }
 #pragma unroll
@@ -268,8 +288,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
         if constexpr (NCH == 1) {
           uint8_t* sbuf = my_stage + buf * 4096;
-          if (half == 0 && lane == 0) bulk_wait_group_read<1>();
+          if (half == 0 && lane == 0) {
+            bulk_wait_group_read<1>();
+            if (has_add) {
+              mbar_expect_tx(my_add_bar, 4096);
+              tma_load_3d(smem_u32(sbuf), &map_add, my_add_bar, w.n0, row_base, 0);
+            }
+          }
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // buffer is free, both warps present
+          if (has_add) { mbar_wait(my_add_bar, add_phase); add_phase ^= 1; }
           stage_32cols(sbuf, tacc + half * 32, w.n0 + half * 32, half * 4);
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // whole 32x64 tile staged
@@ -286,8 +313,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int col0 = w.n0 + c * 64;
             if (col0 >= p.N) continue;                   // chunk entirely past the N edge
             uint8_t* sbuf = my_stage + buf * 4096;
-            if (lane == 0) bulk_wait_group_read<1>();     // the TMA store that last read this buffer has drained
+            if (lane == 0) {
+              bulk_wait_group_read<1>();                  // the TMA store that last read this buffer has drained
+              if (has_add) {
+                mbar_expect_tx(my_add_bar, 4096);
+                tma_load_3d(smem_u32(sbuf), &map_add, my_add_bar, col0, row_base, 0);
+              }
+            }
             __syncwarp();
+            if (has_add) { mbar_wait(my_add_bar, add_phase); add_phase ^= 1; }
             stage_32cols(sbuf, tacc + c * 64, col0, 0);
             stage_32cols(sbuf, tacc + c * 64 + 32, col0 + 32, 4);
             fence_proxy_async_smem();
@@ -357,7 +391,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 }
 
 template <int BN, int EPI>
-static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo,
+static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& md,
                               const ConvGemmParams& p, int grid, cudaStream_t stream) {
   using C = Cfg<BN>;
   auto kern = conv_gemm_kernel<BN, EPI>;
@@ -367,24 +401,25 @@ static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, cons
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ma, mb, mo, p);
+  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ma, mb, mo, md, p);
   return cudaGetLastError();
 }
 
 }  // namespace b200
 
 extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap* map_b, const CUtensorMap* map_out,
-                                     const ConvGemmParams* p, int bn, int grid, cudaStream_t stream) {
+                                     const CUtensorMap* map_add, const ConvGemmParams* p, int bn, int grid,
+                                     cudaStream_t stream) {
   using namespace b200;
   cudaError_t e = cudaErrorInvalidValue;
   if (p->epi == EPI_BF16) {
-    if (bn == 64) e = launch_one<64, EPI_BF16>(*map_a, *map_b, *map_out, *p, grid, stream);
-    else if (bn == 128) e = launch_one<128, EPI_BF16>(*map_a, *map_b, *map_out, *p, grid, stream);
-    else if (bn == 256) e = launch_one<256, EPI_BF16>(*map_a, *map_b, *map_out, *p, grid, stream);
+    if (bn == 64) e = launch_one<64, EPI_BF16>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
+    else if (bn == 128) e = launch_one<128, EPI_BF16>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
+    else if (bn == 256) e = launch_one<256, EPI_BF16>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
   } else {
-    if (bn == 64) e = launch_one<64, EPI_F32_RED>(*map_a, *map_b, *map_out, *p, grid, stream);
-    else if (bn == 128) e = launch_one<128, EPI_F32_RED>(*map_a, *map_b, *map_out, *p, grid, stream);
-    else if (bn == 256) e = launch_one<256, EPI_F32_RED>(*map_a, *map_b, *map_out, *p, grid, stream);
+    if (bn == 64) e = launch_one<64, EPI_F32_RED>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
+    else if (bn == 128) e = launch_one<128, EPI_F32_RED>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
+    else if (bn == 256) e = launch_one<256, EPI_F32_RED>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
   }
   return (int)e;
 }

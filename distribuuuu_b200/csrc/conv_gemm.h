@@ -31,10 +31,12 @@ struct ConvGemmParams {
   long long tap_stride; // wgrad: element offset between taps inside one output row
   float* stats;         // optional [2][N] per-column sum / sum of squares (fp32, atomically accumulated)
   const float* bias;    // optional [N]
+  long long addend;     // non-zero: add the bf16 tile described by map_add before storing (same geometry as out)
   int total_items;
 };
 
 // map_out: 2-D tiled map over the bf16 output [M][N] (box 64 cols x 32 rows, 128B swizzle) for the TMA-store
 // epilogue; ignored (pass any valid map) for EPI_F32_RED.
 extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap* map_b, const CUtensorMap* map_out,
-                                     const ConvGemmParams* p, int bn, int grid, cudaStream_t stream);
+                                     const CUtensorMap* map_add, const ConvGemmParams* p, int bn, int grid,
+                                     cudaStream_t stream);

@@ -70,7 +70,8 @@ class BasicBlock(nn.Module):
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
         out = Fn.conv_bn_act(x, self.conv1, self.bn1, "relu")
-        return Fn.conv_bn_act(out, self.conv2, self.bn2, "relu", residual=identity)
+        sink = self.conv1 if self.downsample is None else None   # identity shortcut: conv1 reads the same tensor
+        return Fn.conv_bn_act(out, self.conv2, self.bn2, "relu", residual=identity, residual_sink=sink)
 
 
 class Bottleneck(nn.Module):
@@ -95,7 +96,8 @@ class Bottleneck(nn.Module):
         identity = x if self.downsample is None else self.downsample(x)
         out = Fn.conv_bn_act(x, self.conv1, self.bn1, "relu")
         out = Fn.conv_bn_act(out, self.conv2, self.bn2, "relu")
-        return Fn.conv_bn_act(out, self.conv3, self.bn3, "relu", residual=identity)
+        sink = self.conv1 if self.downsample is None else None   # identity shortcut: conv1 reads the same tensor
+        return Fn.conv_bn_act(out, self.conv3, self.bn3, "relu", residual=identity, residual_sink=sink)
 
 
 class ResNet(nn.Module):

@@ -31,6 +31,20 @@ def _nchw_view(x_nhwc: torch.Tensor) -> torch.Tensor:
     return x_nhwc.permute(0, 3, 1, 2)
 
 
+class _GradSink:
+    """Mailbox between a BnActFn (producer of a residual-branch gradient) and the ConvFn that consumes the same
+    block input: the gradient is added inside that conv's dgrad epilogue instead of by a separate add kernel."""
+
+    __slots__ = ("ptr", "pending")
+
+    def __init__(self, ptr):
+        self.ptr, self.pending = ptr, None
+
+    def take(self):
+        t, self.pending = self.pending, None
+        return t
+
+
 class ConvFn(torch.autograd.Function):
     """Implicit-GEMM convolution (fprop / dgrad / wgrad on tcgen05), optional BN-statistics epilogue."""
 
@@ -49,6 +63,9 @@ class ConvFn(torch.autograd.Function):
         ctx.eng, ctx.conv = eng, conv
         ctx.save_for_backward(xh)
         ctx.x_needs_grad = x.requires_grad
+        # a later BnActFn whose residual IS this input may hand us its residual gradient (fused into our dgrad)
+        ctx.sink = _GradSink(xh.data_ptr()) if (x.requires_grad and s == 1) else None
+        eng.last_sink[conv] = ctx.sink
         return _nchw_view(y)
 
     @staticmethod
@@ -64,7 +81,8 @@ class ConvFn(torch.autograd.Function):
             w = eng.w16_krsc(conv.weight)
             if s == 1:
                 dxh = torch.empty_like(xh)
-                K.conv_dgrad(dyh, w, dxh, 1, p, d)
+                addend = ctx.sink.take() if ctx.sink is not None else None
+                K.conv_dgrad(dyh, w, dxh, 1, p, d, addend)
             else:
                 dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d)
             dx = _nchw_view(dxh)
@@ -82,7 +100,7 @@ def _strided_dgrad(K, dyh, w, x_shape, s, p, d):
         # 1x1 strided conv: only the sampled pixels receive gradient -> compact pointwise dgrad + strided scatter
         Pc, Qc = dyh.shape[1], dyh.shape[2]
         compact = torch.empty((N, Pc, Qc, C), dtype=dyh.dtype, device=dyh.device)
-        K.conv_dgrad(dyh, w, compact, 1, 0, 1)
+        K.conv_dgrad(dyh, w, compact, 1, 0, 1, None)
         dxh = torch.zeros((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
         dxh[:, ::s, ::s, :][:, :Pc, :Qc] = compact
         return dxh
@@ -91,8 +109,43 @@ def _strided_dgrad(K, dyh, w, x_shape, s, p, d):
     up = torch.zeros((N, P1, Q1, Kc), dtype=dyh.dtype, device=dyh.device)
     up[:, ::s, ::s, :][:, : dyh.shape[1], : dyh.shape[2]] = dyh
     dxh = torch.empty((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
-    K.conv_dgrad(up, w, dxh, 1, p, d)
+    K.conv_dgrad(up, w, dxh, 1, p, d, None)
     return dxh
+
+
+class DwConvFn(torch.autograd.Function):
+    """Depthwise kxk convolution (k <= 5, stride 1/2) on the CUDA-core kernels of ``csrc/dwconv.cu``."""
+
+    @staticmethod
+    def forward(ctx, x, eng, conv, stats, anchor):
+        K = eng.K
+        xh = _nhwc(x)
+        N, H, W, C = xh.shape
+        k, s, p = conv.kernel_size[0], conv.stride[0], conv.padding[0]
+        P, Q = (H + 2 * p - k) // s + 1, (W + 2 * p - k) // s + 1
+        y = torch.empty((N, P, Q, C), dtype=torch.bfloat16, device=x.device)
+        K.dw_fprop(xh, eng.w16_view(conv.weight).view(C, k, k), y, stats, k, s, p)
+        ctx.eng, ctx.conv, ctx.geom = eng, conv, (k, s, p)
+        ctx.save_for_backward(xh)
+        ctx.x_needs_grad = x.requires_grad
+        return _nchw_view(y)
+
+    @staticmethod
+    def backward(ctx, dy):
+        eng, conv = ctx.eng, ctx.conv
+        K = eng.K
+        (xh,) = ctx.saved_tensors
+        k, s, p = ctx.geom
+        C = xh.shape[-1]
+        dyh = _nhwc(dy)
+        K.dw_wgrad(dyh, xh, eng.grad_flat_view(conv.weight).view(C, k, k), k, s, p)
+        dx = None
+        if ctx.x_needs_grad:
+            dxh = torch.empty_like(xh)
+            K.dw_dgrad(dyh, eng.w16_view(conv.weight).view(C, k, k), dxh, k, s, p)
+            dx = _nchw_view(dxh)
+        eng.mark_ready(conv.weight)
+        return dx, None, None, None, None
 
 
 class StemConvFn(torch.autograd.Function):
@@ -139,7 +192,7 @@ class BnActFn(torch.autograd.Function):
     passes backward; SyncBN statistics are exchanged through peer memory inside the same kernels."""
 
     @staticmethod
-    def forward(ctx, y, residual, eng, bn, act, stats_slot, training, anchor):
+    def forward(ctx, y, residual, eng, bn, act, stats_slot, training, anchor, sink=None):
         K = eng.K
         yh = _nhwc(y)
         N, H, W, C = yh.shape
@@ -159,6 +212,9 @@ class BnActFn(torch.autograd.Function):
         ctx.eng, ctx.bn, ctx.act, ctx.count = eng, bn, act, count
         ctx.has_res = residual is not None
         ctx.res_needs_grad = residual is not None and residual.requires_grad
+        # only fuse when the sink's conv really consumes this very tensor
+        ctx.sink = sink if (sink is not None and residual is not None and ctx.res_needs_grad
+                            and _nhwc(residual).data_ptr() == sink.ptr) else None
         need_res = residual is not None and act is not None
         ctx.save_for_backward(y2, res2 if need_res else None, save)
         ctx.shape = (N, H, W, C)
@@ -183,7 +239,10 @@ class BnActFn(torch.autograd.Function):
         if bn.affine:
             eng.mark_ready(bn.weight)
             eng.mark_ready(bn.bias)
-        return _nchw_view(dy), (_nchw_view(dres) if dres is not None else None), None, None, None, None, None, None
+        if ctx.sink is not None and dres is not None:
+            ctx.sink.pending = dres      # consumed by the dgrad of the conv that reads the same block input
+            dres = None
+        return _nchw_view(dy), (_nchw_view(dres) if dres is not None else None), None, None, None, None, None, None, None
 
 
 class LinearFn(torch.autograd.Function):
@@ -212,7 +271,7 @@ class LinearFn(torch.autograd.Function):
         if fc.bias is not None:
             eng.grad_flat_view(fc.bias).add_(d2.float().sum(0))
         dx = torch.empty((B, 1, 1, Cin), dtype=torch.bfloat16, device=dout.device)
-        K.conv_dgrad(d2.view(B, 1, 1, Kc), eng.w16_view(fc.weight).view(Kc, 1, 1, Cin), dx, 1, 0, 1)
+        K.conv_dgrad(d2.view(B, 1, 1, Kc), eng.w16_view(fc.weight).view(Kc, 1, 1, Cin), dx, 1, 0, 1, None)
         eng.mark_ready(fc.weight)
         if fc.bias is not None:
             eng.mark_ready(fc.bias)
@@ -310,6 +369,13 @@ class NativeOps:
                 and x.dtype == torch.bfloat16 and conv.padding_mode == "zeros")
 
     @staticmethod
+    def _depthwise_ok(conv: nn.Conv2d, x) -> bool:
+        kh, kw = conv.kernel_size
+        return (conv.groups == conv.in_channels == conv.out_channels and conv.groups > 1 and conv.bias is None
+                and kh == kw and kh <= 5 and conv.stride[0] == conv.stride[1] and conv.padding[0] == conv.padding[1]
+                and conv.dilation == (1, 1) and conv.in_channels % 8 == 0 and x.dtype == torch.bfloat16)
+
+    @staticmethod
     def _is_stem(conv: nn.Conv2d, x) -> bool:
         return (conv.in_channels < 8 and conv.groups == 1 and conv.bias is None and x.dtype == torch.float32
                 and conv.out_channels % 8 == 0 and conv.dilation[0] == 1)
@@ -330,7 +396,7 @@ class NativeOps:
         return F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
 
     # ---- functional surface ----------------------------------------------------------------------
-    def conv_bn_act(self, x, conv, bn, act, residual):
+    def conv_bn_act(self, x, conv, bn, act, residual, residual_sink=None):
         eng = self.eng
         training = bn is not None and bn.training
         slot = eng.fwd_slot(bn) if (training and conv.out_channels % 8 == 0) else None
@@ -339,6 +405,8 @@ class NativeOps:
             y = StemConvFn.apply(x, eng, conv, stats, eng.anchor)
         elif self._native_conv_ok(conv, x):
             y = ConvFn.apply(x, eng, conv, stats, eng.anchor)
+        elif self._depthwise_ok(conv, x):
+            y = DwConvFn.apply(x, eng, conv, stats, eng.anchor)
         else:
             y = self._torch_conv(x, conv)
             if stats is not None:
@@ -355,7 +423,8 @@ class NativeOps:
             if residual is not None:
                 y = y + residual
             return _torch_act(y, act)
-        return BnActFn.apply(y, residual, eng, bn, act, slot, training, eng.anchor)
+        sink = eng.last_sink.get(residual_sink) if (residual_sink is not None and torch.is_grad_enabled()) else None
+        return BnActFn.apply(y, residual, eng, bn, act, slot, training, eng.anchor, sink)
 
     def bn_act(self, x, bn, act):
         eng = self.eng

@@ -122,6 +122,7 @@ class NativeEngine(nn.Module):
         self._scratch: Dict[str, torch.Tensor] = {}
         self._leaves: Dict[nn.Parameter, torch.Tensor] = {}
         self._bn_stepped: List[torch.Tensor] = []
+        self.last_sink: Dict[nn.Module, object] = {}   # conv module -> gradient mailbox of its latest forward
         self._step_parity = 0
         self.comm_stream = torch.cuda.Stream(device)
         # autograd anchor: lets Functions whose tensor inputs carry no grad (first layer) still get a backward call
@@ -406,6 +407,7 @@ class NativeEngine(nn.Module):
         base = self._step_parity * self.stats_len
         self.stats_buf[base:base + self.stats_len].zero_()
         self._bn_stepped.clear()
+        self.last_sink.clear()
 
     def train_step(self, inputs, targets, optimizer, topk: int):
         assert optimizer is self.optimizer, "the native engine steps its own FusedSGD (utils.construct_optimizer)"

@@ -240,6 +240,33 @@ def check_sgd(n=4096 * 8 + 64, steps=3):
     return {"master": e_w, "momentum": e_m, "bf16": e_16}
 
 
+def check_depthwise(N=4, H=14, W=14, C=96, k=5, stride=2):
+    Kmod = _K()
+    pad = k // 2
+    P, Q = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    x = _bf16(N, H, W, C, seed=20)
+    w = _bf16(C, k, k, scale=1.0 / k, seed=21)
+    dy = _bf16(N, P, Q, C, seed=22)
+    y = torch.empty((N, P, Q, C), dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2 * C, device="cuda")
+    Kmod.dw_fprop(x, w, y, st, k, stride, pad)
+    dx = torch.empty_like(x)
+    Kmod.dw_dgrad(dy, w, dx, k, stride, pad)
+    dw = torch.zeros((C, k, k), device="cuda")
+    Kmod.dw_wgrad(dy, x, dw, k, stride, pad)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = w.float().view(C, 1, k, k).clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, stride, pad, 1, C)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    yf = y.float().view(-1, C)
+    errs = {"y": _rel_err(y, yr.permute(0, 2, 3, 1)), "dx": _rel_err(dx, xr.grad.permute(0, 2, 3, 1)),
+            "dw": _rel_err(dw, wr.grad.view(C, k, k)), "stats": _rel_err(st[:C], yf.sum(0)),
+            "stats_sq": _rel_err(st[C:], (yf * yf).sum(0))}
+    assert all(v < 2e-2 for v in errs.values()), errs
+    return errs
+
+
 def check_stem():
     Kmod = _K()
     x = torch.randn(2, 3, 32, 32, device="cuda")

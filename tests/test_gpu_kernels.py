@@ -28,6 +28,12 @@ def test_batchnorm_kernels(act, residual, C):
     selftest.check_bn(act=act, residual=residual, C=C)
 
 
+@pytest.mark.parametrize("k,stride,C", [(3, 1, 32), (5, 2, 96), (3, 2, 144)])
+def test_depthwise_conv_kernels(k, stride, C):
+    from distribuuuu_b200 import selftest
+    selftest.check_depthwise(k=k, stride=stride, C=C)
+
+
 def test_pool_kernels():
     from distribuuuu_b200 import selftest
     selftest.check_pools()

@@ -28,6 +28,8 @@ def registry():
         "ce_topk": st.check_ce_topk,
         "sgd": st.check_sgd,
         "stem": st.check_stem,
+        "depthwise_5x5_s2": lambda: st.check_depthwise(k=5, stride=2),
+        "depthwise_3x3_s1": lambda: st.check_depthwise(k=3, stride=1, C=32, H=16, W=16),
         "engine_resnet18": lambda: st.check_engine_vs_torch("resnet18", batch=16, size=64),
         "engine_resnet50": lambda: st.check_engine_vs_torch("resnet50", batch=8, size=64),
         "engine_resnext50": lambda: st.check_engine_vs_torch("resnext50_32x4d", batch=8, size=64, tol=0.15),
