@@ -214,7 +214,7 @@ def run_ours(args):
                "clocks": clocks, "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1)}
         if e2e is not None:
             out["e2e"] = e2e
-        print(json.dumps(out), flush=True)
+        _emit(out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -255,7 +255,7 @@ class _TimedLoader:
 def run_reference(args):
     ref_dir = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.isdir(os.path.join(ref_dir, "distribuuuu")):
-        print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref missing (run baseline/install_reference.sh)"}))
+        _emit({"impl": "reference", "unavailable": "baseline/_ref missing (run baseline/install_reference.sh)"})
         return
     sys.path.insert(0, os.path.join(ROOT, "baseline", "shims"))
     sys.path.insert(0, ref_dir)
@@ -272,7 +272,7 @@ def run_reference(args):
         from distribuuuu import models as ref_models, trainer as ref_trainer, utils as ref_utils
         from distribuuuu.config import cfg as rcfg
     except Exception as exc:
-        print(json.dumps({"impl": "reference", "unavailable": f"import failed: {type(exc).__name__}: {exc}"}))
+        _emit({"impl": "reference", "unavailable": f"import failed: {type(exc).__name__}: {exc}"})
         return
     rcfg.MODEL.ARCH, rcfg.MODEL.SYNCBN, rcfg.MODEL.DUMMY_INPUT = args.arch, not args.no_syncbn, True
     rcfg.TRAIN.BATCH_SIZE, rcfg.TRAIN.PRINT_FREQ = args.batch, 10 ** 9
@@ -323,8 +323,27 @@ def run_reference(args):
     dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def _quiet_stdout():
+    """Library banners (e.g. 'NCCL version ...') go to fd 1; the contract is ONE JSON line on stdout, so fd 1 is
+    pointed at stderr for the duration of the run and the JSON is written to the saved descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
     args = parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

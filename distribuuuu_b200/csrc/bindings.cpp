@@ -80,6 +80,30 @@ CUtensorMap tiled_map_3d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
   return m;
 }
 
+// Rank-4 tiled map (weights viewed as (Cin/g, taps, Cout/g, groups)); strides in ELEMENTS for d1..d3.
+CUtensorMap tiled_map_4d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, uint64_t s1, uint64_t s2,
+                         uint64_t s3, uint32_t b0, uint32_t b1, uint32_t b2, uint32_t b3) {
+  MapKey key{{(uint64_t)ptr, d0, d1, d2, d3, s1, s2, s3, ((uint64_t)b0 << 32) | b1, ((uint64_t)b2 << 32) | b3, 0, 3}};
+  std::lock_guard<std::mutex> lock(g_map_mutex);
+  auto it = g_map_cache.find(key);
+  if (it != g_map_cache.end()) return it->second;
+  static EncodeTiledFn encode = driver_fn<EncodeTiledFn>("cuTensorMapEncodeTiled");
+  TORCH_CHECK(((uintptr_t)ptr & 15) == 0, "TMA base address must be 16-byte aligned");
+  TORCH_CHECK((s1 * 2) % 16 == 0 && (s2 * 2) % 16 == 0 && (s3 * 2) % 16 == 0, "TMA strides must be multiples of 16 bytes");
+  CUtensorMap m;
+  cuuint64_t dims[4] = {d0, d1, d2, d3};
+  cuuint64_t strides[3] = {s1 * 2, s2 * 2, s3 * 2};
+  cuuint32_t box[4] = {b0, b1, b2, b3};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  TORCH_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(4d) failed with ", (int)r);
+  if (g_map_cache.size() > 8192) g_map_cache.clear();
+  g_map_cache.emplace(key, m);
+  return m;
+}
+
 // im2col map over an NHWC bf16 activation (dims C, W, H, N).
 CUtensorMap im2col_map_4d(const void* ptr, int N, int H, int W, int C, int low_w, int low_h, int up_w, int up_h,
                           int stride, uint32_t channels_per_pixel, uint32_t pixels_per_column) {
@@ -148,11 +172,12 @@ cudaStream_t cur_stream() { return at::cuda::getCurrentCUDAStream().stream(); }
 
 struct ConvGeom { int N, H, W, C, K, R, S, P, Q, stride, pad, dil; };
 
-ConvGeom geom(const at::Tensor& x, const at::Tensor& w, int stride, int pad, int dil) {
+ConvGeom geom(const at::Tensor& x, const at::Tensor& w, int stride, int pad, int dil, int groups = 1) {
   ConvGeom g;
   g.N = x.size(0); g.H = x.size(1); g.W = x.size(2); g.C = x.size(3);
   g.K = w.size(0); g.R = w.size(1); g.S = w.size(2);
-  TORCH_CHECK(w.size(3) == g.C, "weight Cin ", w.size(3), " != activation channels ", g.C);
+  TORCH_CHECK(w.size(3) * groups == g.C && g.K % groups == 0, "weight [", g.K, ",", w.size(3), "] x groups ", groups,
+              " does not match activation channels ", g.C);
   g.stride = stride; g.pad = pad; g.dil = dil;
   g.P = (g.H + 2 * pad - dil * (g.R - 1) - 1) / stride + 1;
   g.Q = (g.W + 2 * pad - dil * (g.S - 1) - 1) / stride + 1;
@@ -162,20 +187,22 @@ ConvGeom geom(const at::Tensor& x, const at::Tensor& w, int stride, int pad, int
 // ---------------------------------------------------------------------------------------------- conv fprop
 // x [N,H,W,C], w [K,R,S,C], out [N,P,Q,K] (all bf16, contiguous).  stats: fp32 [2*K] accumulated, bias fp32 [K].
 void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const c10::optional<at::Tensor>& stats,
-                const c10::optional<at::Tensor>& bias, int64_t stride, int64_t pad, int64_t dil) {
+                const c10::optional<at::Tensor>& bias, int64_t stride, int64_t pad, int64_t dil, int64_t groups) {
   check_bf16_contig(x, "x"); check_bf16_contig(w, "w"); check_bf16_contig(out, "out");
   c10::cuda::CUDAGuard guard(x.device());
-  const ConvGeom g = geom(x, w, stride, pad, dil);
+  const ConvGeom g = geom(x, w, stride, pad, dil, groups);
   TORCH_CHECK(out.numel() == (int64_t)g.N * g.P * g.Q * g.K, "bad output shape");
-  TORCH_CHECK(g.C % 8 == 0 && g.K % 8 == 0, "channels must be multiples of 8 (C=", g.C, " K=", g.K, ")");
+  const int G = groups, cin_g = g.C / G, cout_g = g.K / G;
+  TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8 (", cin_g, ", ", cout_g, ")");
   const int M = g.N * g.P * g.Q;
-  const int bn = pick_bn(g.K);
+  const int bn = pick_bn(cout_g);
   const bool pointwise = (g.R == 1 && g.S == 1 && stride == 1 && pad == 0);
   ConvGemmParams p{};
   p.kind = KIND_FPROP; p.epi = EPI_BF16;
-  p.M = M; p.N = g.K;
-  p.m_blocks = (M + 127) / 128; p.n_blocks = (g.K + bn - 1) / bn;
-  p.taps = g.R * g.S; p.S = g.S; p.kb_per_tap = (g.C + 63) / 64; p.dil = dil;
+  p.M = M; p.N = cout_g;
+  p.groups = G; p.a_cg = cin_g; p.out_cg = cout_g;
+  p.m_blocks = (M + 127) / 128; p.n_blocks = (cout_g + bn - 1) / bn;
+  p.taps = g.R * g.S; p.S = g.S; p.kb_per_tap = (cin_g + 63) / 64; p.dil = dil;
   p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
   p.b_im2col = 0; p.b_nbox = 1; p.b_kstep16 = kKMajorStep16; p.b_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
   p.b_flip_taps = 0;
@@ -186,13 +213,15 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;
   p.bias = bias.has_value() ? bias->data_ptr<float>() : nullptr;
   if (stats.has_value()) TORCH_CHECK(stats->numel() >= 2 * g.K && stats->scalar_type() == at::kFloat, "stats must be fp32 [2*K]");
-  p.total_items = p.m_blocks * p.n_blocks;
+  p.vb_per_item = 0; p.cin_boxes = 1; p.vboxes_total = 0;
+  p.total_items = p.m_blocks * p.n_blocks * G;
   CUtensorMap ma = pointwise
                        ? tiled_map_3d(x.data_ptr(), g.C, 1, M, g.C, g.C, 64, 1, 128)
                        : im2col_map_4d(x.data_ptr(), g.N, g.H, g.W, g.C, -pad, -pad, pad - (g.S - 1) * dil,
                                        pad - (g.R - 1) * dil, stride, 64, 128);
-  CUtensorMap mb = tiled_map_3d(w.data_ptr(), g.C, p.taps, g.K, g.C, (uint64_t)p.taps * g.C, 64, 1, bn);
-  CUtensorMap mo = tiled_map_3d(out.data_ptr(), g.K, M, 1, g.K, (uint64_t)g.K * M, 64, 32, 1);
+  CUtensorMap mb = tiled_map_4d(w.data_ptr(), cin_g, p.taps, cout_g, G, cin_g, (uint64_t)p.taps * cin_g,
+                                (uint64_t)p.taps * cin_g * cout_g, 64, 1, bn, 1);
+  CUtensorMap mo = tiled_map_3d(out.data_ptr(), cout_g, M, G, g.K, cout_g, 64, 32, 1);
   const int grid = std::min(p.total_items, num_sms());
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &mo, &p, bn, grid, cur_stream()));
 }
@@ -200,25 +229,27 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
 // ---------------------------------------------------------------------------------------------- conv dgrad (stride 1)
 // dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C].
 void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64_t stride, int64_t pad, int64_t dil,
-                const c10::optional<at::Tensor>& addend) {
+                const c10::optional<at::Tensor>& addend, int64_t groups) {
   check_bf16_contig(dy, "dy"); check_bf16_contig(w, "w"); check_bf16_contig(dx, "dx");
   TORCH_CHECK(stride == 1, "tcgen05 dgrad handles stride 1 (strided layers use the zero-insertion path)");
   c10::cuda::CUDAGuard guard(dy.device());
   const int N = dx.size(0), H = dx.size(1), W = dx.size(2), C = dx.size(3);
   const int K = w.size(0), R = w.size(1), S = w.size(2);
   const int P = dy.size(1), Q = dy.size(2);
-  TORCH_CHECK(dy.size(3) == K && w.size(3) == C, "dgrad shape mismatch");
+  const int G = groups, cin_g = C / G, cout_g = K / G;
+  TORCH_CHECK(dy.size(3) == K && w.size(3) == cin_g, "dgrad shape mismatch");
   TORCH_CHECK(P == H + 2 * pad - dil * (R - 1) && Q == W + 2 * pad - dil * (S - 1), "dgrad: dy spatial size inconsistent");
-  TORCH_CHECK(C % 8 == 0 && K % 8 == 0, "channels must be multiples of 8");
+  TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8");
   const int M = N * H * W;
-  const int bn = pick_bn(C);
+  const int bn = pick_bn(cin_g);
   const bool pointwise = (R == 1 && S == 1 && pad == 0);
   const int padp_h = dil * (R - 1) - pad, padp_w = dil * (S - 1) - pad;  // padding of the transposed problem
   ConvGemmParams p{};
   p.kind = KIND_DGRAD; p.epi = EPI_BF16;
-  p.M = M; p.N = C;
-  p.m_blocks = (M + 127) / 128; p.n_blocks = (C + bn - 1) / bn;
-  p.taps = R * S; p.S = S; p.kb_per_tap = (K + 63) / 64; p.dil = dil;
+  p.M = M; p.N = cin_g;
+  p.groups = G; p.a_cg = cout_g; p.out_cg = cin_g;
+  p.m_blocks = (M + 127) / 128; p.n_blocks = (cin_g + bn - 1) / bn;
+  p.taps = R * S; p.S = S; p.kb_per_tap = (cout_g + 63) / 64; p.dil = dil;
   p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
   p.b_im2col = 0; p.b_nbox = bn / 64; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
   p.b_flip_taps = 1;
@@ -226,19 +257,20 @@ void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64
   p.im_P = H; p.im_Q = W; p.im_stride = 1; p.im_low_w = -padp_w; p.im_low_h = -padp_h;
   p.splits = 1;
   p.out = dx.data_ptr(); p.ldo = C;
-  p.total_items = p.m_blocks * p.n_blocks;
+  p.total_items = p.m_blocks * p.n_blocks * G;
   CUtensorMap ma = pointwise ? tiled_map_3d(dy.data_ptr(), K, 1, M, K, K, 64, 1, 128)
                              : im2col_map_4d(dy.data_ptr(), N, P, Q, K, -padp_w, -padp_h, padp_w - (S - 1) * dil,
                                              padp_h - (R - 1) * dil, 1, 64, 128);
   // weights viewed as (C inner, taps, K): MN-major B boxes of [64 k-rows (Cout)][64 n (Cin)]
-  CUtensorMap mb = tiled_map_3d(w.data_ptr(), C, p.taps, K, C, (uint64_t)p.taps * C, 64, 1, 64);
-  CUtensorMap mo = tiled_map_3d(dx.data_ptr(), C, M, 1, C, (uint64_t)C * M, 64, 32, 1);
+  CUtensorMap mb = tiled_map_4d(w.data_ptr(), cin_g, p.taps, cout_g, G, cin_g, (uint64_t)p.taps * cin_g,
+                                (uint64_t)p.taps * cin_g * cout_g, 64, 1, 64, 1);
+  CUtensorMap mo = tiled_map_3d(dx.data_ptr(), cin_g, M, G, C, cin_g, 64, 32, 1);
   CUtensorMap md = mo;
   if (addend.has_value()) {
     check_bf16_contig(*addend, "addend");
     TORCH_CHECK(addend->numel() == dx.numel(), "addend must have dx's shape");
     p.addend = 1;
-    md = tiled_map_3d(addend->data_ptr(), C, M, 1, C, (uint64_t)C * M, 64, 32, 1);
+    md = tiled_map_3d(addend->data_ptr(), cin_g, M, G, C, cin_g, 64, 32, 1);
   }
   const int grid = std::min(p.total_items, num_sms());
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &md, &p, bn, grid, cur_stream()));
@@ -246,21 +278,23 @@ void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64
 
 // ---------------------------------------------------------------------------------------------- conv wgrad
 // dy [N,P,Q,K], x [N,H,W,C] -> dw fp32 [K,R,S,C] (accumulated with red.add; caller zeroes).
-void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64_t stride, int64_t pad, int64_t dil) {
+void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64_t stride, int64_t pad, int64_t dil,
+                int64_t groups) {
   check_bf16_contig(dy, "dy"); check_bf16_contig(x, "x");
   TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.is_contiguous(), "dw must be contiguous fp32");
   c10::cuda::CUDAGuard guard(dy.device());
   const int N = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
   const int K = dw.size(0), R = dw.size(1), S = dw.size(2);
   const int P = dy.size(1), Q = dy.size(2);
-  TORCH_CHECK(dy.size(3) == K && dw.size(3) == C && dy.size(0) == N, "wgrad shape mismatch");
-  TORCH_CHECK(C % 8 == 0 && K % 8 == 0, "channels must be multiples of 8");
+  const int G = groups, cin_g = C / G, cout_g = K / G;
+  TORCH_CHECK(dy.size(3) == K && dw.size(3) == cin_g && dy.size(0) == N, "wgrad shape mismatch");
+  TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8");
   const long long pixels = (long long)N * P * Q;
   const bool pointwise = (R == 1 && S == 1 && stride == 1 && pad == 0);
   // B operand = "virtual boxes": (tap, 64-channel slice of Cin).  One work item accumulates up to 4 of them
   // (N = 64..256 TMEM columns) against a single load of the dY^T tile, so dY is re-read taps*Cin/(64*vpi) times
   // instead of taps*Cin/64 times.
-  const int cin_boxes = (C + 63) / 64;
+  const int cin_boxes = (cin_g + 63) / 64;
   const int vboxes = R * S * cin_boxes;
   int vpi = 1;
   for (int cand = 4; cand >= 1; --cand) if (vboxes % cand == 0) { vpi = cand; break; }
@@ -268,8 +302,9 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   const int bn = vpi > 2 ? 256 : (vpi == 2 ? 128 : 64);
   ConvGemmParams p{};
   p.kind = KIND_WGRAD; p.epi = EPI_F32_RED;
-  p.M = K; p.N = C;
-  p.m_blocks = (K + 127) / 128; p.n_blocks = (vboxes + vpi - 1) / vpi;
+  p.M = cout_g; p.N = cin_g;
+  p.groups = G; p.a_cg = cin_g; p.out_cg = cout_g;
+  p.m_blocks = (cout_g + 127) / 128; p.n_blocks = (vboxes + vpi - 1) / vpi;
   p.vb_per_item = vpi; p.cin_boxes = cin_boxes; p.vboxes_total = vboxes;
   p.taps = R * S; p.S = S; p.kb_per_tap = 0; p.dil = dil;
   p.a_im2col = 0; p.a_nbox = 2; p.a_kstep16 = kMnMajorStep16; p.a_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
@@ -278,7 +313,7 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   p.idesc = idesc_bf16(128, 64 * vpi, 1, 1);
   p.im_P = P; p.im_Q = Q; p.im_stride = stride; p.im_low_w = -pad; p.im_low_h = -pad;
   p.k_blocks_total = (int)((pixels + 63) / 64);
-  const int base_items = p.m_blocks * p.n_blocks;
+  const int base_items = p.m_blocks * p.n_blocks * G;
   // split-K so that the item count is just UNDER a whole number of waves (an extra partial wave costs a full
   // item time): aim at 2 waves, fall back to no split for shapes that already have many items
   const int sms = num_sms();
@@ -286,7 +321,7 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   if (splits < 1) splits = 1;
   splits = std::max(1, std::min(splits, std::max(1, p.k_blocks_total / 8)));
   p.splits = splits;
-  p.out = dw.data_ptr(); p.ldo = (long long)p.taps * C; p.tap_stride = C;
+  p.out = dw.data_ptr(); p.ldo = (long long)p.taps * cin_g; p.tap_stride = cin_g;
   p.total_items = base_items * splits;
   CUtensorMap ma = tiled_map_3d(dy.data_ptr(), K, 1, pixels, K, K, 64, 1, 64);
   CUtensorMap mb = pointwise ? tiled_map_3d(x.data_ptr(), C, 1, pixels, C, C, 64, 1, 64)
@@ -542,10 +577,13 @@ void rank_barrier(CommState* cs) {
 
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "distribuuuu_b200 sm_100a kernels";
-  m.def("conv_fprop", &conv_fprop, "tcgen05 implicit-GEMM convolution forward (NHWC bf16)");
+  m.def("conv_fprop", &conv_fprop, "tcgen05 implicit-GEMM convolution forward (NHWC bf16)", py::arg("x"), py::arg("w"),
+        py::arg("out"), py::arg("stats"), py::arg("bias"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("groups") = 1);
   m.def("conv_dgrad", &conv_dgrad, "tcgen05 implicit-GEMM data gradient (stride 1), optional fused addend",
-        py::arg("dy"), py::arg("w"), py::arg("dx"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("addend") = py::none());
-  m.def("conv_wgrad", &conv_wgrad, "tcgen05 split-K weight gradient (fp32 accumulate)");
+        py::arg("dy"), py::arg("w"), py::arg("dx"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("addend") = py::none(),
+        py::arg("groups") = 1);
+  m.def("conv_wgrad", &conv_wgrad, "tcgen05 split-K weight gradient (fp32 accumulate)", py::arg("dy"), py::arg("x"), py::arg("dw"),
+        py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("groups") = 1);
   py::class_<PeerState>(m, "PeerState")
       .def(py::init<>())
       .def_readwrite("world", &PeerState::world).def_readwrite("rank", &PeerState::rank)

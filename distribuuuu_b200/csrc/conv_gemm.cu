@@ -45,19 +45,23 @@ __device__ __forceinline__ PixelCoord decode_pixel(const ConvGemmParams& p, int 
   return {q * p.im_stride + p.im_low_w, ph * p.im_stride + p.im_low_h, n};
 }
 
-struct WorkItem { int m0, n0, nb, tap, it_begin, it_end, vb0, nbox; };
+struct WorkItem { int m0, n0, nb, tap, it_begin, it_end, vb0, nbox, g; };
 
 __device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn) {
   WorkItem w;
   if (p.kind != KIND_WGRAD) {
     int nb = item % p.n_blocks;
-    int mb = item / p.n_blocks;
-    w.m0 = mb * BM; w.n0 = nb * bn; w.nb = nb; w.tap = 0; w.vb0 = 0; w.nbox = 0;
+    int rest = item / p.n_blocks;
+    int mb = rest % p.m_blocks;
+    w.g = rest / p.m_blocks;                       // conv group (0 when groups == 1)
+    w.m0 = mb * BM; w.n0 = nb * bn; w.nb = w.g * p.n_blocks + nb; w.tap = 0; w.vb0 = 0; w.nbox = 0;
     w.it_begin = 0; w.it_end = p.taps * p.kb_per_tap;
   } else {
     // wgrad: an item owns `nbox` consecutive virtual B boxes (tap, 64-channel slice of Cin) -> N = 64*nbox columns
     int split = item % p.splits; int rest = item / p.splits;
-    int group = rest % p.n_blocks; int mb = rest / p.n_blocks;
+    int group = rest % p.n_blocks; rest /= p.n_blocks;
+    int mb = rest % p.m_blocks;
+    w.g = rest / p.m_blocks;
     w.m0 = mb * BM; w.n0 = 0; w.nb = group; w.tap = 0;
     w.vb0 = group * p.vb_per_item;
     w.nbox = min(p.vb_per_item, p.vboxes_total - w.vb0);
@@ -126,20 +130,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             const int tap = it / p.kb_per_tap;
             const int kb = it - tap * p.kb_per_tap;
             const int r = tap / p.S, s = tap - r * p.S;
+            const int ca = w.g * p.a_cg + kb * BK;         // A channel coordinate (group slice + K block)
             if (p.a_im2col)
-              tma_load_im2col_4d(dst_a, &map_a, bar, kb * BK, pa.w, pa.h, pa.n, (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+              tma_load_im2col_4d(dst_a, &map_a, bar, ca, pa.w, pa.h, pa.n, (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
             else
-              tma_load_3d(dst_a, &map_a, bar, kb * BK, 0, w.m0);
+              tma_load_3d(dst_a, &map_a, bar, ca, 0, w.m0);
             const int btap = p.b_flip_taps ? (p.taps - 1 - tap) : tap;
+            // weights are mapped as (Cin/g, taps, Cout/g, groups): anything past a group's extent is zero-filled
             if (p.kind == KIND_FPROP) {
-              tma_load_3d(dst_b, &map_b, bar, kb * BK, btap, w.n0);          // K-major weights [N][tap][K]
+              tma_load_4d(dst_b, &map_b, bar, kb * BK, btap, w.n0, w.g);      // K-major weights [N][tap][K]
             } else {
               for (int j = 0; j < p.b_nbox; ++j)                              // MN-major weights [K][tap][N]
-                tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + 64 * j, btap, kb * BK);
+                tma_load_4d(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + 64 * j, btap, kb * BK, w.g);
             }
           } else {
             const int k0 = it * BK;  // first reduction pixel of this block
-            for (int j = 0; j < p.a_nbox; ++j) tma_load_3d(dst_a + j * kBoxBytes, &map_a, bar, w.m0 + 64 * j, 0, k0);
+            for (int j = 0; j < p.a_nbox; ++j)
+              tma_load_3d(dst_a + j * kBoxBytes, &map_a, bar, w.g * p.out_cg + w.m0 + 64 * j, 0, k0);
             PixelCoord pb{0, 0, 0};
             if (p.b_im2col) pb = decode_pixel(p, k0);
             for (int j = 0; j < w.nbox; ++j) {
@@ -147,10 +154,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               const int tap = vb / p.cin_boxes, cbox = vb - tap * p.cin_boxes;
               if (p.b_im2col) {
                 const int r = tap / p.S, s = tap - r * p.S;
-                tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, cbox * 64, pb.w, pb.h, pb.n,
+                tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, w.g * p.a_cg + cbox * 64, pb.w, pb.h, pb.n,
                                    (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
               } else {
-                tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, cbox * 64, 0, k0);
+                tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, w.g * p.a_cg + cbox * 64, 0, k0);
               }
             }
           }
@@ -221,16 +228,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           if (NCH > 1 && (c & 1) != half) continue;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
-            const int col = nb * BN + c * 64 + 2 * lane + h;
+            // nb enumerates (group, n-block); p.N is the per-group column count, stats are [2][groups * N]
+            const int g = nb / p.n_blocks, col = (nb % p.n_blocks) * BN + c * 64 + 2 * lane + h;
             if (col < p.N) {
-              atomicAdd(p.stats + col, st_sum[c][h]);
-              atomicAdd(p.stats + p.N + col, st_sq[c][h]);
+              atomicAdd(p.stats + g * p.N + col, st_sum[c][h]);
+              atomicAdd(p.stats + p.groups * p.N + g * p.N + col, st_sq[c][h]);
             }
             st_sum[c][h] = 0.f; st_sq[c][h] = 0.f;
           }
         }
       };
       // 32 accumulator columns -> four swizzled 16-byte pieces (g0..g0+3) of this thread's staging row
+      int bias_off = 0;                              // group offset into the bias vector (set per item)
       auto stage_32cols = [&](uint8_t* sbuf, uint32_t taddr, int col_first, int g0) {
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr, v);
@@ -239,7 +248,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col_first + j;
-            const float b = (col < p.N) ? __ldg(p.bias + col) : 0.f;
+            const float b = (col < p.N) ? __ldg(p.bias + bias_off + col) : 0.f;
             v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
           }
         }
@@ -285,6 +294,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         tc_fence_after();
         const int row_base = w.m0 + quarter * 32;
         const int rows_valid = min(32, p.M - row_base);
+        bias_off = w.g * p.N;
         const uint32_t tacc = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN;
         if constexpr (NCH == 1) {
           uint8_t* sbuf = my_stage + buf * 4096;
@@ -292,7 +302,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             bulk_wait_group_read<1>();
             if (has_add) {
               mbar_expect_tx(my_add_bar, 4096);
-              tma_load_3d(smem_u32(sbuf), &map_add, my_add_bar, w.n0, row_base, 0);
+              tma_load_3d(smem_u32(sbuf), &map_add, my_add_bar, w.n0, row_base, w.g);
             }
           }
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // buffer is free, both warps present
@@ -301,7 +311,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           fence_proxy_async_smem();
           asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // whole 32x64 tile staged
           if (half == 0 && lane == 0) {
-            tma_store_3d(&map_out, smem_u32(sbuf), w.n0, row_base, 0);
+            tma_store_3d(&map_out, smem_u32(sbuf), w.n0, row_base, w.g);
             bulk_commit_group();
           }
           if (want_stats) column_stats(sbuf, half * 16, half * 16 + 16, rows_valid, 0);
@@ -317,7 +327,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               bulk_wait_group_read<1>();                  // the TMA store that last read this buffer has drained
               if (has_add) {
                 mbar_expect_tx(my_add_bar, 4096);
-                tma_load_3d(smem_u32(sbuf), &map_add, my_add_bar, col0, row_base, 0);
+                tma_load_3d(smem_u32(sbuf), &map_add, my_add_bar, col0, row_base, w.g);
               }
             }
             __syncwarp();
@@ -327,7 +337,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
-              tma_store_3d(&map_out, smem_u32(sbuf), col0, row_base, 0);
+              tma_store_3d(&map_out, smem_u32(sbuf), col0, row_base, w.g);
               bulk_commit_group();
             }
             if (want_stats) column_stats(sbuf, 0, 32, rows_valid, c);
@@ -363,7 +373,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const int tap = vb / p.cin_boxes, cbox = vb - tap * p.cin_boxes;
           const int col0 = cbox * 64 + (c & 1) * 32;    // channel offset inside the tap
           if (row_ok && col0 < p.N && has_k) {
-            float* dst = reinterpret_cast<float*>(p.out) + (long long)row * p.ldo + (long long)tap * p.tap_stride + col0;
+            float* dst = reinterpret_cast<float*>(p.out) + (long long)(w.g * p.out_cg + row) * p.ldo + (long long)tap * p.tap_stride + col0;
             if (col0 + 32 <= p.N && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
 #pragma unroll
               for (int g = 0; g < 8; ++g)

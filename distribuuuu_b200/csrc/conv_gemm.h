@@ -26,6 +26,7 @@ struct ConvGemmParams {
   int im_P, im_Q, im_stride, im_low_w, im_low_h;  // pixel enumeration of the im2col operand
   int k_blocks_total, splits;                     // wgrad: 64-pixel reduction blocks and split-K factor
   int vb_per_item, cin_boxes, vboxes_total;       // wgrad: B boxes (tap, 64-channel slice) handled by one work item
+  int groups, a_cg, out_cg;                       // grouped conv: #groups, A-operand channels per group, output channels per group
   void* out;
   long long ldo;        // output row pitch in elements
   long long tap_stride; // wgrad: element offset between taps inside one output row

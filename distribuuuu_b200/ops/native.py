@@ -59,7 +59,7 @@ class ConvFn(torch.autograd.Function):
         P = (H + 2 * p - d * (R - 1) - 1) // s + 1
         Q = (W + 2 * p - d * (S - 1) - 1) // s + 1
         y = torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
-        K.conv_fprop(xh, w, y, stats, None, s, p, d)
+        K.conv_fprop(xh, w, y, stats, None, s, p, d, conv.groups)
         ctx.eng, ctx.conv = eng, conv
         ctx.save_for_backward(xh)
         ctx.x_needs_grad = x.requires_grad
@@ -75,23 +75,23 @@ class ConvFn(torch.autograd.Function):
         (xh,) = ctx.saved_tensors
         dyh = _nhwc(dy)
         s, p, d = conv.stride[0], conv.padding[0], conv.dilation[0]
-        K.conv_wgrad(dyh, xh, eng.grad_krsc(conv.weight), s, p, d)
+        K.conv_wgrad(dyh, xh, eng.grad_krsc(conv.weight), s, p, d, conv.groups)
         dx = None
         if ctx.x_needs_grad:
             w = eng.w16_krsc(conv.weight)
             if s == 1:
                 dxh = torch.empty_like(xh)
                 addend = ctx.sink.take() if ctx.sink is not None else None
-                K.conv_dgrad(dyh, w, dxh, 1, p, d, addend)
+                K.conv_dgrad(dyh, w, dxh, 1, p, d, addend, conv.groups)
             else:
-                dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d)
+                dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d, conv.groups)
             dx = _nchw_view(dxh)
         # only now: the bucket's fused update overwrites the bf16 weights the dgrad above still reads
         eng.mark_ready(conv.weight)
         return dx, None, None, None, None
 
 
-def _strided_dgrad(K, dyh, w, x_shape, s, p, d):
+def _strided_dgrad(K, dyh, w, x_shape, s, p, d, groups=1):
     """Data gradient of a strided conv: scatter dy onto a zero-filled stride-1 grid, then run the stride-1
     tcgen05 dgrad (costs s^2 x the FLOPs of the few strided layers; a parity-decomposed kernel is future work)."""
     N, H, W, C = x_shape
@@ -100,7 +100,7 @@ def _strided_dgrad(K, dyh, w, x_shape, s, p, d):
         # 1x1 strided conv: only the sampled pixels receive gradient -> compact pointwise dgrad + strided scatter
         Pc, Qc = dyh.shape[1], dyh.shape[2]
         compact = torch.empty((N, Pc, Qc, C), dtype=dyh.dtype, device=dyh.device)
-        K.conv_dgrad(dyh, w, compact, 1, 0, 1, None)
+        K.conv_dgrad(dyh, w, compact, 1, 0, 1, None, groups)
         dxh = torch.zeros((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
         dxh[:, ::s, ::s, :][:, :Pc, :Qc] = compact
         return dxh
@@ -109,7 +109,7 @@ def _strided_dgrad(K, dyh, w, x_shape, s, p, d):
     up = torch.zeros((N, P1, Q1, Kc), dtype=dyh.dtype, device=dyh.device)
     up[:, ::s, ::s, :][:, : dyh.shape[1], : dyh.shape[2]] = dyh
     dxh = torch.empty((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
-    K.conv_dgrad(up, w, dxh, 1, p, d, None)
+    K.conv_dgrad(up, w, dxh, 1, p, d, None, groups)
     return dxh
 
 
@@ -363,9 +363,14 @@ class NativeOps:
     @staticmethod
     def _native_conv_ok(conv: nn.Conv2d, x) -> bool:
         kh, kw = conv.kernel_size
-        return (conv.groups == 1 and conv.bias is None and kh == kw and conv.stride[0] == conv.stride[1]
+        g = conv.groups
+        cin_g, cout_g = conv.in_channels // g, conv.out_channels // g
+        # grouped convs run as `g` independent implicit GEMMs in one launch; very thin groups (ResNeXt's 4-8
+        # channels) would waste the 64-wide K block, they stay on the library path
+        group_ok = g == 1 or (cin_g >= 32 and cout_g >= 32)
+        return (group_ok and conv.bias is None and kh == kw and conv.stride[0] == conv.stride[1]
                 and conv.padding[0] == conv.padding[1] and conv.dilation[0] == conv.dilation[1]
-                and isinstance(conv.padding, tuple) and conv.in_channels % 8 == 0 and conv.out_channels % 8 == 0
+                and isinstance(conv.padding, tuple) and cin_g % 8 == 0 and cout_g % 8 == 0
                 and x.dtype == torch.bfloat16 and conv.padding_mode == "zeros")
 
     @staticmethod

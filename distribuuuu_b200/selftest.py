@@ -86,6 +86,36 @@ def check_conv_wgrad(N=4, H=14, W=14, C=64, K=128, R=3, stride=1, pad=1, dil=1, 
     return {"rel_err": err}
 
 
+def check_grouped_conv(N=2, H=14, W=14, C=224, K=224, G=2, R=3, stride=1, pad=1, tol=2e-2):
+    """Grouped convolution (RegNet group widths): fprop (+stats), dgrad, wgrad against F.conv2d(groups=G)."""
+    Kmod = _K()
+    cin_g = C // G
+    P = (H + 2 * pad - (R - 1) - 1) // stride + 1
+    x = _bf16(N, H, W, C, seed=31)
+    w = _bf16(K, R, R, cin_g, scale=(cin_g * R * R) ** -0.5, seed=32)
+    dy = _bf16(N, P, P, K, seed=33)
+    y = torch.full((N, P, P, K), float("nan"), dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2 * K, device="cuda")
+    Kmod.conv_fprop(x, w, y, st, None, stride, pad, 1, G)
+    dw = torch.zeros((K, R, R, cin_g), device="cuda")
+    Kmod.conv_wgrad(dy, x, dw, stride, pad, 1, G)
+    errs = {}
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = w.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, stride, pad, 1, G)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    if stride == 1:
+        dx = torch.full((N, H, W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+        Kmod.conv_dgrad(dy, w, dx, 1, pad, 1, None, G)
+        errs["dx"] = _rel_err(dx, xr.grad.permute(0, 2, 3, 1))
+    torch.cuda.synchronize()
+    yf = y.float().view(-1, K)
+    errs.update(y=_rel_err(y, yr.permute(0, 2, 3, 1)), dw=_rel_err(dw, wr.grad.permute(0, 2, 3, 1)),
+                stats=_rel_err(st[:K], yf.sum(0)), stats_sq=_rel_err(st[K:], (yf * yf).sum(0)))
+    assert all(v < tol for v in errs.values()), errs
+    return errs
+
+
 CONV_CASES = {
     # name: (kind, kwargs)
     "fprop_1x1_k64": ("fprop", dict(N=2, H=28, W=28, C=64, K=64, R=1, pad=0)),
@@ -337,6 +367,7 @@ def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_class
     from .parallel.native_engine import NativeEngine
     from .trainer import TorchEngine
     torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = False  # the fp32 reference only runs a few steps: skip the autotuning
     dev = torch.device("cuda", torch.cuda.current_device())
     net_a = models.build_model(arch, num_classes=num_classes).to(dev)
     net_b = copy.deepcopy(net_a)

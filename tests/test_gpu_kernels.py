@@ -28,6 +28,12 @@ def test_batchnorm_kernels(act, residual, C):
     selftest.check_bn(act=act, residual=residual, C=C)
 
 
+@pytest.mark.parametrize("C,G,stride", [(224, 2, 1), (512, 4, 2), (696, 3, 1)])
+def test_grouped_conv_tcgen05(C, G, stride):
+    from distribuuuu_b200 import selftest
+    selftest.check_grouped_conv(C=C, K=C, G=G, stride=stride, H=28 if stride == 2 else 14, W=28 if stride == 2 else 14)
+
+
 @pytest.mark.parametrize("k,stride,C", [(3, 1, 32), (5, 2, 96), (3, 2, 144)])
 def test_depthwise_conv_kernels(k, stride, C):
     from distribuuuu_b200 import selftest

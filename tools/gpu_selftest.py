@@ -28,6 +28,9 @@ def registry():
         "ce_topk": st.check_ce_topk,
         "sgd": st.check_sgd,
         "stem": st.check_stem,
+        "grouped_regnety": lambda: st.check_grouped_conv(C=224, K=224, G=2),
+        "grouped_regnetx_s2": lambda: st.check_grouped_conv(C=512, K=512, G=4, stride=2, H=28, W=28),
+        "grouped_232": lambda: st.check_grouped_conv(C=696, K=696, G=3, H=14, W=14),
         "depthwise_5x5_s2": lambda: st.check_depthwise(k=5, stride=2),
         "depthwise_3x3_s1": lambda: st.check_depthwise(k=3, stride=1, C=32, H=16, W=16),
         "engine_resnet18": lambda: st.check_engine_vs_torch("resnet18", batch=16, size=64),
