@@ -318,7 +318,7 @@ def run_reference(args):
                "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8,
                        "d2h_bytes_per_step": 12, "note": "the reference loop is end-to-end by construction"},
                "clocks": clocks, "gpu_launches": 0}
-        print(json.dumps(out), flush=True)
+        _emit(out)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -344,6 +344,10 @@ def _emit(obj):
 def main():
     args = parse_args()
     _quiet_stdout()
+    import torch
+    if not torch.cuda.is_available():
+        _emit({"impl": args.impl, "unavailable": "no CUDA device visible (bench.py measures on B200)"})
+        return
     if args.impl == "reference":
         run_reference(args)
     else:
