@@ -636,23 +636,24 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     const int h = ph * stride - pad + r, w = wp - pad;
     tile[i] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(x + (((long long)n * C + c) * H + h) * W + w) : 0.f;
   }
+  // per-k lookup of the tile offset (c, r, s) -> (c*R + r)*Wp + s, built once per CTA (no div/mod in the hot loop)
+  __shared__ int koff[256];
+  const int kdim = R * S * C;
+  for (int k = threadIdx.x; k < Kpad && k < 256; k += blockDim.x) {
+    if (k < kdim) { const int c = k % C, rs = k / C; koff[k] = (c * R + rs / S) * Wp + rs % S; }
+    else koff[k] = -1;
+  }
   __syncthreads();
   const int vec_per_row = Kpad / 8;
-  const int kdim = R * S * C;
   __nv_bfloat16* out_row = patches + ((long long)n * P + ph) * Q * Kpad;
   for (int item = threadIdx.x; item < Q * vec_per_row; item += blockDim.x) {
     const int j8 = item % vec_per_row, q = item / vec_per_row;
+    const int base = q * stride;
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int k = j8 * 8 + i;
-      float val = 0.f;
-      if (k < kdim) {
-        const int c = k % C; const int rs = k / C;
-        const int s = rs % S, r = rs / S;
-        val = tile[(c * R + r) * Wp + q * stride + s];
-      }
-      v[i] = val;
+      const int o = koff[j8 * 8 + i];
+      v[i] = o >= 0 ? tile[o + base] : 0.f;
     }
     store8(out_row + (long long)q * Kpad + j8 * 8, v);
   }

@@ -394,3 +394,44 @@ def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_class
     assert all(l[0] == l[0] for l in losses), f"NaN loss {losses}"
     assert rel < tol, f"loss trajectories diverge: {losses}"
     return {"losses": losses, "max_rel_loss_diff": rel, "last_weight_drift": drift}
+
+
+def check_engine_grads(arch="efficientnet_b0", batch=16, size=128, num_classes=16, min_cos=0.98, report=8):
+    """One forward/backward on identical weights and data: per-parameter cosine similarity between the native
+    engine's flat fp32 gradients and the fp32 torch path.  Pinpoints which layer type disagrees."""
+    import copy
+    from . import models
+    from .ops import runtime
+    from .parallel.native_engine import NativeEngine
+    torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = False
+    dev = torch.device("cuda", torch.cuda.current_device())
+    net_a = models.build_model(arch, num_classes=num_classes).to(dev)
+    net_b = copy.deepcopy(net_a)
+    eng = NativeEngine(net_a, dev)
+    eng.make_optimizer(lr=0.05, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=True)
+    eng.train(), net_b.train()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(batch, 3, size, size, device=dev, generator=g)
+    y = torch.randint(0, num_classes, (batch,), device=dev, generator=g)
+    eng._begin_step()
+    eng._reset_pending()
+    with runtime.native_scope(eng):
+        loss_a, _, _ = eng.ops.cross_entropy_topk(eng.module(x), y, 5)
+    loss_a.backward()
+    loss_b = F.cross_entropy(net_b(x), y)
+    loss_b.backward()
+    torch.cuda.synchronize()
+    rows = []
+    for (name, pa), pb in zip(net_a.named_parameters(), net_b.parameters()):
+        ga = eng.logical_view(eng.flat_grad, pa).float().reshape(-1)
+        gb = pb.grad.float().reshape(-1)
+        cos = float(F.cosine_similarity(ga, gb, dim=0)) if float(gb.norm()) > 0 else 1.0
+        ratio = float(ga.norm() / gb.norm().clamp_min(1e-12))
+        rows.append((cos, ratio, name, tuple(pa.shape)))
+    rows.sort()
+    worst = [dict(cos=round(c, 4), norm_ratio=round(r, 3), name=n, shape=s) for c, r, n, s in rows[:report]]
+    out = {"loss_native": float(loss_a), "loss_torch": float(loss_b), "worst": worst,
+           "n_below": sum(1 for r in rows if r[0] < min_cos), "n_params": len(rows)}
+    assert out["n_below"] == 0, out
+    return out

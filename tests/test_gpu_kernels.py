@@ -66,11 +66,17 @@ def test_native_engine_tracks_fp32_reference(arch):
     selftest.check_engine_vs_torch(arch, batch=8, size=64)
 
 
-@pytest.mark.parametrize("arch,batch,size", [("resnext50_32x4d", 8, 64), ("densenet121", 8, 64), ("efficientnet_b0", 8, 64),
+@pytest.mark.parametrize("arch,batch,size", [("resnext50_32x4d", 8, 64), ("densenet121", 8, 64), ("efficientnet_b0", 16, 128),
                                              ("regnety_160", 4, 64), ("regnetx_160", 4, 64), ("botnet50", 4, 224)])
 def test_every_model_family_trains_on_native_engine(arch, batch, size):
     from distribuuuu_b200 import selftest
     selftest.check_engine_vs_torch(arch, batch=batch, size=size, tol=0.15)
+
+
+@pytest.mark.parametrize("arch,batch,size", [("resnet50", 16, 128), ("efficientnet_b0", 16, 128), ("regnety_160", 8, 128)])
+def test_native_gradients_match_fp32_per_parameter(arch, batch, size):
+    from distribuuuu_b200 import selftest
+    selftest.check_engine_grads(arch, batch=batch, size=size)
 
 
 def test_checkpoint_interop_native_vs_torch_optim():
