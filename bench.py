@@ -37,6 +37,7 @@ def parse_args():
     ap.add_argument("--no-syncbn", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--exposed", action="store_true", help="also time the step with the gradient exchange disabled and report the exposed all-reduce ms/step")
     return ap.parse_args()
 
 
@@ -184,6 +185,20 @@ def run_ours(args):
     clocks = sampler.stop()
     value = world * B * args.steps / sec
 
+    exposed = None
+    if args.exposed and world > 1:
+        eng.debug_skip_comm = True
+        for i in range(2):
+            step(i)
+        sec_nocomm = _timed(dev, step, args.steps)
+        eng.debug_skip_comm = False
+        eng.refresh_compute_weights()  # ranks diverged during the no-comm loop: restore a consistent state
+        if dist.get_world_size() > 1:
+            dist.broadcast(eng.flat_master, src=0)
+            eng.refresh_compute_weights()
+        exposed = {"ms_per_step_with_comm": sec * 1e3 / args.steps, "ms_per_step_without_comm": sec_nocomm * 1e3 / args.steps,
+                   "exposed_allreduce_ms_per_step": (sec - sec_nocomm) * 1e3 / args.steps}
+
     e2e = None
     if not args.skip_e2e:
         hx = [torch.randn(B, 3, 224, 224).pin_memory() for _ in range(nbuf)]
@@ -214,6 +229,8 @@ def run_ours(args):
                "clocks": clocks, "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1)}
         if e2e is not None:
             out["e2e"] = e2e
+        if exposed is not None:
+            out["exposed_allreduce"] = exposed
         _emit(out)
     dist.barrier()
     dist.destroy_process_group()

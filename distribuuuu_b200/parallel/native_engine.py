@@ -376,7 +376,7 @@ class NativeEngine(nn.Module):
         if b is None:
             return
         b.pending -= 1
-        if b.pending == 0 and self.world > 1 and self._in_train_step:
+        if b.pending == 0 and self.world > 1 and self._in_train_step and not self.debug_skip_comm:
             self._launch_bucket(b)
 
     def _launch_bucket(self, b: _Bucket):
@@ -396,6 +396,7 @@ class NativeEngine(nn.Module):
                                  lr, mom, damp, wd, nest, first, 1.0 / self.world, True)
 
     _in_train_step = False
+    debug_skip_comm = False   # measurement aid: update locally without any gradient exchange (ranks diverge!)
 
     # ------------------------------------------------------------------------------ steps
     def forward(self, x):
@@ -424,7 +425,7 @@ class NativeEngine(nn.Module):
         if self._bn_stepped:
             torch._foreach_add_(self._bn_stepped, 1)
         lr, mom, damp, wd, nest, first = optimizer.hyper()
-        if self.world == 1:
+        if self.world == 1 or self.debug_skip_comm:
             self.K.sgd_local(self.flat_master, self.flat_mom, self.flat_grad, self.flat_w16, 0, self.total,
                              lr, mom, damp, wd, nest, first, 1.0, True)
         else:
