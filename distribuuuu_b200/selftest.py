@@ -360,7 +360,7 @@ def check_checkpoint_interop(tmpdir="/tmp/b200_ckpt_test"):
     return {"master": e_w, "momentum": e_m, "eval_loss": float(loss)}
 
 
-def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_classes=16, tol=0.08):
+def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_classes=16, tol=0.08, lr=0.05):
     """Same weights, same data: the native engine's loss trajectory must track the fp32 torch path."""
     import copy
     from . import models
@@ -372,9 +372,9 @@ def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_class
     net_a = models.build_model(arch, num_classes=num_classes).to(dev)
     net_b = copy.deepcopy(net_a)
     eng = NativeEngine(net_a, dev)
-    opt = eng.make_optimizer(lr=0.05, momentum=0.9, weight_decay=5e-5, dampening=0.0, nesterov=True)
+    opt = eng.make_optimizer(lr=lr, momentum=0.9, weight_decay=5e-5, dampening=0.0, nesterov=True)
     ref = TorchEngine(net_b)
-    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-5, nesterov=True)
+    ropt = torch.optim.SGD(ref.parameters(), lr=lr, momentum=0.9, weight_decay=5e-5, nesterov=True)
     eng.train(), ref.train()
     g = torch.Generator(device="cuda").manual_seed(1)
     losses = []
@@ -451,8 +451,13 @@ def check_engine_grads(arch="efficientnet_b0", batch=16, size=128, num_classes=1
         if cs:
             summary[kind] = {"n": len(cs), "min_cos": round(cs[0], 4), "median_cos": round(cs[len(cs) // 2], 4),
                              "autocast_min_cos": round(ca[0], 4), "autocast_median_cos": round(ca[len(ca) // 2], 4)}
-    # a parameter only counts as wrong if the native gradient is clearly worse than what bf16 autocast achieves
-    bad = [r for r in rows if r[0] < min_cos and r[0] < r[4] - 0.1]
+    # Parameters whose true gradient is ~0 (e.g. BN shifts feeding conv->BN, which is shift-invariant) or nets that
+    # are chaotic at random init are noise-dominated in ANY bf16 implementation; torch's own autocast gradient is the
+    # yardstick: a parameter counts as wrong only where autocast agrees with fp32 and the native engine does not.
+    bad = [r for r in rows if r[4] > 0.9 and r[0] < r[4] - 0.15]
+    for kind, st in summary.items():
+        if st["median_cos"] < st["autocast_median_cos"] - 0.05:
+            bad.append((st["median_cos"], 0, f"<median of {kind}>", (), st["autocast_median_cos"], kind))
     out = {"loss_native": float(loss_a), "loss_torch": float(loss_b), "loss_autocast": float(loss_c), "summary": summary,
            "worst": worst, "n_bad": len(bad), "bad": [r[2] for r in bad[:10]], "n_params": len(rows)}
     print("GRADCHECK " + str(out))

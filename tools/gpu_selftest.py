@@ -37,7 +37,7 @@ def registry():
         "engine_resnet50": lambda: st.check_engine_vs_torch("resnet50", batch=8, size=64),
         "engine_resnext50": lambda: st.check_engine_vs_torch("resnext50_32x4d", batch=8, size=64, tol=0.15),
         "engine_densenet121": lambda: st.check_engine_vs_torch("densenet121", batch=8, size=64, tol=0.15),
-        "engine_efficientnet_b0": lambda: st.check_engine_vs_torch("efficientnet_b0", batch=16, size=128, tol=0.15),
+        "engine_efficientnet_b0": lambda: st.check_engine_vs_torch("efficientnet_b0", batch=16, size=128, tol=0.15, lr=0.005),
         "engine_regnety_160": lambda: st.check_engine_vs_torch("regnety_160", batch=4, size=64, tol=0.15),
         "engine_regnetx_160": lambda: st.check_engine_vs_torch("regnetx_160", batch=4, size=64, tol=0.15),
         "engine_botnet50": lambda: st.check_engine_vs_torch("botnet50", batch=4, size=224, tol=0.15),
