@@ -480,6 +480,21 @@ void avgpool2_bwd(const at::Tensor& dout, at::Tensor& dx) {
   B200_CUDA_OK(b200_avgpool2_bwd(dout.data_ptr(), dx.data_ptr(), dx.size(0), dx.size(1), dx.size(2), dx.size(3), cur_stream()));
 }
 
+// x/out/dout/dx: [N,H,W,C] bf16; gate: [N,C] bf16; dgate: [N,C] fp32 (accumulated).
+void channel_scale_fwd(const at::Tensor& x, const at::Tensor& gate, at::Tensor& out) {
+  check_bf16_contig(x, "x"); check_bf16_contig(gate, "gate"); check_bf16_contig(out, "out");
+  c10::cuda::CUDAGuard guard(x.device());
+  TORCH_CHECK(x.size(3) % 8 == 0 && gate.size(0) == x.size(0) && gate.size(1) == x.size(3), "channel_scale shapes");
+  B200_CUDA_OK(b200_channel_scale_fwd(x.data_ptr(), gate.data_ptr(), out.data_ptr(), x.size(0), x.size(1) * x.size(2), x.size(3), cur_stream()));
+}
+void channel_scale_bwd(const at::Tensor& dout, const at::Tensor& x, const at::Tensor& gate, at::Tensor& dx, at::Tensor& dgate) {
+  check_bf16_contig(dout, "dout"); check_bf16_contig(x, "x"); check_bf16_contig(gate, "gate"); check_bf16_contig(dx, "dx");
+  TORCH_CHECK(dgate.scalar_type() == at::kFloat && dgate.is_contiguous(), "dgate must be contiguous fp32");
+  c10::cuda::CUDAGuard guard(x.device());
+  B200_CUDA_OK(b200_channel_scale_bwd(dout.data_ptr(), x.data_ptr(), gate.data_ptr(), dx.data_ptr(), dgate.data_ptr<float>(),
+                                      x.size(0), x.size(1) * x.size(2), x.size(3), cur_stream()));
+}
+
 // accum: fp32 [3] = (sum of per-sample losses, top-1 hits, top-k hits), accumulated.
 void ce_topk(const at::Tensor& logits, const at::Tensor& target, c10::optional<at::Tensor> dlogits, at::Tensor& accum,
              int64_t topk, double grad_scale) {
@@ -610,6 +625,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gap_bwd", &gap_bwd);
   m.def("avgpool2_fwd", &avgpool2_fwd);
   m.def("avgpool2_bwd", &avgpool2_bwd);
+  m.def("channel_scale_fwd", &channel_scale_fwd);
+  m.def("channel_scale_bwd", &channel_scale_bwd);
   m.def("ce_topk", &ce_topk);
   m.def("nchw_to_nhwc", &nchw_to_nhwc);
   m.def("stem_im2col", &stem_im2col);

@@ -546,6 +546,52 @@ __global__ void avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv
 }
 
 // ------------------------------------------------------------------------------------------------
+// Squeeze-excite gating (RegNetY / EfficientNet): out[n,hw,c] = x[n,hw,c] * gate[n,c].
+// Backward in ONE pass over (dout, x): dx = dout * gate and dgate[n,c] = sum_hw dout * x (fp32 atomics).
+// grid: (channel-vector blocks, hw chunks, N)
+// ------------------------------------------------------------------------------------------------
+__global__ void channel_scale_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gate,
+                                         __nv_bfloat16* __restrict__ out, int HW, int C) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  if (c0 >= C) return;
+  const int n = blockIdx.z;
+  float g[8];
+  load8(gate + (long long)n * C + c0, g);
+  for (int t = blockIdx.y * blockDim.y + threadIdx.y; t < HW; t += gridDim.y * blockDim.y) {
+    const long long o = ((long long)n * HW + t) * C + c0;
+    float v[8];
+    load8(x + o, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] *= g[i];
+    store8(out + o, v);
+  }
+}
+__global__ void channel_scale_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+                                         const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ dx,
+                                         float* __restrict__ dgate, int HW, int C) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  if (c0 >= C) return;
+  const int n = blockIdx.z;
+  float g[8], acc[8];
+  load8(gate + (long long)n * C + c0, g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int t = blockIdx.y * blockDim.y + threadIdx.y; t < HW; t += gridDim.y * blockDim.y) {
+    const long long o = ((long long)n * HW + t) * C + c0;
+    float d[8], v[8];
+    load8(dout + o, d);
+    load8(x + o, v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { acc[i] = fmaf(d[i], v[i], acc[i]); d[i] *= g[i]; }
+    store8(dx + o, d);
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) atomicAdd(dgate + (long long)n * C + c0 + i, acc[i]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Fused softmax cross-entropy + top-1/top-k hit counting + dlogits, one CTA per sample.
 // loss_sum / hits are accumulated atomically; dlogits = (softmax - onehot) * grad_scale.
 // ------------------------------------------------------------------------------------------------
@@ -772,6 +818,30 @@ extern "C" int b200_avgpool2_bwd(const void* dout, void* dx, int N, int H, int W
       (const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, H, W, C);
   return (int)cudaGetLastError();
 }
+static inline void scale_dims(int HW, int C, int N, dim3& grid, dim3& block) {
+  const int cvs = C / VEC;
+  int bx = 1;
+  while (bx < 32 && bx < cvs) bx <<= 1;
+  const int by = 256 / bx;
+  int gy = (HW + by - 1) / by;
+  if (gy > 32) gy = 32;
+  grid = dim3((cvs + bx - 1) / bx, gy, N);
+  block = dim3(bx, by);
+}
+extern "C" int b200_channel_scale_fwd(const void* x, const void* gate, void* out, int N, int HW, int C, cudaStream_t s) {
+  dim3 g, b;
+  scale_dims(HW, C, N, g, b);
+  channel_scale_fwd_kernel<<<g, b, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gate, (__nv_bfloat16*)out, HW, C);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_channel_scale_bwd(const void* dout, const void* x, const void* gate, void* dx, float* dgate, int N, int HW,
+                                      int C, cudaStream_t s) {
+  dim3 g, b;
+  scale_dims(HW, C, N, g, b);
+  channel_scale_bwd_kernel<<<g, b, 0, s>>>((const __nv_bfloat16*)dout, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gate,
+                                           (__nv_bfloat16*)dx, dgate, HW, C);
+  return (int)cudaGetLastError();
+}
 extern "C" int b200_ce_topk(const void* logits, const long long* target, void* dlogits, float* accum, int rows, int ncls,
                             long long ld, int topk, float grad_scale, cudaStream_t s) {
   ce_topk_kernel<<<rows, 256, 0, s>>>((const __nv_bfloat16*)logits, target, (__nv_bfloat16*)dlogits, accum, ncls, ld, topk, grad_scale);
@@ -783,6 +853,7 @@ extern "C" int b200_nchw_to_nhwc(const float* x, void* out, int N, int C, int H,
 }
 extern "C" int b200_stem_im2col(const float* x, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S,
                                 int stride, int pad, int Kpad, cudaStream_t s) {
+  if (Kpad > 256) return (int)cudaErrorInvalidValue;
   stem_im2col_kernel<<<N * P, 256, (size_t)C * R * (W + 2 * pad) * sizeof(float), s>>>(x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad);
   return (int)cudaGetLastError();
 }

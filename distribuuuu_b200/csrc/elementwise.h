@@ -64,6 +64,8 @@ int b200_gap_fwd(const void* x, void* out, int N, int HW, int C, cudaStream_t s)
 int b200_gap_bwd(const void* dout, void* dx, int N, int HW, int C, cudaStream_t s);
 int b200_avgpool2_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s);
 int b200_avgpool2_bwd(const void* dout, void* dx, int N, int H, int W, int C, cudaStream_t s);
+int b200_channel_scale_fwd(const void* x, const void* gate, void* out, int N, int HW, int C, cudaStream_t s);
+int b200_channel_scale_bwd(const void* dout, const void* x, const void* gate, void* dx, float* dgate, int N, int HW, int C, cudaStream_t s);
 int b200_ce_topk(const void* logits, const long long* target, void* dlogits, float* accum, int rows, int ncls, long long ld, int topk, float grad_scale, cudaStream_t s);
 int b200_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, cudaStream_t s);
 int b200_stem_im2col(const float* x, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad, cudaStream_t s);

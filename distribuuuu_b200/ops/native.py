@@ -333,6 +333,28 @@ class GapFn(torch.autograd.Function):
         return _nchw_view(dx), None
 
 
+class ChannelScaleFn(torch.autograd.Function):
+    """x * gate[n, c] (squeeze-excite gating) with a one-pass backward (dx and the per-sample gate gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, gate, eng):
+        xh = _nhwc(x)
+        g = gate.contiguous()
+        out = torch.empty_like(xh)
+        eng.K.channel_scale_fwd(xh, g, out)
+        ctx.eng = eng
+        ctx.save_for_backward(xh, g)
+        return _nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        xh, g = ctx.saved_tensors
+        dx = torch.empty_like(xh)
+        dg = torch.zeros(g.shape, dtype=torch.float32, device=g.device)
+        ctx.eng.K.channel_scale_bwd(_nhwc(dout), xh, g, dx, dg)
+        return _nchw_view(dx), dg.to(g.dtype), None
+
+
 class CeTopkFn(torch.autograd.Function):
     """softmax-CE + top-1/top-k counts + dlogits in one kernel (reference trainer.py:43,50 + utils.py:265-277)."""
 
@@ -351,6 +373,14 @@ class CeTopkFn(torch.autograd.Function):
     def backward(ctx, dloss, _daccum):
         (dl,) = ctx.saved_tensors
         return dl * dloss.to(dl.dtype), None, None, None
+
+
+class _FcView:
+    """Presents a 1x1 ``nn.Conv2d`` (weight [out, in, 1, 1], optional bias) to ``LinearFn`` as a linear layer."""
+
+    def __init__(self, conv):
+        self.weight, self.bias = conv.weight, conv.bias
+        self.in_features, self.out_features = conv.in_channels, conv.out_channels
 
 
 class NativeOps:
@@ -468,10 +498,22 @@ class NativeOps:
             return GapFn.apply(x, self.eng)
         return x.mean(dim=(2, 3))
 
+    def _se_fc(self, v, conv):
+        """A squeeze-excite 1x1 conv on a pooled [N, C] vector: tcgen05 GEMM when the widths allow, else ATen."""
+        cin, cout = conv.in_channels, conv.out_channels
+        if cin % 8 == 0 and cout % 8 == 0 and conv.groups == 1:
+            return LinearFn.apply(v, self.eng, _FcView(conv), self.eng.anchor)
+        return self._torch_conv(v[:, :, None, None], conv).flatten(1)
+
     def squeeze_excite(self, x, fc1, fc2, act):
-        s = self.global_avg_pool(x)[:, :, None, None]
-        s = _torch_act(self._torch_conv(s, fc1), act)
-        return x * torch.sigmoid(self._torch_conv(s, fc2))
+        if x.dtype != torch.bfloat16 or x.shape[1] % 8 != 0:
+            s = x.mean(dim=(2, 3), keepdim=True)
+            s = _torch_act(self._torch_conv(s, fc1), act)
+            return x * torch.sigmoid(self._torch_conv(s, fc2))
+        s = self.global_avg_pool(x)                                   # [N, C]  (native pooling kernel)
+        h = _torch_act(self._se_fc(s, fc1), act)                      # [N, r]
+        gate = torch.sigmoid(self._se_fc(h, fc2))                     # [N, C]
+        return ChannelScaleFn.apply(x, gate, self.eng)
 
     def concat_channels(self, tensors):
         tensors = [self._as_act(t) for t in tensors]

@@ -40,6 +40,12 @@ def test_depthwise_conv_kernels(k, stride, C):
     selftest.check_depthwise(k=k, stride=stride, C=C)
 
 
+def test_squeeze_excite_scale_kernels():
+    from distribuuuu_b200 import selftest
+    selftest.check_channel_scale()
+    selftest.check_channel_scale(N=2, H=14, W=14, C=1232)
+
+
 def test_pool_kernels():
     from distribuuuu_b200 import selftest
     selftest.check_pools()

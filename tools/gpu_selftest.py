@@ -28,6 +28,7 @@ def registry():
         "ce_topk": st.check_ce_topk,
         "sgd": st.check_sgd,
         "stem": st.check_stem,
+        "channel_scale": st.check_channel_scale,
         "grouped_regnety": lambda: st.check_grouped_conv(C=224, K=224, G=2),
         "grouped_regnetx_s2": lambda: st.check_grouped_conv(C=512, K=512, G=4, stride=2, H=28, W=28),
         "grouped_232": lambda: st.check_grouped_conv(C=696, K=696, G=3, H=14, W=14),
