@@ -386,7 +386,7 @@ class NativeEngine(nn.Module):
         self.comm_stream.wait_event(ev)
         with torch.cuda.stream(self.comm_stream):
             if self.comm_mode == "peer":
-                grid = 8 if b.one_shot else 48
+                grid = 8 if b.one_shot else 120   # <= #SMs: every CTA must become resident for the grid barrier
                 self.K.allreduce_sgd(self.comm_state, self.flat_master, self.flat_mom, self.flat_grad, b.off, b.n,
                                      lr, mom, damp, wd, nest, first, b.one_shot, grid)
             else:  # NCCL baseline: library all-reduce, then the local fused update

@@ -49,7 +49,7 @@ def main():
     hyper = (0.1, 0.9, 0.0, 5e-5, True, False)
     for bi, b in enumerate(eng.buckets):
         nbytes16 = b.n * 2
-        grid = 8 if b.one_shot else 48
+        grid = 8 if b.one_shot else 120
         t_fused = timed(lambda: K.allreduce_sgd(eng.comm_state, eng.flat_master, eng.flat_mom, eng.flat_grad, b.off, b.n,
                                                 *hyper, b.one_shot, grid), 20, dev)
         g = eng.flat_grad[b.off:b.off + b.n]
