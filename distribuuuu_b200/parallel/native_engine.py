@@ -123,6 +123,7 @@ class NativeEngine(nn.Module):
         self._leaves: Dict[nn.Parameter, torch.Tensor] = {}
         self._bn_stepped: List[torch.Tensor] = []
         self.last_sink: Dict[nn.Module, object] = {}   # conv module -> gradient mailbox of its latest forward
+        self._slots_used = set()
         self._step_parity = 0
         self.comm_stream = torch.cuda.Stream(device)
         # autograd anchor: lets Functions whose tensor inputs carry no grad (first layer) still get a backward call
@@ -213,15 +214,23 @@ class NativeEngine(nn.Module):
                 off += 2 * m.num_features          # backward: sum(dz), sum(dz*xhat)
         self.stats_len = (off + 63) // 64 * 64
 
-    def fwd_slot(self, bn) -> _Slot:
-        base = self._step_parity * self.stats_len + self.bn_offsets[bn]
+    def _slot(self, bn, which: int) -> _Slot:
         n = 2 * bn.num_features
-        return _Slot(self.stats_buf[base:base + n], self.stats_sym_base + base)
+        base = self._step_parity * self.stats_len + self.bn_offsets[bn] + which * n
+        view = self.stats_buf[base:base + n]
+        # all slots are zeroed in one memset at the start of a step; a second use within the same step
+        # (activation-checkpoint recomputation, a BN module applied twice) must start from zero again
+        key = (bn, which)
+        if key in self._slots_used:
+            view.zero_()
+        self._slots_used.add(key)
+        return _Slot(view, self.stats_sym_base + base)
+
+    def fwd_slot(self, bn) -> _Slot:
+        return self._slot(bn, 0)
 
     def bwd_slot(self, bn) -> _Slot:
-        base = self._step_parity * self.stats_len + self.bn_offsets[bn] + 2 * bn.num_features
-        n = 2 * bn.num_features
-        return _Slot(self.stats_buf[base:base + n], self.stats_sym_base + base)
+        return self._slot(bn, 1)
 
     def note_bn_step(self, bn):
         if bn.num_batches_tracked is not None:
@@ -409,6 +418,7 @@ class NativeEngine(nn.Module):
         self.stats_buf[base:base + self.stats_len].zero_()
         self._bn_stepped.clear()
         self.last_sink.clear()
+        self._slots_used.clear()
 
     def train_step(self, inputs, targets, optimizer, topk: int):
         assert optimizer is self.optimizer, "the native engine steps its own FusedSGD (utils.construct_optimizer)"

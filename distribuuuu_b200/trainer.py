@@ -105,12 +105,15 @@ def train_epoch(train_loader, engine, optimizer, cur_epoch, start_epoch, tic, de
 
     metrics = utils.DeviceMetrics(device)
     sync_freq = max(int(cfg.B200.METRIC_SYNC_FREQ), 1)
+    timer = utils.StepTimer(device, enabled=bool(cfg.B200.PROFILE))   # CUDA-event phase timing (B200.PROFILE)
     end = time.time()
     for idx, (inputs, targets) in enumerate(train_loader):
         if idx >= n_iters:
             break
         data_time.update(time.time() - end)
+        timer.start("step")
         loss, hits1, hitsk = engine.train_step(inputs, targets, optimizer, cfg.TRAIN.TOPK)
+        timer.stop("step")
         metrics.update(loss, hits1, hitsk, targets.size(0))
 
         last = (idx + 1) == n_iters
@@ -125,6 +128,11 @@ def train_epoch(train_loader, engine, optimizer, cur_epoch, start_epoch, tic, de
         if rank == 0 and ((idx + 1) % cfg.TRAIN.PRINT_FREQ == 0 or last):
             progress.cal_eta(idx + 1, n_iters, tic, cur_epoch, start_epoch)
             progress.display(idx + 1)
+    if cfg.B200.PROFILE and rank == 0:
+        for name, st in timer.summary().items():
+            per_gpu = st["n"] * targets.size(0) / max(st["total_ms"], 1e-9) * 1e3
+            logger.info(f"PROFILE [{cur_epoch + 1}] {name}: {st['mean_ms']:.3f} ms/iter device time over {st['n']} iters "
+                        f"({per_gpu:.1f} img/s per rank)")
     return losses.avg, top1.avg, topk.avg
 
 
