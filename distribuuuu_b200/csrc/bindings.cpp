@@ -396,7 +396,7 @@ void bn_apply(const at::Tensor& y, const c10::optional<at::Tensor>& residual, at
               int64_t sym_offset, const c10::optional<at::Tensor>& gamma, const c10::optional<at::Tensor>& beta,
               c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var, at::Tensor& save_mean,
               at::Tensor& save_invstd, double count, double eps, double momentum, int64_t act, bool training,
-              PeerState* peer) {
+              PeerState* peer, c10::optional<at::Tensor> relu_mask) {
   c10::cuda::CUDAGuard guard(y.device());
   TORCH_CHECK(y.dim() == 2 && y.stride(1) == 1 && out.stride(1) == 1 && y.size(1) % 8 == 0, "bn_apply expects [rows, C] with C % 8 == 0");
   BnApplyParams p{};
@@ -409,6 +409,11 @@ void bn_apply(const at::Tensor& y, const c10::optional<at::Tensor>& residual, at
   p.running_mean = fptr_mut(running_mean); p.running_var = fptr_mut(running_var);
   p.save_mean = save_mean.data_ptr<float>(); p.save_invstd = save_invstd.data_ptr<float>();
   p.count = (float)count; p.eps = (float)eps; p.momentum = (float)momentum; p.act = act; p.training = training;
+  p.relu_mask = nullptr;
+  if (relu_mask.has_value()) {
+    TORCH_CHECK(relu_mask->scalar_type() == at::kByte && relu_mask->is_contiguous() && relu_mask->numel() == y.size(0) * (y.size(1) / 8) && act == ACT_RELU, "relu_mask: uint8 [rows, C/8], relu only");
+    p.relu_mask = relu_mask->data_ptr<uint8_t>();
+  }
   if (peer && training) p.peer = peer->make(); else { p.peer = PeerCtx{}; p.peer.world = 1; }
   B200_CUDA_OK(b200_bn_apply(&p, cur_stream()));
 }
@@ -423,7 +428,7 @@ void bn_backward(const at::Tensor& y, const at::Tensor& dout, const c10::optiona
                  c10::optional<at::Tensor> dresidual, at::Tensor& sums, int64_t sym_offset,
                  const c10::optional<at::Tensor>& gamma, const c10::optional<at::Tensor>& beta, const at::Tensor& save_mean,
                  const at::Tensor& save_invstd, c10::optional<at::Tensor> dgamma, c10::optional<at::Tensor> dbeta,
-                 double count, int64_t act, PeerState* peer) {
+                 double count, int64_t act, PeerState* peer, const c10::optional<at::Tensor>& relu_mask) {
   c10::cuda::CUDAGuard guard(y.device());
   TORCH_CHECK(y.dim() == 2 && y.stride(1) == 1 && dout.stride(1) == 1 && dy.stride(1) == 1, "bn_backward expects [rows, C] views");
   TORCH_CHECK(dy.stride(0) == y.stride(0), "dy must share y's row pitch");
@@ -440,6 +445,7 @@ void bn_backward(const at::Tensor& y, const at::Tensor& dout, const c10::optiona
   p.save_mean = save_mean.data_ptr<float>(); p.save_invstd = save_invstd.data_ptr<float>();
   p.dgamma = fptr_mut(dgamma); p.dbeta = fptr_mut(dbeta);
   p.count = (float)count; p.act = act;
+  p.relu_mask = relu_mask.has_value() ? relu_mask->data_ptr<uint8_t>() : nullptr;
   p.peer = PeerCtx{}; p.peer.world = 1;
   B200_CUDA_OK(b200_bn_bwd_reduce(&p, cur_stream()));
   if (peer) p.peer = peer->make();
@@ -616,9 +622,13 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dw_fprop", &dw_fprop, "depthwise conv forward (+BN statistics)");
   m.def("dw_dgrad", &dw_dgrad);
   m.def("dw_wgrad", &dw_wgrad);
-  m.def("bn_apply", &bn_apply);
+  m.def("bn_apply", &bn_apply, py::arg("y"), py::arg("residual"), py::arg("out"), py::arg("stats"), py::arg("sym_offset"), py::arg("gamma"),
+        py::arg("beta"), py::arg("running_mean"), py::arg("running_var"), py::arg("save_mean"), py::arg("save_invstd"), py::arg("count"),
+        py::arg("eps"), py::arg("momentum"), py::arg("act"), py::arg("training"), py::arg("peer"), py::arg("relu_mask") = py::none());
   m.def("bn_stats", &bn_stats);
-  m.def("bn_backward", &bn_backward);
+  m.def("bn_backward", &bn_backward, py::arg("y"), py::arg("dout"), py::arg("residual"), py::arg("dy"), py::arg("dresidual"), py::arg("sums"),
+        py::arg("sym_offset"), py::arg("gamma"), py::arg("beta"), py::arg("save_mean"), py::arg("save_invstd"), py::arg("dgamma"), py::arg("dbeta"),
+        py::arg("count"), py::arg("act"), py::arg("peer"), py::arg("relu_mask") = py::none());
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
   m.def("gap_fwd", &gap_fwd);

@@ -196,6 +196,12 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyParams p) {
       for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]), p.act);
     }
     store8(p.out + r * p.ldo + c0, x);
+    if (p.relu_mask) {
+      uint32_t bits = 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) bits |= (x[i] > 0.f ? 1u : 0u) << i;
+      p.relu_mask[r * (p.C / VEC) + cv] = (uint8_t)bits;
+    }
     st = (st + 1) % kRing;
   }
   cp_async_wait<0>();
@@ -271,7 +277,10 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdParams p) {
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const long long rstride = (long long)gridDim.y * blockDim.y;
     const long long row0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-    const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr);
+    const bool use_mask = (p.relu_mask != nullptr);
+    const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr) && !use_mask;
+    const uint8_t* mrow = p.relu_mask + cv;
+    const int mpitch = p.C / VEC;
     auto issue = [&](int stage, long long r) {
       if (r < p.rows) {
         cp_async16(&ring[(stage * 3 + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
@@ -292,9 +301,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdParams p) {
       unpack8f(ring[(st * 3 + 0) * kBnThreads + tid], y);
       unpack8f(ring[(st * 3 + 1) * kBnThreads + tid], d);
       if (need_res) unpack8f(ring[(st * 3 + 2) * kBnThreads + tid], q);
+      const uint32_t mbits = use_mask ? (uint32_t)__ldg(mrow + r * mpitch) : 0u;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
+        if (use_mask) d[i] = ((mbits >> i) & 1u) ? d[i] : 0.f;
+        else if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
         a[i] += d[i];
         b[i] = fmaf(d[i], fmaf(y[i], invstd[i], nmi[i]), b[i]);
       }
@@ -357,7 +368,10 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdParams p) {
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const long long rstride = (long long)gridDim.y * blockDim.y;
   const long long k0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-  const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr);
+  const bool use_mask = (p.relu_mask != nullptr);
+  const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr) && !use_mask;
+  const uint8_t* mrow = p.relu_mask + cv;
+  const int mpitch = p.C / VEC;
   // rows are visited from the END of the tensor: the reduce pass finished there, so those lines are the likeliest L2 hits
   auto issue = [&](int stage, long long kk) {
     if (kk < p.rows) {
@@ -381,9 +395,11 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdParams p) {
     unpack8f(ring[(st * 3 + 0) * kBnThreads + tid], y);
     unpack8f(ring[(st * 3 + 1) * kBnThreads + tid], d);
     if (need_res) unpack8f(ring[(st * 3 + 2) * kBnThreads + tid], q);
+    const uint32_t mbits = use_mask ? (uint32_t)__ldg(mrow + r * mpitch) : 0u;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
+      if (use_mask) d[i] = ((mbits >> i) & 1u) ? d[i] : 0.f;
+      else if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
       o[i] = fmaf(d[i], scale[i], fmaf(y[i], ca[i], cb[i]));
     }
     if (p.dresidual) store8(p.dresidual + r * p.ldr + c0, d);
@@ -729,14 +745,14 @@ __global__ void unpad_add_kernel(const float* __restrict__ src, float* __restric
 // ================================================================================================
 using namespace b200;
 
-static inline void bn_launch_dims(int C, long long rows, dim3& grid, dim3& block) {
+static inline void bn_launch_dims(int C, long long rows, dim3& grid, dim3& block, int ctas_per_sm = 4) {
   const int cvs = C / VEC;
   int bx = 1;
   while (bx < 32 && bx < cvs) bx <<= 1;     // power of two <= 32 covering the channel vectors
   const int by = 256 / bx;
   const int gx = (cvs + bx - 1) / bx;
   long long want = (rows + by - 1) / by;
-  long long cap = (148 * 4 + gx - 1) / gx;   // ~4 CTAs per SM in total (2-3 resident: ring smem + registers)
+  long long cap = (148 * ctas_per_sm + gx - 1) / gx;   // CTAs per SM in total (2 resident: ring smem + registers)
   int gy = (int)(want < cap ? want : cap);
   if (gy < 1) gy = 1;
   grid = dim3(gx, gy);
@@ -769,7 +785,7 @@ extern "C" int b200_bn_bwd_reduce(const BnBwdParams* p, cudaStream_t s) {
   static cudaError_t once = allow_big_smem(bn_bwd_reduce_kernel, kRingBytes3);
   if (once != cudaSuccess) return (int)once;
   dim3 g, b;
-  bn_launch_dims(p->C, p->rows, g, b);
+  bn_launch_dims(p->C, p->rows, g, b, 2);   // exactly the resident wave: fewer CTAs = fewer contended atomics at the end
   bn_bwd_reduce_kernel<<<g, b, kRingBytes3, s>>>(*p);
   return (int)cudaGetLastError();
 }

@@ -33,6 +33,8 @@ struct BnApplyParams {
   float count;               // elements per channel over ALL ranks
   float eps, momentum;
   int act, training;
+  uint8_t* relu_mask;        // optional [rows][C/8]: bit i of byte (row, cv) = (output channel cv*8+i > 0); saves the
+                             // backward passes from re-reading the residual just to rebuild the ReLU mask
   PeerCtx peer;
 };
 
@@ -50,6 +52,7 @@ struct BnBwdParams {
   float* dgamma; float* dbeta; // fp32 gradient slots (accumulated)
   float count;
   int act;
+  const uint8_t* relu_mask;  // optional, see BnApplyParams
   PeerCtx peer;
 };
 

@@ -203,10 +203,15 @@ class BnActFn(torch.autograd.Function):
         peer = eng.peer_state if (training and eng.sync_bn) else None
         count = float(y2.shape[0] * (eng.world if peer is not None else 1))
         stats = stats_slot.tensor if stats_slot is not None else save  # eval: unused
+        # residual + ReLU layers: keep a 1-bit/element mask so backward need not re-read the residual (2 B/element,
+        # twice) just to rebuild relu'(z)
+        mask = None
+        if training and residual is not None and act == "relu" and (y.requires_grad or residual.requires_grad):
+            mask = torch.empty((y2.shape[0], C // 8), dtype=torch.uint8, device=y.device)
         K.bn_apply(y2, res2, out.view(-1, C), stats, stats_slot.sym_offset if stats_slot is not None else 0,
                    eng.master_view(bn.weight) if bn.affine else None, eng.master_view(bn.bias) if bn.affine else None,
                    bn.running_mean, bn.running_var, save[0], save[1], count, bn.eps,
-                   bn.momentum if bn.momentum is not None else 0.1, ACT[act], training, peer)
+                   bn.momentum if bn.momentum is not None else 0.1, ACT[act], training, peer, mask)
         if training and bn.track_running_stats:
             eng.note_bn_step(bn)
         ctx.eng, ctx.bn, ctx.act, ctx.count = eng, bn, act, count
@@ -215,8 +220,8 @@ class BnActFn(torch.autograd.Function):
         # only fuse when the sink's conv really consumes this very tensor
         ctx.sink = sink if (sink is not None and residual is not None and ctx.res_needs_grad
                             and _nhwc(residual).data_ptr() == sink.ptr) else None
-        need_res = residual is not None and act is not None
-        ctx.save_for_backward(y2, res2 if need_res else None, save)
+        need_res = residual is not None and act is not None and mask is None
+        ctx.save_for_backward(y2, res2 if need_res else None, save, mask)
         ctx.shape = (N, H, W, C)
         return _nchw_view(out)
 
@@ -224,7 +229,7 @@ class BnActFn(torch.autograd.Function):
     def backward(ctx, dout):
         eng, bn = ctx.eng, ctx.bn
         K = eng.K
-        y2, res2, save = ctx.saved_tensors
+        y2, res2, save, mask = ctx.saved_tensors
         N, H, W, C = ctx.shape
         d2 = _nhwc(dout).view(-1, C)
         dy = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dout.device)
@@ -235,7 +240,7 @@ class BnActFn(torch.autograd.Function):
                       slot.sym_offset, eng.master_view(bn.weight) if bn.affine else None,
                       eng.master_view(bn.bias) if bn.affine else None, save[0], save[1],
                       eng.grad_flat_view(bn.weight) if bn.affine else None,
-                      eng.grad_flat_view(bn.bias) if bn.affine else None, ctx.count, ACT[ctx.act], peer)
+                      eng.grad_flat_view(bn.bias) if bn.affine else None, ctx.count, ACT[ctx.act], peer, mask)
         if bn.affine:
             eng.mark_ready(bn.weight)
             eng.mark_ready(bn.bias)

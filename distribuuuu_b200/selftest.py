@@ -147,7 +147,7 @@ def check_conv_case(name: str):
 
 
 # ---------------------------------------------------------------------------------------------- BN / pools / CE / SGD
-def check_bn(N=8, H=14, W=14, C=64, act="relu", residual=True):
+def check_bn(N=8, H=14, W=14, C=64, act="relu", residual=True, use_mask=False):
     Kmod = _K()
     from .ops.native import ACT
     y = _bf16(N * H * W, C, seed=7)
@@ -160,7 +160,8 @@ def check_bn(N=8, H=14, W=14, C=64, act="relu", residual=True):
     out = torch.empty_like(y)
     save = torch.empty(2, C, device="cuda")
     rows = y.shape[0]
-    Kmod.bn_apply(y, res, out, stats, 0, gamma, beta, rm, rv, save[0], save[1], float(rows), 1e-5, 0.1, ACT[act], True, None)
+    mask = torch.empty((rows, C // 8), dtype=torch.uint8, device="cuda") if use_mask else None
+    Kmod.bn_apply(y, res, out, stats, 0, gamma, beta, rm, rv, save[0], save[1], float(rows), 1e-5, 0.1, ACT[act], True, None, mask)
     # reference
     yr = y.float().clone().requires_grad_(True)
     rr = res.float().clone().requires_grad_(True) if residual else None
@@ -180,7 +181,8 @@ def check_bn(N=8, H=14, W=14, C=64, act="relu", residual=True):
     dres = torch.empty_like(y) if residual else None
     sums = torch.zeros(2 * C, device="cuda")
     dgamma, dbeta = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    Kmod.bn_backward(y, dout, res, dy, dres, sums, 0, gamma, beta, save[0], save[1], dgamma, dbeta, float(rows), ACT[act], None)
+    Kmod.bn_backward(y, dout, None if use_mask else res, dy, dres, sums, 0, gamma, beta, save[0], save[1], dgamma, dbeta, float(rows),
+                     ACT[act], None, mask)
     torch.cuda.synchronize()
     errs = {"out": e_out, "dy": _rel_err(dy, yr.grad), "dgamma": _rel_err(dgamma, g_ref.grad), "dbeta": _rel_err(dbeta, b_ref.grad)}
     if residual:

@@ -28,6 +28,11 @@ def test_batchnorm_kernels(act, residual, C):
     selftest.check_bn(act=act, residual=residual, C=C)
 
 
+def test_batchnorm_relu_bitmask_backward():
+    from distribuuuu_b200 import selftest
+    selftest.check_bn(act="relu", residual=True, C=256, use_mask=True)
+
+
 @pytest.mark.parametrize("C,G,stride", [(224, 2, 1), (512, 4, 2), (696, 3, 1)])
 def test_grouped_conv_tcgen05(C, G, stride):
     from distribuuuu_b200 import selftest

@@ -22,6 +22,7 @@ def registry():
     checks = {name: (lambda n=name: st.check_conv_case(n)) for name in st.CONV_CASES}
     checks.update({
         "bn_relu_res": lambda: st.check_bn(act="relu", residual=True),
+        "bn_relu_res_mask": lambda: st.check_bn(act="relu", residual=True, C=256, use_mask=True),
         "bn_none": lambda: st.check_bn(act=None, residual=False, C=256),
         "bn_silu_c24": lambda: st.check_bn(act="silu", residual=False, C=24),
         "pools": st.check_pools,
