@@ -154,6 +154,30 @@ constexpr uint32_t kMnMajorLbo = 8192, kMnMajorSbo = 1024, kMnMajorStep16 = 128;
 
 int pick_bn(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
 
+// Tile plan for fprop / dgrad.  Streaming mode re-loads the BN x 64 weight tile for every (M tile, k block); when the
+// CTA's whole weight slab (k_iters x BN x 128 B) fits in shared memory next to >= 2 A stages, keeping it resident
+// removes that L2->SM traffic (the dominant term for the K <= 256 pointwise layers).  Pick whichever moves fewer
+// bytes per 128-row tile: resident = A * ceil(N/bn);  streaming = (A + B) * ceil(N/bn).
+struct TilePlan { int bn; int resident; int res_stages; };
+TilePlan plan_tiles(int n_cols, int k_iters, long long m_tiles, int groups, int sms) {
+  constexpr int kRing = 160 * 1024, kA = 16384;
+  const int bn0 = pick_bn(n_cols);
+  TilePlan best{bn0, 0, 0};
+  if (groups != 1) return best;
+  auto nblk = [&](int bn) { return (n_cols + bn - 1) / bn; };
+  double best_traffic = (double)(kA + bn0 * 128) * k_iters * nblk(bn0);
+  for (int bn : {256, 128, 64}) {
+    if (bn > bn0) continue;
+    const long long slab = (long long)k_iters * bn * 128;
+    const int stages = (int)((kRing - slab) / kA);
+    if (slab > kRing || stages < 2) continue;
+    if (nblk(bn) > sms || m_tiles * nblk(bn) < 2LL * sms) continue;   // needs several tiles per CTA to amortise
+    const double traffic = (double)kA * k_iters * nblk(bn);
+    if (traffic < 0.85 * best_traffic) { best_traffic = traffic; best = TilePlan{bn, 1, std::min(stages, 12)}; }
+  }
+  return best;
+}
+
 void check_bf16_contig(const at::Tensor& t, const char* name) {
   TORCH_CHECK(t.is_cuda() && t.scalar_type() == at::kBFloat16 && t.is_contiguous(), name, " must be a contiguous CUDA bf16 tensor");
 }
@@ -195,9 +219,11 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   const int G = groups, cin_g = g.C / G, cout_g = g.K / G;
   TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8 (", cin_g, ", ", cout_g, ")");
   const int M = g.N * g.P * g.Q;
-  const int bn = pick_bn(cout_g);
+  const TilePlan plan = plan_tiles(cout_g, g.R * g.S * ((cin_g + 63) / 64), (M + 127) / 128, G, num_sms());
+  const int bn = plan.bn;
   const bool pointwise = (g.R == 1 && g.S == 1 && stride == 1 && pad == 0);
   ConvGemmParams p{};
+  p.b_resident = plan.resident; p.res_stages = plan.res_stages;
   p.kind = KIND_FPROP; p.epi = EPI_BF16;
   p.M = M; p.N = cout_g;
   p.groups = G; p.a_cg = cin_g; p.out_cg = cout_g;
@@ -222,7 +248,8 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   CUtensorMap mb = tiled_map_4d(w.data_ptr(), cin_g, p.taps, cout_g, G, cin_g, (uint64_t)p.taps * cin_g,
                                 (uint64_t)p.taps * cin_g * cout_g, 64, 1, bn, 1);
   CUtensorMap mo = tiled_map_3d(out.data_ptr(), cout_g, M, G, g.K, cout_g, 64, 32, 1);
-  const int grid = std::min(p.total_items, num_sms());
+  int grid = std::min(p.total_items, num_sms());
+  if (p.b_resident) grid = (grid / p.n_blocks) * p.n_blocks;   // every CTA keeps ONE n-block for its whole life
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &mo, &p, bn, grid, cur_stream()));
 }
 
@@ -241,10 +268,12 @@ void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64
   TORCH_CHECK(P == H + 2 * pad - dil * (R - 1) && Q == W + 2 * pad - dil * (S - 1), "dgrad: dy spatial size inconsistent");
   TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8");
   const int M = N * H * W;
-  const int bn = pick_bn(cin_g);
+  const TilePlan plan = plan_tiles(cin_g, R * S * ((cout_g + 63) / 64), (M + 127) / 128, G, num_sms());
+  const int bn = plan.bn;
   const bool pointwise = (R == 1 && S == 1 && pad == 0);
   const int padp_h = dil * (R - 1) - pad, padp_w = dil * (S - 1) - pad;  // padding of the transposed problem
   ConvGemmParams p{};
+  p.b_resident = plan.resident; p.res_stages = plan.res_stages;
   p.kind = KIND_DGRAD; p.epi = EPI_BF16;
   p.M = M; p.N = cin_g;
   p.groups = G; p.a_cg = cout_g; p.out_cg = cin_g;
@@ -272,7 +301,8 @@ void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64
     p.addend = 1;
     md = tiled_map_3d(addend->data_ptr(), cin_g, M, G, C, cin_g, 64, 32, 1);
   }
-  const int grid = std::min(p.total_items, num_sms());
+  int grid = std::min(p.total_items, num_sms());
+  if (p.b_resident) grid = (grid / p.n_blocks) * p.n_blocks;
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &md, &p, bn, grid, cur_stream()));
 }
 

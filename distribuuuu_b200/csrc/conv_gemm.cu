@@ -30,7 +30,11 @@ struct Cfg {
   static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages; 128/256/512 are all legal allocations
   static constexpr int kStagingBytes = kEpiWarps * 2 /*double buffer*/ * 4096;  // 32 rows x 128 B each
-  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kMaxStages = 12;     // resident-weights mode re-partitions the ring into A-only stages
+  static constexpr int kRingBytes = 160 * 1024;  // same for every BN (>= kStages * kStageBytes) so that a resident
+                                                 // 128 KB weight slab + 2 A stages fits
+  static_assert(kStages * kStageBytes <= kRingBytes, "ring too small");
+  static constexpr int kSmemBytes = kRingBytes + kStagingBytes + 1024 /*align slack*/ + 512 /*barriers*/;
 };
 
 struct PixelCoord { int w, h, n; };
@@ -81,15 +85,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + C::kStages * kABytes;
-  uint8_t* smem_stage_out = smem + C::kStages * C::kStageBytes;  // epilogue staging (1024-aligned)
+  uint8_t* smem_b = smem + C::kStages * kABytes;  // (re-pointed below in resident mode)
+  uint8_t* smem_stage_out = smem + C::kRingBytes;  // epilogue staging (1024-aligned)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_stage_out + C::kStagingBytes);
-  uint64_t* full_bar = bars;                       // [kStages] TMA -> MMA
-  uint64_t* empty_bar = bars + C::kStages;         // [kStages] MMA -> TMA
-  uint64_t* tmem_full = bars + 2 * C::kStages;     // [2] MMA -> epilogue
+  uint64_t* full_bar = bars;                       // [kMaxStages] TMA -> MMA
+  uint64_t* empty_bar = bars + C::kMaxStages;      // [kMaxStages] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * C::kMaxStages;  // [2] MMA -> epilogue
   uint64_t* tmem_empty = tmem_full + 2;            // [2] epilogue -> MMA
   uint64_t* add_bar = tmem_empty + 2;              // [kEpiWarps] addend-tile loads (epilogue only)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(add_bar + kEpiWarps);
+  uint64_t* bres_bar = add_bar + kEpiWarps;        // [1] resident weight slab landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bres_bar + 1);
+  // Resident-weights mode (fprop/dgrad with a small weight slab): the CTA's n-block of the weights for ALL k
+  // iterations is loaded once to the front of the ring memory; the rest becomes a deeper ring of A-only stages.
+  const bool resident = p.b_resident != 0;
+  const int n_stages = resident ? p.res_stages : C::kStages;
+  const int k_iters_fd = p.taps * p.kb_per_tap;
+  if (resident) { smem_a = smem + k_iters_fd * C::kBBytes; smem_b = smem; }
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -98,7 +109,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
     if (EPI == EPI_BF16) tma_prefetch_desc(&map_out);
-    for (int i = 0; i < C::kStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+    for (int i = 0; i < C::kMaxStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+    mbar_init(smem_u32(bres_bar), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiThreads); }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(smem_u32(&add_bar[i]), 1);
     fence_barrier_init();
@@ -116,6 +128,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (resident && (int)blockIdx.x < p.total_items) {
+        // every item of this CTA has the same n-block (grid is a multiple of n_blocks, groups == 1)
+        const WorkItem w0 = decode_item(p, blockIdx.x, BN);
+        const uint32_t bb = smem_u32(bres_bar);
+        mbar_expect_tx(bb, (uint32_t)(k_iters_fd * C::kBBytes));
+        for (int it = 0; it < k_iters_fd; ++it) {
+          const int tap = it / p.kb_per_tap, kb = it - tap * p.kb_per_tap;
+          const int btap = p.b_flip_taps ? (p.taps - 1 - tap) : tap;
+          const uint32_t dst = smem_u32(smem_b + it * C::kBBytes);
+          if (p.kind == KIND_FPROP) {
+            tma_load_4d(dst, &map_b, bb, kb * BK, btap, w0.n0, 0);
+          } else {
+            for (int j = 0; j < p.b_nbox; ++j) tma_load_4d(dst + j * kBoxBytes, &map_b, bb, w0.n0 + 64 * j, btap, kb * BK, 0);
+          }
+        }
+      }
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const WorkItem w = decode_item(p, item, BN);
         PixelCoord pa{0, 0, 0};
@@ -125,7 +153,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint32_t bar = smem_u32(&full_bar[stage]);
           const uint32_t dst_a = smem_u32(smem_a + stage * kABytes);
           const uint32_t dst_b = smem_u32(smem_b + stage * C::kBBytes);
-          mbar_expect_tx(bar, p.kind == KIND_WGRAD ? (uint32_t)(kABytes + w.nbox * kBoxBytes) : (uint32_t)C::kStageBytes);
+          mbar_expect_tx(bar, p.kind == KIND_WGRAD ? (uint32_t)(kABytes + w.nbox * kBoxBytes)
+                                                   : (resident ? (uint32_t)kABytes : (uint32_t)C::kStageBytes));
           if (p.kind != KIND_WGRAD) {
             const int tap = it / p.kb_per_tap;
             const int kb = it - tap * p.kb_per_tap;
@@ -137,7 +166,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               tma_load_3d(dst_a, &map_a, bar, ca, 0, w.m0);
             const int btap = p.b_flip_taps ? (p.taps - 1 - tap) : tap;
             // weights are mapped as (Cin/g, taps, Cout/g, groups): anything past a group's extent is zero-filled
-            if (p.kind == KIND_FPROP) {
+            if (resident) {
+              // B slab already in shared memory
+            } else if (p.kind == KIND_FPROP) {
               tma_load_4d(dst_b, &map_b, bar, kb * BK, btap, w.n0, w.g);      // K-major weights [N][tap][K]
             } else {
               for (int j = 0; j < p.b_nbox; ++j)                              // MN-major weights [K][tap][N]
@@ -161,7 +192,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               }
             }
           }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
@@ -170,6 +201,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      if (resident && (int)blockIdx.x < p.total_items) { mbar_wait(smem_u32(bres_bar), 0); tc_fence_after(); }
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const WorkItem w = decode_item(p, item, BN);
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);   // epilogue has drained this accumulator
@@ -180,13 +212,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           mbar_wait(smem_u32(&full_bar[stage]), phase);          // TMA bytes have landed
           tc_fence_after();
           const uint64_t a_desc = p.a_desc_hi | (uint64_t)((smem_u32(smem_a + stage * kABytes) >> 4) & 0x3fff);
-          const uint64_t b_desc = p.b_desc_hi | (uint64_t)((smem_u32(smem_b + stage * C::kBBytes) >> 4) & 0x3fff);
+          const uint8_t* b_tile = resident ? (smem_b + (it - w.it_begin) * C::kBBytes) : (smem_b + stage * C::kBBytes);
+          const uint64_t b_desc = p.b_desc_hi | (uint64_t)((smem_u32(b_tile) >> 4) & 0x3fff);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(tmem_d, a_desc + (uint64_t)(k * p.a_kstep16), b_desc + (uint64_t)(k * p.b_kstep16), idesc,
                       (it > w.it_begin || k > 0) ? 1u : 0u);
           umma_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when the MMAs retire
-          if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(smem_u32(&tmem_full[acc]));                   // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }

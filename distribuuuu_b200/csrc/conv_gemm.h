@@ -27,6 +27,8 @@ struct ConvGemmParams {
   int k_blocks_total, splits;                     // wgrad: 64-pixel reduction blocks and split-K factor
   int vb_per_item, cin_boxes, vboxes_total;       // wgrad: B boxes (tap, 64-channel slice) handled by one work item
   int groups, a_cg, out_cg;                       // grouped conv: #groups, A-operand channels per group, output channels per group
+  int b_resident;       // fprop/dgrad: the CTA's whole B (weight) slab stays in smem; only A tiles stream through the ring
+  int res_stages;       // ring depth (A-only stages) in resident mode
   void* out;
   long long ldo;        // output row pitch in elements
   long long tap_stride; // wgrad: element offset between taps inside one output row

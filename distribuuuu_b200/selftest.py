@@ -379,7 +379,7 @@ def check_checkpoint_interop(tmpdir="/tmp/b200_ckpt_test"):
     return {"master": e_w, "momentum": e_m, "eval_loss": float(loss)}
 
 
-def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_classes=16, tol=0.08, lr=0.05):
+def check_engine_vs_torch(arch="resnet18", batch=16, size=64, steps=3, num_classes=16, tol=0.1, lr=0.01):
     """Same weights, same data: the native engine's loss trajectory must track the fp32 torch path."""
     import copy
     from . import models

@@ -83,7 +83,7 @@ def test_every_model_family_trains_on_native_engine(arch, batch, size):
     from distribuuuu_b200 import selftest
     # EfficientNet's SiLU/SE stack is chaotic at random init with a large step; a small LR keeps the 3-step
     # trajectories of the bf16 and fp32 paths comparable
-    selftest.check_engine_vs_torch(arch, batch=batch, size=size, tol=0.15, lr=0.005 if arch == "efficientnet_b0" else 0.05)
+    selftest.check_engine_vs_torch(arch, batch=batch, size=size, tol=0.15, lr=0.005 if arch == "efficientnet_b0" else 0.01)
 
 
 @pytest.mark.parametrize("arch,batch,size", [("resnet50", 16, 128), ("efficientnet_b0", 16, 128), ("regnety_160", 8, 128)])
