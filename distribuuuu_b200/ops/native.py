@@ -8,9 +8,10 @@ gradients are written by the kernels *directly* into the engine's flat fp32 grad
 (no ``.grad`` tensors, no bucket copies -- SURVEY G19) and the engine is told when a parameter
 is ready so the fused all-reduce + SGD kernel can start while backward is still running.
 
-Layers the kernels do not cover yet (grouped / depthwise convs, strided dgrad, SE, attention)
-run as plain torch ops on the same bf16 NHWC tensors, with their parameter gradients routed
-into the same flat buffer by a hook (see ``NativeEngine._make_leaf``).
+What still runs as plain torch ops on the same bf16 NHWC tensors (their parameter gradients are routed into the
+same flat buffer by a hook, see ``NativeEngine.w16_leaf``): very thin grouped convs (ResNeXt's 4-8 channels per
+group), convs / BN whose channel count is not a multiple of 8, the attention core of BoTNet's MHSA (QK^T +
+relative-position logits + softmax + PV) and the tiny activation / sigmoid ops of squeeze-excite.
 """
 from __future__ import annotations
 
