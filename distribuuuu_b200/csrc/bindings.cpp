@@ -165,15 +165,14 @@ TilePlan plan_tiles(int n_cols, int k_iters, long long m_tiles, int groups, int 
   TilePlan best{bn0, 0, 0};
   if (groups != 1) return best;
   auto nblk = [&](int bn) { return (n_cols + bn - 1) / bn; };
-  double best_traffic = (double)(kA + bn0 * 128) * k_iters * nblk(bn0);
-  for (int bn : {256, 128, 64}) {
-    if (bn > bn0) continue;
+  // Measured (profiles/conv_shapes_*): shrinking BN to make the slab fit, or running with fewer than 4 A stages,
+  // loses more to A re-reads / exposed latency than the saved weight traffic gains -- so only the natural BN and
+  // only slabs that leave a deep A ring qualify.
+  {
+    const int bn = bn0;
     const long long slab = (long long)k_iters * bn * 128;
-    const int stages = (int)((kRing - slab) / kA);
-    if (slab > kRing || stages < 2) continue;
-    if (nblk(bn) > sms || m_tiles * nblk(bn) < 2LL * sms) continue;   // needs several tiles per CTA to amortise
-    const double traffic = (double)kA * k_iters * nblk(bn);
-    if (traffic < 0.85 * best_traffic) { best_traffic = traffic; best = TilePlan{bn, 1, std::min(stages, 12)}; }
+    const int stages = slab <= kRing ? (int)((kRing - slab) / kA) : 0;
+    if (stages >= 4 && nblk(bn) <= sms && m_tiles * nblk(bn) >= 2LL * sms) best = TilePlan{bn, 1, std::min(stages, 12)};
   }
   return best;
 }
