@@ -1,0 +1,75 @@
+"""Host-side logic of the native engine that needs no GPU: bucket planning over the flat layout and the
+torch.optim.SGD-compatible optimizer state of FusedSGD (reference checkpoint layout, utils.py:375-380)."""
+import torch
+import torch.nn as nn
+
+from distribuuuu_b200.models import build_model
+from distribuuuu_b200.parallel.native_engine import _ALIGN, FusedSGD, NativeEngine
+
+
+class _HostEngine(NativeEngine):
+    """NativeEngine with the CUDA-dependent construction replaced by CPU tensors (layout logic only)."""
+
+    def __init__(self, module):
+        nn.Module.__init__(self)
+        self.module = module
+        self.world, self.rank, self.comm_mode = 1, 0, "local"
+        self.device = torch.device("cpu")
+        self._build_flat_storage()
+        self.flat_w16 = torch.zeros(self.total, dtype=torch.bfloat16)
+
+    def sync_masters(self):
+        pass
+
+
+def test_flat_layout_keeps_state_dict_and_alignment():
+    net = build_model("resnet18", num_classes=10)
+    want = {k: v.clone() for k, v in net.state_dict().items()}
+    eng = _HostEngine(net)
+    got = net.state_dict()
+    assert all(torch.equal(got[k], want[k]) for k in want)              # values survive the re-binding
+    for p in eng.params:
+        off, n = eng.index[p]
+        assert off % _ALIGN == 0 and n == p.numel()
+        assert p.data.data_ptr() == eng.flat_master[off:].data_ptr()    # parameters are views of the flat master
+    conv = net.conv1.weight                                             # 4-D weights are physically [O,H,W,I]
+    off, n = eng.index[conv]
+    O, I, H, W = conv.shape
+    assert torch.equal(eng.flat_master[off:off + n].view(O, H, W, I), conv.data.permute(0, 2, 3, 1))
+
+
+def test_buckets_cover_all_parameters_in_reverse_order():
+    net = build_model("resnet50")
+    eng = _HostEngine(net)
+    eng._plan_buckets(25 * 1024 * 1024)
+    assert (eng.buckets[0].n * 4) <= (1 << 20) + 4 * 2048 * 1000        # first bucket ~1 MiB (fc bias + ...)
+    covered = sorted((b.off, b.off + b.n) for b in eng.buckets)
+    assert covered[0][0] == 0 and covered[-1][1] == eng.total
+    assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))      # contiguous, non-overlapping
+    assert eng.buckets[0].params[0] is eng.params[-1]                    # gradients become ready last-layer first
+    assert sum(len(b.params) for b in eng.buckets) == len(eng.params)
+    assert all(b.n % 8 == 0 and b.off % 8 == 0 for b in eng.buckets)    # 16-byte vectors in the fused kernel
+
+
+def test_fused_sgd_state_dict_is_torch_sgd_compatible():
+    net = build_model("resnet18", num_classes=10)
+    eng = _HostEngine(net)
+    opt = FusedSGD(eng, lr=0.1, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    eng.flat_mom.uniform_(-1, 1)
+    opt.has_momentum_state = True
+    sd = opt.state_dict()
+    plain = build_model("resnet18", num_classes=10)
+    topt = torch.optim.SGD(plain.parameters(), lr=0.5, momentum=0.9, nesterov=True)
+    topt.load_state_dict(sd)                                            # the reference's optimizer accepts it
+    assert topt.param_groups[0]["lr"] == 0.1 and topt.param_groups[0]["weight_decay"] == 5e-5
+    for p_native, p_plain in zip(eng.params, plain.parameters()):
+        buf = topt.state[p_plain]["momentum_buffer"]
+        assert buf.shape == p_plain.shape
+        assert torch.equal(buf, eng.logical_view(eng.flat_mom, p_native))
+    # and the reverse direction: torch.optim.SGD state -> flat momentum
+    eng2 = _HostEngine(build_model("resnet18", num_classes=10))
+    opt2 = FusedSGD(eng2, lr=0.3, momentum=0.9, nesterov=True)
+    opt2.load_state_dict(topt.state_dict())
+    assert opt2.has_momentum_state and opt2.param_groups[0]["lr"] == 0.1
+    for pa, pb in zip(eng.params, eng2.params):                          # (alignment padding between parameters is don't-care)
+        assert torch.equal(eng.logical_view(eng.flat_mom, pa), eng2.logical_view(eng2.flat_mom, pb))
