@@ -237,6 +237,7 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   p.out = out.data_ptr(); p.ldo = g.K; p.tap_stride = 0;
   p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;
   p.bias = bias.has_value() ? bias->data_ptr<float>() : nullptr;
+  if (bias.has_value()) p.epi = EPI_BF16_BIAS;
   if (stats.has_value()) TORCH_CHECK(stats->numel() >= 2 * g.K && stats->scalar_type() == at::kFloat, "stats must be fp32 [2*K]");
   p.vb_per_item = 0; p.cin_boxes = 1; p.vboxes_total = 0;
   p.total_items = p.m_blocks * p.n_blocks * G;
@@ -298,6 +299,7 @@ void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64
     check_bf16_contig(*addend, "addend");
     TORCH_CHECK(addend->numel() == dx.numel(), "addend must have dx's shape");
     p.addend = 1;
+    p.epi = EPI_BF16_ADD;
     md = tiled_map_3d(addend->data_ptr(), cin_g, M, G, C, cin_g, 64, 32, 1);
   }
   int grid = std::min(p.total_items, num_sms());

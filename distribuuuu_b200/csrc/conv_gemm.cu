@@ -51,7 +51,9 @@ __device__ __forceinline__ PixelCoord decode_pixel(const ConvGemmParams& p, int 
 
 struct WorkItem { int m0, n0, nb, tap, it_begin, it_end, vb0, nbox, g; };
 
-__device__ __forceinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn) {
+// out of line on purpose: three warp roles call it once per work item; inlining triples ~150 instructions of
+// integer division in an instruction-cache-bound kernel
+__device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn) {
   WorkItem w;
   if (p.kind != KIND_WGRAD) {
     int nb = item % p.n_blocks;
@@ -108,7 +110,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
     tma_prefetch_desc(&map_b);
-    if (EPI == EPI_BF16) tma_prefetch_desc(&map_out);
+    if (EPI != EPI_F32_RED) tma_prefetch_desc(&map_out);
     for (int i = 0; i < C::kMaxStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
     mbar_init(smem_u32(bres_bar), 1);
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiThreads); }
@@ -231,7 +233,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int row_in_tile = quarter * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
 
-    if constexpr (EPI == EPI_BF16) {
+    if constexpr (EPI != EPI_F32_RED) {
+      constexpr bool kBias = (EPI == EPI_BF16_BIAS);
+      constexpr bool kAdd = (EPI == EPI_BF16_ADD);
       // TMEM -> registers -> bf16 -> 128B-swizzled smem (32 rows x 64 cols) -> TMA store (coalesced, clipped at the
       // M/N edges).  The BN statistics are column sums read back from that same smem tile: lane l owns columns
       // 2l, 2l+1 of the 64-column chunk (conflict-free LDS.32).  Two warps serve each TMEM lane quarter: with
@@ -239,9 +243,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // its statistics rows and meet on a named barrier.
       constexpr int NCH = BN / 64;
       const int half = (warp - 2) >> 2;
-      float st_sum[NCH][2], st_sq[NCH][2];
+      constexpr int NMINE = (NCH == 1) ? 1 : NCH / 2;   // 64-column chunks this warp owns per tile
+      float st_sum[NMINE][2], st_sq[NMINE][2];
 #pragma unroll
-      for (int c = 0; c < NCH; ++c) { st_sum[c][0] = st_sum[c][1] = 0.f; st_sq[c][0] = st_sq[c][1] = 0.f; }
+      for (int c = 0; c < NMINE; ++c) { st_sum[c][0] = st_sum[c][1] = 0.f; st_sq[c][0] = st_sq[c][1] = 0.f; }
       int st_nb = -1;
       const bool want_stats = (p.stats != nullptr);
       int buf = 0;
@@ -250,24 +255,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       const uint32_t pair_bar = 1 + quarter;      // named barrier id shared by the two warps of a quarter
       // optional addend (e.g. the residual-branch gradient in a dgrad): its tile is TMA-loaded into the staging
       // buffer first and summed in registers, which removes a separate elementwise add pass
-      const bool has_add = (p.addend != 0);
+      constexpr bool has_add = kAdd;
       const uint32_t my_add_bar = smem_u32(&add_bar[(NCH == 1 ? 0 : half) * 4 + quarter]);
       uint32_t add_phase = 0;
 
       auto flush_stats = [&](int nb) {
         if (nb < 0) return;
 #pragma unroll
-        for (int c = 0; c < NCH; ++c) {
-          if (NCH > 1 && (c & 1) != half) continue;
+        for (int ci = 0; ci < NMINE; ++ci) {
+          const int c = (NCH == 1) ? 0 : (2 * ci + half);
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             // nb enumerates (group, n-block); p.N is the per-group column count, stats are [2][groups * N]
             const int g = nb / p.n_blocks, col = (nb % p.n_blocks) * BN + c * 64 + 2 * lane + h;
             if (col < p.N) {
-              atomicAdd(p.stats + g * p.N + col, st_sum[c][h]);
-              atomicAdd(p.stats + p.groups * p.N + g * p.N + col, st_sq[c][h]);
+              atomicAdd(p.stats + g * p.N + col, st_sum[ci][h]);
+              atomicAdd(p.stats + p.groups * p.N + g * p.N + col, st_sq[ci][h]);
             }
-            st_sum[c][h] = 0.f; st_sq[c][h] = 0.f;
+            st_sum[ci][h] = 0.f; st_sq[ci][h] = 0.f;
           }
         }
       };
@@ -277,7 +282,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr, v);
         tmem_ld_wait();
-        if (p.bias != nullptr) {
+        if constexpr (kBias) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int col = col_first + j;
@@ -285,7 +290,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             v[j] = __float_as_uint(__uint_as_float(v[j]) + b);
           }
         }
-        if (has_add) {
+        if constexpr (kAdd) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             const uint4 ad = *reinterpret_cast<const uint4*>(sbuf + lane * 128 + (((g0 + g) ^ (lane & 7)) << 4));
@@ -307,7 +312,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((g0 + g) ^ (lane & 7)) << 4)) = pk;
         }
       };
-      auto column_stats = [&](const uint8_t* sbuf, int r0, int r1, int rows_valid, int c) {
+      auto column_stats = [&](const uint8_t* sbuf, int r0, int r1, int rows_valid, int ci) {
         float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
         for (int r = r0; r < r1; ++r) {
@@ -317,7 +322,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           a0 += f0; q0 = fmaf(f0, f0, q0);
           a1 += f1; q1 = fmaf(f1, f1, q1);
         }
-        st_sum[c][0] += a0; st_sum[c][1] += a1; st_sq[c][0] += q0; st_sq[c][1] += q1;
+        st_sum[ci][0] += a0; st_sum[ci][1] += a1; st_sq[ci][0] += q0; st_sq[ci][1] += q1;
       };
 
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -351,8 +356,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           buf ^= 1;
         } else {
 #pragma unroll
-          for (int c = 0; c < NCH; ++c) {
-            if ((c & 1) != half) continue;               // the sibling warp of this quarter takes these chunks
+          for (int ci = 0; ci < NMINE; ++ci) {
+            const int c = 2 * ci + half;                  // the sibling warp of this quarter takes the other chunks
             const int col0 = w.n0 + c * 64;
             if (col0 >= p.N) continue;                   // chunk entirely past the N edge
             uint8_t* sbuf = my_stage + buf * 4096;
@@ -373,7 +378,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               tma_store_3d(&map_out, smem_u32(sbuf), col0, row_base, w.g);
               bulk_commit_group();
             }
-            if (want_stats) column_stats(sbuf, 0, 32, rows_valid, c);
+            if (want_stats) column_stats(sbuf, 0, 32, rows_valid, ci);
             buf ^= 1;
           }
         }
@@ -455,14 +460,19 @@ extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap
                                      cudaStream_t stream) {
   using namespace b200;
   cudaError_t e = cudaErrorInvalidValue;
-  if (p->epi == EPI_BF16) {
-    if (bn == 64) e = launch_one<64, EPI_BF16>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
-    else if (bn == 128) e = launch_one<128, EPI_BF16>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
-    else if (bn == 256) e = launch_one<256, EPI_BF16>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
-  } else {
-    if (bn == 64) e = launch_one<64, EPI_F32_RED>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
-    else if (bn == 128) e = launch_one<128, EPI_F32_RED>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
-    else if (bn == 256) e = launch_one<256, EPI_F32_RED>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
+#define B200_DISPATCH_BN(EPI_)                                                                          \
+  do {                                                                                                 \
+    if (bn == 64) e = launch_one<64, EPI_>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);       \
+    else if (bn == 128) e = launch_one<128, EPI_>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream); \
+    else if (bn == 256) e = launch_one<256, EPI_>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream); \
+  } while (0)
+  switch (p->epi) {
+    case EPI_BF16: B200_DISPATCH_BN(EPI_BF16); break;
+    case EPI_BF16_BIAS: B200_DISPATCH_BN(EPI_BF16_BIAS); break;
+    case EPI_BF16_ADD: B200_DISPATCH_BN(EPI_BF16_ADD); break;
+    case EPI_F32_RED: B200_DISPATCH_BN(EPI_F32_RED); break;
+    default: break;
   }
+#undef B200_DISPATCH_BN
   return (int)e;
 }

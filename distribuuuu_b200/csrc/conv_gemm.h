@@ -5,7 +5,9 @@
 #include <stdint.h>
 
 enum ConvGemmKind { KIND_FPROP = 0, KIND_DGRAD = 1, KIND_WGRAD = 2 };
-enum ConvGemmEpi { EPI_BF16 = 0, EPI_F32_RED = 1 };
+// EPI_BF16: bf16 TMA-store epilogue (+ BN statistics); _BIAS / _ADD add a per-column bias / an addend tile.  They are
+// separate instantiations so the common path carries no dead bias/addend code (the epilogue is I-cache sensitive).
+enum ConvGemmEpi { EPI_BF16 = 0, EPI_F32_RED = 1, EPI_BF16_BIAS = 2, EPI_BF16_ADD = 3 };
 
 struct ConvGemmParams {
   int kind;            // ConvGemmKind
