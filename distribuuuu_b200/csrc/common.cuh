@@ -46,7 +46,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: traps (instead of hanging the device) if the barrier never flips.  The slow path lives in ONE
 // out-of-line function: the persistent GEMM kernel has ~20 wait sites and is instruction-cache sensitive.
-__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
+static __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity) {
   long long t0 = clock64();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {

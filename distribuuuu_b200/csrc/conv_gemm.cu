@@ -53,7 +53,7 @@ struct WorkItem { int m0, n0, nb, tap, it_begin, it_end, vb0, nbox, g; };
 
 // out of line on purpose: three warp roles call it once per work item; inlining triples ~150 instructions of
 // integer division in an instruction-cache-bound kernel
-__device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn) {
+static __device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn) {
   WorkItem w;
   if (p.kind != KIND_WGRAD) {
     int nb = item % p.n_blocks;
