@@ -459,7 +459,8 @@ void bn_backward(const at::Tensor& y, const at::Tensor& dout, const c10::optiona
                  c10::optional<at::Tensor> dresidual, at::Tensor& sums, int64_t sym_offset,
                  const c10::optional<at::Tensor>& gamma, const c10::optional<at::Tensor>& beta, const at::Tensor& save_mean,
                  const at::Tensor& save_invstd, c10::optional<at::Tensor> dgamma, c10::optional<at::Tensor> dbeta,
-                 double count, int64_t act, PeerState* peer, const c10::optional<at::Tensor>& relu_mask) {
+                 double count, int64_t act, PeerState* peer, const c10::optional<at::Tensor>& relu_mask, int64_t phase) {
+  // phase: 3 = reduce + apply (normal); 1 / 2 = only that pass (tools/bench_bn.py times them separately)
   c10::cuda::CUDAGuard guard(y.device());
   TORCH_CHECK(y.dim() == 2 && y.stride(1) == 1 && dout.stride(1) == 1 && dy.stride(1) == 1, "bn_backward expects [rows, C] views");
   TORCH_CHECK(dy.stride(0) == y.stride(0), "dy must share y's row pitch");
@@ -478,9 +479,9 @@ void bn_backward(const at::Tensor& y, const at::Tensor& dout, const c10::optiona
   p.count = (float)count; p.act = act;
   p.relu_mask = relu_mask.has_value() ? relu_mask->data_ptr<uint8_t>() : nullptr;
   p.peer = PeerCtx{}; p.peer.world = 1;
-  B200_CUDA_OK(b200_bn_bwd_reduce(&p, cur_stream()));
+  if (phase & 1) B200_CUDA_OK(b200_bn_bwd_reduce(&p, cur_stream()));
   if (peer) p.peer = peer->make();
-  B200_CUDA_OK(b200_bn_bwd_apply(&p, cur_stream()));
+  if (phase & 2) B200_CUDA_OK(b200_bn_bwd_apply(&p, cur_stream()));
 }
 
 void maxpool_fwd(const at::Tensor& x, at::Tensor& out, c10::optional<at::Tensor> argmax, int64_t k, int64_t stride, int64_t pad) {
@@ -659,7 +660,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_stats", &bn_stats);
   m.def("bn_backward", &bn_backward, py::arg("y"), py::arg("dout"), py::arg("residual"), py::arg("dy"), py::arg("dresidual"), py::arg("sums"),
         py::arg("sym_offset"), py::arg("gamma"), py::arg("beta"), py::arg("save_mean"), py::arg("save_invstd"), py::arg("dgamma"), py::arg("dbeta"),
-        py::arg("count"), py::arg("act"), py::arg("peer"), py::arg("relu_mask") = py::none());
+        py::arg("count"), py::arg("act"), py::arg("peer"), py::arg("relu_mask") = py::none(), py::arg("phase") = 3);
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
   m.def("gap_fwd", &gap_fwd);

@@ -34,7 +34,6 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-constexpr int kRing = 4;        // ring depth (stages); kRing-1 rows per thread are in flight
 constexpr int kBnThreads = 256;
 __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   BF8 raw;
@@ -42,15 +41,9 @@ __device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) {
   for (int i = 0; i < 4; ++i) raw.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
   *reinterpret_cast<BF8*>(p) = raw;
 }
-__device__ __forceinline__ float act_fwd(float z, int act) {
-  if (act == ACT_RELU) return fmaxf(z, 0.f);
-  if (act == ACT_SILU) return z / (1.f + __expf(-z));
-  return z;
-}
-__device__ __forceinline__ float act_bwd(float z, int act) {  // d act / d z
-  if (act == ACT_RELU) return z > 0.f ? 1.f : 0.f;
-  if (act == ACT_SILU) { float s = 1.f / (1.f + __expf(-z)); return s * (1.f + z * (1.f - s)); }
-  return 1.f;
+__device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -123,77 +116,97 @@ __device__ __forceinline__ void gather_stats(const PeerCtx& pc, const float* loc
 // (+ residual) + activation in ONE pass over the conv output.
 // grid: (ceil(C/8 / blockDim.x), row_chunks); block: (cvx, rows_per_block)
 // ------------------------------------------------------------------------------------------------
+template <int ACT>
+__device__ __forceinline__ float act_fwd_t(float z) {
+  if (ACT == ACT_RELU) return fmaxf(z, 0.f);
+  if (ACT == ACT_SILU) return z / (1.f + __expf(-z));
+  return z;
+}
+template <bool RES> struct FwdRing {
+  static constexpr int kArr = RES ? 2 : 1;
+  static constexpr int kDepth = RES ? 4 : 8;
+  static constexpr int kBytes = kDepth * kArr * kBnThreads * 16;   // 32 KB
+};
+template <int ACT, bool RES>
 __global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyParams p) {
-  if (p.peer.world > 1 && p.training) peer_exchange_wait(p.peer);
+  using R = FwdRing<RES>;
+  constexpr int D = R::kDepth, A = R::kArr;
+  extern __shared__ __align__(16) unsigned char dyn_raw[];
+  uint4* ring = reinterpret_cast<uint4*>(dyn_raw);  // [D][A][256]
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = cv * VEC;
-  if (c0 >= p.C) return;
-  float scale[8], shift[8];
-  if (p.training) {
-    float s0[8], s1[8];
-    gather_stats(p.peer, p.stats, p.sym_offset, p.C, c0, s0, s1);
-    const float inv_n = 1.f / p.count;
-    const bool writer = (blockIdx.y == 0 && threadIdx.y == 0);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float mean = s0[i] * inv_n;
-      const float var = fmaxf(s1[i] * inv_n - mean * mean, 0.f);
-      const float invstd = rsqrtf(var + p.eps);
-      const float g = p.gamma ? p.gamma[c0 + i] : 1.f;
-      const float b = p.beta ? p.beta[c0 + i] : 0.f;
-      scale[i] = g * invstd;
-      shift[i] = b - mean * scale[i];
-      if (writer) {
-        p.save_mean[c0 + i] = mean;
-        p.save_invstd[c0 + i] = invstd;
-        if (p.running_mean) {
-          const float unbiased = var * (p.count / fmaxf(p.count - 1.f, 1.f));
-          p.running_mean[c0 + i] = (1.f - p.momentum) * p.running_mean[c0 + i] + p.momentum * mean;
-          p.running_var[c0 + i] = (1.f - p.momentum) * p.running_var[c0 + i] + p.momentum * unbiased;
-        }
-      }
-    }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float invstd = rsqrtf(p.running_var[c0 + i] + p.eps);
-      const float g = p.gamma ? p.gamma[c0 + i] : 1.f;
-      const float b = p.beta ? p.beta[c0 + i] : 0.f;
-      scale[i] = g * invstd;
-      shift[i] = b - p.running_mean[c0 + i] * scale[i];
-    }
-  }
-  extern __shared__ __align__(16) unsigned char dyn_raw[];
-  uint4* ring = reinterpret_cast<uint4*>(dyn_raw);  // [kRing][2][256]
+  const bool active = c0 < p.C;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const long long rstride = (long long)gridDim.y * blockDim.y;
   const long long row0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-  const bool has_res = p.residual != nullptr;
   auto issue = [&](int stage, long long r) {
-    if (r < p.rows) {
-      cp_async16(&ring[(stage * 2 + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
-      if (has_res) cp_async16(&ring[(stage * 2 + 1) * kBnThreads + tid], p.residual + r * p.ldr + c0);
+    if (active && r < p.rows) {
+      cp_async16(&ring[(stage * A + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
+      if (RES) cp_async16(&ring[(stage * A + A - 1) * kBnThreads + tid], p.residual + r * p.ldr + c0);
     }
     cp_async_commit();
   };
+  // the conv output does not depend on the peers' statistics: start streaming it before waiting on the exchange
   long long r_issue = row0;
 #pragma unroll
-  for (int st = 0; st < kRing - 1; ++st) { issue(st, r_issue); r_issue += rstride; }
+  for (int st = 0; st < D - 1; ++st) { issue(st, r_issue); r_issue += rstride; }
+  if (p.peer.world > 1 && p.training) peer_exchange_wait(p.peer);
+  if (!active) { cp_async_wait<0>(); return; }
+  float scale[8], shift[8];
+  {
+    float g[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = 1.f; b[i] = 0.f; }
+    if (p.gamma) ld8f(p.gamma + c0, g);
+    if (p.beta) ld8f(p.beta + c0, b);
+    if (p.training) {
+      float s0[8], s1[8];
+      gather_stats(p.peer, p.stats, p.sym_offset, p.C, c0, s0, s1);
+      const float inv_n = 1.f / p.count;
+      const bool writer = (blockIdx.y == 0 && threadIdx.y == 0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mean = s0[i] * inv_n;
+        const float var = fmaxf(s1[i] * inv_n - mean * mean, 0.f);
+        const float invstd = rsqrtf(var + p.eps);
+        scale[i] = g[i] * invstd;
+        shift[i] = b[i] - mean * scale[i];
+        if (writer) {
+          p.save_mean[c0 + i] = mean;
+          p.save_invstd[c0 + i] = invstd;
+          if (p.running_mean) {
+            const float unbiased = var * (p.count / fmaxf(p.count - 1.f, 1.f));
+            p.running_mean[c0 + i] = (1.f - p.momentum) * p.running_mean[c0 + i] + p.momentum * mean;
+            p.running_var[c0 + i] = (1.f - p.momentum) * p.running_var[c0 + i] + p.momentum * unbiased;
+          }
+        }
+      }
+    } else {
+      float rm[8], rv[8];
+      ld8f(p.running_mean + c0, rm);
+      ld8f(p.running_var + c0, rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        scale[i] = g[i] * rsqrtf(rv[i] + p.eps);
+        shift[i] = b[i] - rm[i] * scale[i];
+      }
+    }
+  }
   int st = 0;
   for (long long r = row0; r < p.rows; r += rstride) {
-    issue((st + kRing - 1) % kRing, r_issue);
+    issue(st == 0 ? D - 1 : st - 1, r_issue);
     r_issue += rstride;
-    cp_async_wait<kRing - 1>();
+    cp_async_wait<D - 1>();
     float x[8];
-    unpack8f(ring[(st * 2 + 0) * kBnThreads + tid], x);
-    if (has_res) {
+    unpack8f(ring[(st * A + 0) * kBnThreads + tid], x);
+    if (RES) {
       float q[8];
-      unpack8f(ring[(st * 2 + 1) * kBnThreads + tid], q);
+      unpack8f(ring[(st * A + A - 1) * kBnThreads + tid], q);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]) + q[i], p.act);
+      for (int i = 0; i < 8; ++i) x[i] = act_fwd_t<ACT>(fmaf(x[i], scale[i], shift[i]) + q[i]);
     } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) x[i] = act_fwd(fmaf(x[i], scale[i], shift[i]), p.act);
+      for (int i = 0; i < 8; ++i) x[i] = act_fwd_t<ACT>(fmaf(x[i], scale[i], shift[i]));
     }
     store8(p.out + r * p.ldo + c0, x);
     if (p.relu_mask) {
@@ -202,7 +215,7 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyParams p) {
       for (int i = 0; i < 8; ++i) bits |= (x[i] > 0.f ? 1u : 0u) << i;
       p.relu_mask[r * (p.C / VEC) + cv] = (uint8_t)bits;
     }
-    st = (st + 1) % kRing;
+    st = (st + 1 == D) ? 0 : st + 1;
   }
   cp_async_wait<0>();
 }
@@ -252,159 +265,238 @@ __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ y, long long r
 }
 
 // ------------------------------------------------------------------------------------------------
-// BN backward, pass 1: per-channel sum(dz) and sum(dz * xhat), dz = dout * act'(z), z recomputed from y.
+// BN backward.  Both passes are specialised at compile time on the activation and on how act'(z) is obtained:
+//   BWD_PLAIN : recomputed from the conv output y (z = y*scale + shift)
+//   BWD_MASK  : read from the 1-bit/element ReLU mask the forward pass stored (residual layers)
+//   BWD_RES   : recomputed from y and the forward residual (three input streams)
+// so the streaming loops are straight-line code.  The cp.async ring is 6 deep for two input streams and 4 deep for
+// three (48 KB either way); the mask byte of a row is fetched into a register when that row's cp.async is issued,
+// i.e. RING-1 iterations before it is consumed, so no global-load latency is exposed inside the loop.
 // ------------------------------------------------------------------------------------------------
+enum { BWD_PLAIN = 0, BWD_MASK = 1, BWD_RES = 2 };
+
+__device__ __forceinline__ void red_add_v4(float* dst, float x, float y, float z, float w) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+template <int ACT>
+__device__ __forceinline__ float act_bwd_t(float z) {
+  if (ACT == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+  if (ACT == ACT_SILU) { const float s = 1.f / (1.f + __expf(-z)); return s * (1.f + z * (1.f - s)); }
+  return 1.f;
+}
+template <int MODE> struct BwdRing {
+  static constexpr int kArr = (MODE == BWD_RES) ? 3 : 2;
+  static constexpr int kDepth = (MODE == BWD_RES) ? 4 : 6;
+  static constexpr int kBytes = kDepth * kArr * kBnThreads * 16;   // 48 KB
+};
+// dz = dout * act'(z) for the 8 channels of one row
+template <int ACT, int MODE>
+__device__ __forceinline__ void bwd_dz(float (&d)[8], const float (&y)[8], const float (&q)[8], uint32_t mbits,
+                                       const float (&scale)[8], const float (&shift)[8]) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    if (MODE == BWD_MASK) d[i] = ((mbits >> i) & 1u) ? d[i] : 0.f;
+    else if (ACT != ACT_NONE) d[i] *= act_bwd_t<ACT>(fmaf(y[i], scale[i], shift[i]) + (MODE == BWD_RES ? q[i] : 0.f));
+  }
+}
+
+// pass 1: per-channel sum(dz) and sum(dz * xhat)
+template <int ACT, int MODE>
 __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdParams p) {
+  using R = BwdRing<MODE>;
+  constexpr int D = R::kDepth, A = R::kArr;
   extern __shared__ __align__(16) float dyn[];
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = cv * VEC;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   float a[8], b[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
   if (c0 < p.C) {
-    // xhat = y*invstd + nmi ;  z = y*scale + shift  (z only needed for the activation derivative)
-    float invstd[8], nmi[8], scale[8], shift[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float mean = p.save_mean[c0 + i];
-      invstd[i] = p.save_invstd[c0 + i];
-      nmi[i] = -mean * invstd[i];
-      const float g = p.gamma ? p.gamma[c0 + i] : 1.f, be = p.beta ? p.beta[c0 + i] : 0.f;
-      scale[i] = g * invstd[i];
-      shift[i] = be - mean * scale[i];
-    }
-    uint4* ring = reinterpret_cast<uint4*>(dyn);  // [kRing][3][256]
-    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    uint4* ring = reinterpret_cast<uint4*>(dyn);  // [D][A][256]
     const long long rstride = (long long)gridDim.y * blockDim.y;
     const long long row0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-    const bool use_mask = (p.relu_mask != nullptr);
-    const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr) && !use_mask;
     const uint8_t* mrow = p.relu_mask + cv;
     const int mpitch = p.C / VEC;
-    auto issue = [&](int stage, long long r) {
+    uint32_t mq[D - 1];
+    auto issue = [&](int stage, long long r, uint32_t& m, bool with_mask) {
+      if (with_mask) m = 0u;
       if (r < p.rows) {
-        cp_async16(&ring[(stage * 3 + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
-        cp_async16(&ring[(stage * 3 + 1) * kBnThreads + tid], p.dout + r * p.ldd + c0);
-        if (need_res) cp_async16(&ring[(stage * 3 + 2) * kBnThreads + tid], p.residual + r * p.ldr + c0);
+        cp_async16(&ring[(stage * A + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
+        cp_async16(&ring[(stage * A + 1) * kBnThreads + tid], p.dout + r * p.ldd + c0);
+        if (MODE == BWD_RES) cp_async16(&ring[(stage * A + A - 1) * kBnThreads + tid], p.residual + r * p.ldr + c0);
+        if (MODE == BWD_MASK && with_mask) m = (uint32_t)__ldg(mrow + r * mpitch);
       }
       cp_async_commit();
     };
     long long r_issue = row0;
 #pragma unroll
-    for (int st = 0; st < kRing - 1; ++st) { issue(st, r_issue); r_issue += rstride; }
-    int st = 0;
-    for (long long r = row0; r < p.rows; r += rstride) {
-      issue((st + kRing - 1) % kRing, r_issue);
-      r_issue += rstride;
-      cp_async_wait<kRing - 1>();
-      float y[8], d[8], q[8];
-      unpack8f(ring[(st * 3 + 0) * kBnThreads + tid], y);
-      unpack8f(ring[(st * 3 + 1) * kBnThreads + tid], d);
-      if (need_res) unpack8f(ring[(st * 3 + 2) * kBnThreads + tid], q);
-      const uint32_t mbits = use_mask ? (uint32_t)__ldg(mrow + r * mpitch) : 0u;
+    for (int st = 0; st < D - 1; ++st) { issue(st, r_issue, mq[st], true); r_issue += rstride; }
+    // per-channel constants (loaded after the ring is primed so their latency overlaps the first rows)
+    float invstd[8], nmi[8], scale[8], shift[8];
+    {
+      float mean[8];
+      ld8f(p.save_mean + c0, mean);
+      ld8f(p.save_invstd + c0, invstd);
+      float g[8], be[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { g[i] = 1.f; be[i] = 0.f; }
+      if (ACT != ACT_NONE && MODE != BWD_MASK) {
+        if (p.gamma) ld8f(p.gamma + c0, g);
+        if (p.beta) ld8f(p.beta + c0, be);
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        if (use_mask) d[i] = ((mbits >> i) & 1u) ? d[i] : 0.f;
-        else if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
-        a[i] += d[i];
-        b[i] = fmaf(d[i], fmaf(y[i], invstd[i], nmi[i]), b[i]);
+        nmi[i] = -mean[i] * invstd[i];
+        scale[i] = g[i] * invstd[i];
+        shift[i] = be[i] - mean[i] * scale[i];
       }
-      st = (st + 1) % kRing;
+    }
+    // The loop is unrolled by the number of rows in flight so that the prefetched mask bytes keep fixed register
+    // names (rotating them with moves would make every iteration wait for the load issued just before it).
+    int st = 0;
+    long long r = row0;
+    while (r < p.rows) {
+#pragma unroll
+      for (int j = 0; j < D - 1; ++j) {
+        if (r >= p.rows) break;
+        uint32_t unused;
+        issue(st == 0 ? D - 1 : st - 1, r_issue, unused, false);
+        cp_async_wait<D - 1>();
+        float y[8], d[8], q[8];
+        unpack8f(ring[(st * A + 0) * kBnThreads + tid], y);
+        unpack8f(ring[(st * A + 1) * kBnThreads + tid], d);
+        if (MODE == BWD_RES) unpack8f(ring[(st * A + A - 1) * kBnThreads + tid], q);
+        bwd_dz<ACT, MODE>(d, y, q, mq[j], scale, shift);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[i] += d[i];
+          b[i] = fmaf(d[i], fmaf(y[i], invstd[i], nmi[i]), b[i]);
+        }
+        // reload this slot's mask byte only now that the old one is dead: the load lands in the same register
+        if (MODE == BWD_MASK) mq[j] = (r_issue < p.rows) ? (uint32_t)__ldg(mrow + r_issue * mpitch) : 0u;
+        r_issue += rstride;
+        st = (st + 1 == D) ? 0 : st + 1;
+        r += rstride;
+      }
     }
     cp_async_wait<0>();
   }
-  __syncthreads();  // the ring memory is reused for the cross-row reduction below
-  float* mine = dyn + ((size_t)threadIdx.y * blockDim.x + threadIdx.x) * 16;
+  // CTA-level reduction over threadIdx.y through shared memory (component-major: conflict-free), then one vector
+  // RED per 4 channels -- a quarter of the atomic operations of a scalar flush (the L2 atomic unit serialises them)
+  __syncthreads();   // the ring memory is reused
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { mine[i] = a[i]; mine[8 + i] = b[i]; }
+  for (int i = 0; i < 8; ++i) { dyn[i * kBnThreads + tid] = a[i]; dyn[(8 + i) * kBnThreads + tid] = b[i]; }
   __syncthreads();
-  if (threadIdx.y == 0 && c0 < p.C) {
-    for (int yy = 1; yy < blockDim.y; ++yy) {
-      const float* o = dyn + ((size_t)yy * blockDim.x + threadIdx.x) * 16;
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { a[i] += o[i]; b[i] += o[8 + i]; }
+  const int bdx = blockDim.x, bdy = blockDim.y;
+  if (tid < 4 * bdx) {
+    const int quad = tid / bdx, tx = tid - quad * bdx;
+    const int c = (blockIdx.x * bdx + tx) * VEC;
+    if (c < p.C) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float* src = dyn + (quad * 4) * kBnThreads + tx;
+      for (int yy = 0; yy < bdy; ++yy) {
+        s0 += src[yy * bdx];
+        s1 += src[kBnThreads + yy * bdx];
+        s2 += src[2 * kBnThreads + yy * bdx];
+        s3 += src[3 * kBnThreads + yy * bdx];
+      }
+      red_add_v4(p.sums + (quad >= 2 ? p.C : 0) + c + (quad & 1) * 4, s0, s1, s2, s3);
     }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { atomicAdd(p.sums + c0 + i, a[i]); atomicAdd(p.sums + p.C + c0 + i, b[i]); }
   }
 }
 
-// BN backward, pass 2: dy = (dz - mean(dz) - xhat * mean(dz*xhat)) * gamma * invstd (means over all ranks for SyncBN);
+// pass 2: dy = (dz - mean(dz) - xhat * mean(dz*xhat)) * gamma * invstd (means over all ranks for SyncBN);
 // also emits d(residual) = dz and the local dgamma / dbeta.
+template <int ACT, int MODE>
 __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdParams p) {
-  if (p.peer.world > 1) peer_exchange_wait(p.peer);
+  using R = BwdRing<MODE>;
+  constexpr int D = R::kDepth, A = R::kArr;
+  extern __shared__ __align__(16) unsigned char dyn_raw[];
+  uint4* ring = reinterpret_cast<uint4*>(dyn_raw);  // [D][A][256]
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = cv * VEC;
-  if (c0 >= p.C) return;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  const bool active = c0 < p.C;
+  const long long rstride = (long long)gridDim.y * blockDim.y;
+  const long long k0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
+  const uint8_t* mrow = p.relu_mask + cv;
+  const int mpitch = p.C / VEC;
+  uint32_t mq[D - 1];
+  // rows are visited from the END of the tensor: the reduce pass finished there, so those lines are the likeliest L2 hits
+  auto issue = [&](int stage, long long kk, uint32_t& m, bool with_mask) {
+    if (with_mask) m = 0u;
+    if (active && kk < p.rows) {
+      const long long r = p.rows - 1 - kk;
+      cp_async16(&ring[(stage * A + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
+      cp_async16(&ring[(stage * A + 1) * kBnThreads + tid], p.dout + r * p.ldd + c0);
+      if (MODE == BWD_RES) cp_async16(&ring[(stage * A + A - 1) * kBnThreads + tid], p.residual + r * p.ldr + c0);
+      if (MODE == BWD_MASK && with_mask) m = (uint32_t)__ldg(mrow + r * mpitch);
+    }
+    cp_async_commit();
+  };
+  // the activations do not depend on the peers' statistics: get them moving before waiting on the exchange
+  long long k_issue = k0;
+#pragma unroll
+  for (int st = 0; st < D - 1; ++st) { issue(st, k_issue, mq[st], true); k_issue += rstride; }
+  if (p.peer.world > 1) peer_exchange_wait(p.peer);
+  if (!active) { cp_async_wait<0>(); return; }
   // dy = (dz - mean(dz) - xhat*mean(dz*xhat)) * gamma*invstd  ==  dz*scale + y*ca + cb
   float scale[8], shift[8], ca[8], cb[8];
   {
     float s0[8], s1[8];
     gather_stats(p.peer, p.sums, p.sym_offset, p.C, c0, s0, s1);
     const float inv_n = 1.f / p.count;
-    const bool writer = (blockIdx.y == 0 && threadIdx.y == 0);
+    float mean[8], invstd[8], g[8], be[8];
+    ld8f(p.save_mean + c0, mean);
+    ld8f(p.save_invstd + c0, invstd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = 1.f; be[i] = 0.f; }
+    if (p.gamma) ld8f(p.gamma + c0, g);
+    if (p.beta) ld8f(p.beta + c0, be);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float mean = p.save_mean[c0 + i], invstd = p.save_invstd[c0 + i];
-      const float g = p.gamma ? p.gamma[c0 + i] : 1.f, be = p.beta ? p.beta[c0 + i] : 0.f;
       const float m_dz = s0[i] * inv_n, m_dzx = s1[i] * inv_n;
-      scale[i] = g * invstd;
-      shift[i] = be - mean * scale[i];
-      ca[i] = -invstd * m_dzx * scale[i];
-      cb[i] = -m_dz * scale[i] - mean * ca[i];
+      scale[i] = g[i] * invstd[i];
+      shift[i] = be[i] - mean[i] * scale[i];
+      ca[i] = -invstd[i] * m_dzx * scale[i];
+      cb[i] = -m_dz * scale[i] - mean[i] * ca[i];
     }
-    if (writer && p.dgamma) {
+    if (blockIdx.y == 0 && threadIdx.y == 0 && p.dgamma) {
       // parameter gradients use the LOCAL sums (the gradient all-reduce averages them afterwards, as DDP does)
-      const float* loc = p.sums;
+      float lg[8], lb[8], dg[8], db[8];
+      ld8f(p.sums + p.C + c0, lg);
+      ld8f(p.sums + c0, lb);
+      ld8f(p.dgamma + c0, dg);
+      ld8f(p.dbeta + c0, db);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        p.dgamma[c0 + i] += loc[p.C + c0 + i];
-        p.dbeta[c0 + i] += loc[c0 + i];
-      }
+      for (int i = 0; i < 8; ++i) { p.dgamma[c0 + i] = dg[i] + lg[i]; p.dbeta[c0 + i] = db[i] + lb[i]; }
     }
   }
-  extern __shared__ __align__(16) unsigned char dyn_raw[];
-  uint4* ring = reinterpret_cast<uint4*>(dyn_raw);  // [kRing][3][256]
-  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  const long long rstride = (long long)gridDim.y * blockDim.y;
-  const long long k0 = (long long)blockIdx.y * blockDim.y + threadIdx.y;
-  const bool use_mask = (p.relu_mask != nullptr);
-  const bool need_res = (p.act != ACT_NONE) && (p.residual != nullptr) && !use_mask;
-  const uint8_t* mrow = p.relu_mask + cv;
-  const int mpitch = p.C / VEC;
-  // rows are visited from the END of the tensor: the reduce pass finished there, so those lines are the likeliest L2 hits
-  auto issue = [&](int stage, long long kk) {
-    if (kk < p.rows) {
-      const long long r = p.rows - 1 - kk;
-      cp_async16(&ring[(stage * 3 + 0) * kBnThreads + tid], p.y + r * p.ldy + c0);
-      cp_async16(&ring[(stage * 3 + 1) * kBnThreads + tid], p.dout + r * p.ldd + c0);
-      if (need_res) cp_async16(&ring[(stage * 3 + 2) * kBnThreads + tid], p.residual + r * p.ldr + c0);
-    }
-    cp_async_commit();
-  };
-  long long k_issue = k0;
-#pragma unroll
-  for (int st = 0; st < kRing - 1; ++st) { issue(st, k_issue); k_issue += rstride; }
   int st = 0;
-  for (long long kk = k0; kk < p.rows; kk += rstride) {
-    issue((st + kRing - 1) % kRing, k_issue);
-    k_issue += rstride;
-    cp_async_wait<kRing - 1>();
-    const long long r = p.rows - 1 - kk;
-    float y[8], d[8], q[8], o[8];
-    unpack8f(ring[(st * 3 + 0) * kBnThreads + tid], y);
-    unpack8f(ring[(st * 3 + 1) * kBnThreads + tid], d);
-    if (need_res) unpack8f(ring[(st * 3 + 2) * kBnThreads + tid], q);
-    const uint32_t mbits = use_mask ? (uint32_t)__ldg(mrow + r * mpitch) : 0u;
+  long long kk = k0;
+  while (kk < p.rows) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (use_mask) d[i] = ((mbits >> i) & 1u) ? d[i] : 0.f;
-      else if (p.act != ACT_NONE) d[i] *= act_bwd(fmaf(y[i], scale[i], shift[i]) + (need_res ? q[i] : 0.f), p.act);
-      o[i] = fmaf(d[i], scale[i], fmaf(y[i], ca[i], cb[i]));
+    for (int j = 0; j < D - 1; ++j) {   // unrolled so the prefetched mask bytes keep fixed register names
+      if (kk >= p.rows) break;
+      uint32_t unused;
+      issue(st == 0 ? D - 1 : st - 1, k_issue, unused, false);
+      cp_async_wait<D - 1>();
+      const long long r = p.rows - 1 - kk;
+      float y[8], d[8], q[8], o[8];
+      unpack8f(ring[(st * A + 0) * kBnThreads + tid], y);
+      unpack8f(ring[(st * A + 1) * kBnThreads + tid], d);
+      if (MODE == BWD_RES) unpack8f(ring[(st * A + A - 1) * kBnThreads + tid], q);
+      bwd_dz<ACT, MODE>(d, y, q, mq[j], scale, shift);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(d[i], scale[i], fmaf(y[i], ca[i], cb[i]));
+      if (p.dresidual) store8(p.dresidual + r * p.ldr + c0, d);
+      store8(p.dy + r * p.ldy + c0, o);
+      if (MODE == BWD_MASK) mq[j] = (k_issue < p.rows) ? (uint32_t)__ldg(mrow + (p.rows - 1 - k_issue) * mpitch) : 0u;
+      k_issue += rstride;
+      st = (st + 1 == D) ? 0 : st + 1;
+      kk += rstride;
     }
-    if (p.dresidual) store8(p.dresidual + r * p.ldr + c0, d);
-    store8(p.dy + r * p.ldy + c0, o);
-    st = (st + 1) % kRing;
   }
   cp_async_wait<0>();
 }
@@ -413,73 +505,84 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdParams p) {
 // ------------------------------------------------------------------------------------------------
 // Max-pool 3x3 / stride 2 / pad 1 (NHWC), forward stores the argmax tap (0..8) for an atomic-free backward.
 // ------------------------------------------------------------------------------------------------
-__global__ void maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
+// Index math is 32-bit: one CTA-row loop over (n, output row) and an inner loop over (column, channel vector), so
+// the hot loops contain no 64-bit divisions (they made the first version instruction-bound, ~5x off the HBM time).
+__global__ void __launch_bounds__(256) maxpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out,
                                    uint8_t* __restrict__ argmax, int N, int H, int W, int C, int P, int Q, int k,
                                    int stride, int pad) {
-  const long long total = (long long)N * P * Q * (C / VEC);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = idx % (C / VEC);
-    long long pix = idx / (C / VEC);
-    const int q = pix % Q; pix /= Q;
-    const int ph = pix % P; const int n = pix / P;
-    float best[8]; int arg[8];
+  const int cvs = C / VEC;
+  const int per_row = Q * cvs;
+  for (int row = blockIdx.x; row < N * P; row += gridDim.x) {
+    const int n = row / P, ph = row - n * P;
+    const int h0 = ph * stride - pad;
+    const __nv_bfloat16* xn = x + (long long)n * H * W * C;
+    const long long orow = (long long)row * Q * C;
+    for (int it = threadIdx.x; it < per_row; it += blockDim.x) {
+      const int q = it / cvs, cv = it - q * cvs;
+      const int w0 = q * stride - pad;
+      float best[8]; int arg[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; arg[i] = 0; }
-    for (int r = 0; r < k; ++r) {
-      const int h = ph * stride - pad + r;
-      if (h < 0 || h >= H) continue;
-      for (int s = 0; s < k; ++s) {
-        const int w = q * stride - pad + s;
-        if (w < 0 || w >= W) continue;
-        float v[8];
-        load8(x + (((long long)n * H + h) * W + w) * C + cv * VEC, v);
+      for (int i = 0; i < 8; ++i) { best[i] = -INFINITY; arg[i] = 0; }
+      for (int r = 0; r < k; ++r) {
+        const int h = h0 + r;
+        if (h < 0 || h >= H) continue;
+        for (int s = 0; s < k; ++s) {
+          const int w = w0 + s;
+          if (w < 0 || w >= W) continue;
+          float v[8];
+          load8(xn + ((long long)(h * W + w)) * C + cv * VEC, v);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; arg[i] = r * k + s; }
+          for (int i = 0; i < 8; ++i) if (v[i] > best[i]) { best[i] = v[i]; arg[i] = r * k + s; }
+        }
       }
-    }
-    const long long o = (((long long)n * P + ph) * Q + q) * C + cv * VEC;
-    store8(out + o, best);
-    if (argmax) {
-      uint2 packed;
-      packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
-      packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
-      *reinterpret_cast<uint2*>(argmax + o) = packed;
+      const long long o = orow + (long long)q * C + cv * VEC;
+      store8(out + o, best);
+      if (argmax) {
+        uint2 packed;
+        packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+        packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+        *reinterpret_cast<uint2*>(argmax + o) = packed;
+      }
     }
   }
 }
 
-__global__ void maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
+__global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const uint8_t* __restrict__ argmax,
                                    __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C, int P, int Q, int k,
                                    int stride, int pad) {
   // gather form: each input pixel looks at the (<= ceil(k/stride)^2) windows that contain it
-  const long long total = (long long)N * H * W * (C / VEC);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = idx % (C / VEC);
-    long long pix = idx / (C / VEC);
-    const int w = pix % W; pix /= W;
-    const int h = pix % H; const int n = pix / H;
-    float acc[8];
+  const int cvs = C / VEC;
+  const int per_row = W * cvs;
+  for (int row = blockIdx.x; row < N * H; row += gridDim.x) {
+    const int n = row / H, h = row - n * H;
+    const int ph_lo = max(0, (h + pad - k + stride) / stride);
+    const long long obase = (long long)n * P * Q * C;
+    for (int it = threadIdx.x; it < per_row; it += blockDim.x) {
+      const int w = it / cvs, cv = it - w * cvs;
+      const int q_lo = max(0, (w + pad - k + stride) / stride);
+      float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int ph = max(0, (h + pad - k + stride) / stride); ph < P && ph * stride - pad <= h; ++ph) {
-      const int r = h - (ph * stride - pad);
-      if (r < 0 || r >= k) continue;
-      for (int q = max(0, (w + pad - k + stride) / stride); q < Q && q * stride - pad <= w; ++q) {
-        const int s = w - (q * stride - pad);
-        if (s < 0 || s >= k) continue;
-        const long long o = (((long long)n * P + ph) * Q + q) * C + cv * VEC;
-        const uint2 packed = *reinterpret_cast<const uint2*>(argmax + o);
-        float d[8];
-        load8(dout + o, d);
-        const int tap = r * k + s;
+      for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+      for (int ph = ph_lo; ph < P && ph * stride - pad <= h; ++ph) {
+        const int r = h - (ph * stride - pad);
+        if (r < 0 || r >= k) continue;
+        for (int q = q_lo; q < Q && q * stride - pad <= w; ++q) {
+          const int s = w - (q * stride - pad);
+          if (s < 0 || s >= k) continue;
+          const long long o = obase + ((long long)(ph * Q + q)) * C + cv * VEC;
+          const uint2 packed = *reinterpret_cast<const uint2*>(argmax + o);
+          float d[8];
+          load8(dout + o, d);
+          const int tap = r * k + s;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int a = ((i < 4 ? packed.x : packed.y) >> (8 * (i & 3))) & 0xff;
-          if (a == tap) acc[i] += d[i];
+          for (int i = 0; i < 8; ++i) {
+            const int a = ((i < 4 ? packed.x : packed.y) >> (8 * (i & 3))) & 0xff;
+            if (a == tap) acc[i] += d[i];
+          }
         }
       }
+      store8(dx + ((long long)row * W + w) * C + cv * VEC, acc);
     }
-    store8(dx + (((long long)n * H + h) * W + w) * C + cv * VEC, acc);
   }
 }
 
@@ -503,29 +606,34 @@ __global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat1
     store8(out + (long long)n * C + cv * VEC, acc);
   }
 }
+// I = index type: 32-bit whenever the element count allows it (64-bit divisions cost ~100 instructions each)
+template <typename I>
 __global__ void gap_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int N, int HW, int C) {
-  const long long total = (long long)N * HW * (C / VEC);
+  const I cvs = (I)(C / VEC);
+  const I total = (I)N * (I)HW * cvs;
   const float inv = 1.f / HW;
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = idx % (C / VEC);
-    const int n = (idx / (C / VEC)) / HW;
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvs);
+    const int n = (int)((idx / cvs) / (I)HW);
     float v[8];
     load8(dout + (long long)n * C + cv * VEC, v);
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] *= inv;
-    store8(dx + idx * VEC, v);
+    store8(dx + (long long)idx * VEC, v);
   }
 }
 
 // 2x2 / stride-2 average pool (DenseNet transitions, BoTNet stride-2 block).
+template <typename I>
 __global__ void avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int H, int W, int C) {
   const int P = H / 2, Q = W / 2;
-  const long long total = (long long)N * P * Q * (C / VEC);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = idx % (C / VEC);
-    long long pix = idx / (C / VEC);
-    const int q = pix % Q; pix /= Q;
-    const int ph = pix % P; const int n = pix / P;
+  const I cvs = (I)(C / VEC);
+  const I total = (I)N * (I)P * (I)Q * cvs;
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvs);
+    I pix = idx / cvs;
+    const int q = (int)(pix % (I)Q); pix /= (I)Q;
+    const int ph = (int)(pix % (I)P); const int n = (int)(pix / (I)P);
     float acc[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[i] = 0.f;
@@ -538,17 +646,19 @@ __global__ void avgpool2_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bf
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] += 0.25f * v[i];
       }
-    store8(out + idx * VEC, acc);
+    store8(out + (long long)idx * VEC, acc);
   }
 }
+template <typename I>
 __global__ void avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv_bfloat16* __restrict__ dx, int N, int H, int W, int C) {
   const int P = H / 2, Q = W / 2;
-  const long long total = (long long)N * H * W * (C / VEC);
-  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    const int cv = idx % (C / VEC);
-    long long pix = idx / (C / VEC);
-    const int w = pix % W; pix /= W;
-    const int h = pix % H; const int n = pix / H;
+  const I cvs = (I)(C / VEC);
+  const I total = (I)N * (I)H * (I)W * cvs;
+  for (I idx = (I)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (I)gridDim.x * blockDim.x) {
+    const int cv = (int)(idx % cvs);
+    I pix = idx / cvs;
+    const int w = (int)(pix % (I)W); pix /= (I)W;
+    const int h = (int)(pix % (I)H); const int n = (int)(pix / (I)H);
     float v[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = 0.f;
@@ -557,7 +667,7 @@ __global__ void avgpool2_bwd_kernel(const __nv_bfloat16* __restrict__ dout, __nv
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] *= 0.25f;
     }
-    store8(dx + idx * VEC, v);
+    store8(dx + (long long)idx * VEC, v);
   }
 }
 
@@ -692,11 +802,18 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   extern __shared__ float tile[];                    // [C][R][W + 2*pad]
   const int Wp = W + 2 * pad;
   const int n = blockIdx.x / P, ph = blockIdx.x % P;
-  for (int i = threadIdx.x; i < C * R * Wp; i += blockDim.x) {
-    const int wp = i % Wp; const int cr = i / Wp;
-    const int r = cr % R, c = cr / R;
-    const int h = ph * stride - pad + r, w = wp - pad;
-    tile[i] = (h >= 0 && h < H && w >= 0 && w < W) ? __ldg(x + (((long long)n * C + c) * H + h) * W + w) : 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  // one (channel, filter-row) image row per warp iteration: the divisions are per row, not per element
+  for (int cr = warp; cr < C * R; cr += nwarps) {
+    const int c = cr / R, r = cr - c * R;
+    const int h = ph * stride - pad + r;
+    const bool row_ok = (h >= 0 && h < H);
+    const float* src = x + (((long long)n * C + c) * H + (row_ok ? h : 0)) * W;
+    float* dst = tile + cr * Wp;
+    for (int wp = lane; wp < Wp; wp += 32) {
+      const int w = wp - pad;
+      dst[wp] = (row_ok && w >= 0 && w < W) ? __ldg(src + w) : 0.f;
+    }
   }
   // per-k lookup of the tile offset (c, r, s) -> (c*R + r)*Wp + s, built once per CTA (no div/mod in the hot loop)
   __shared__ int koff[256];
@@ -708,8 +825,10 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
   __syncthreads();
   const int vec_per_row = Kpad / 8;
   __nv_bfloat16* out_row = patches + ((long long)n * P + ph) * Q * Kpad;
-  for (int item = threadIdx.x; item < Q * vec_per_row; item += blockDim.x) {
-    const int j8 = item % vec_per_row, q = item / vec_per_row;
+  // (q, j8) advance incrementally by blockDim.x items per iteration
+  int q = threadIdx.x / vec_per_row, j8 = threadIdx.x - q * vec_per_row;
+  const int dq = blockDim.x / vec_per_row, dj = blockDim.x - dq * vec_per_row;
+  while (q < Q) {
     const int base = q * stride;
     float v[8];
 #pragma unroll
@@ -718,6 +837,8 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
       v[i] = o >= 0 ? tile[o + base] : 0.f;
     }
     store8(out_row + (long long)q * Kpad + j8 * 8, v);
+    q += dq; j8 += dj;
+    if (j8 >= vec_per_row) { j8 -= vec_per_row; ++q; }
   }
 }
 
@@ -764,15 +885,24 @@ template <typename Kern>
 static inline cudaError_t allow_big_smem(Kern kern, int bytes) {
   return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
-constexpr int kRingBytes2 = kRing * 2 * kBnThreads * 16;  // 32 KB
-constexpr int kRingBytes3 = kRing * 3 * kBnThreads * 16;  // 48 KB
 
+typedef void (*BnApplyKernel)(BnApplyParams);
+struct FwdPick { BnApplyKernel kern; int smem; };
+template <int ACT, bool RES>
+static FwdPick fwd_pick_one() {
+  static cudaError_t once = allow_big_smem(bn_apply_kernel<ACT, RES>, FwdRing<RES>::kBytes);
+  return FwdPick{once == cudaSuccess ? bn_apply_kernel<ACT, RES> : nullptr, FwdRing<RES>::kBytes};
+}
 extern "C" int b200_bn_apply(const BnApplyParams* p, cudaStream_t s) {
-  static cudaError_t once = allow_big_smem(bn_apply_kernel, kRingBytes2);
-  if (once != cudaSuccess) return (int)once;
+  const bool res = p->residual != nullptr;
+  FwdPick k;
+  if (p->act == ACT_RELU) k = res ? fwd_pick_one<ACT_RELU, true>() : fwd_pick_one<ACT_RELU, false>();
+  else if (p->act == ACT_SILU) k = res ? fwd_pick_one<ACT_SILU, true>() : fwd_pick_one<ACT_SILU, false>();
+  else k = res ? fwd_pick_one<ACT_NONE, true>() : fwd_pick_one<ACT_NONE, false>();
+  if (!k.kern) return (int)cudaErrorInvalidValue;
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
-  bn_apply_kernel<<<g, b, kRingBytes2, s>>>(*p);
+  k.kern<<<g, b, k.smem, s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_stats(const void* y, long long rows, int C, long long ldy, float* stats, cudaStream_t s) {
@@ -781,22 +911,41 @@ extern "C" int b200_bn_stats(const void* y, long long rows, int C, long long ldy
   bn_stats_kernel<<<g, b, b.x * b.y * 16 * sizeof(float), s>>>((const __nv_bfloat16*)y, rows, C, ldy, stats);
   return (int)cudaGetLastError();
 }
+// (activation, how act' is obtained) -> kernel instance
+typedef void (*BnBwdKernel)(BnBwdParams);
+struct BwdPick { BnBwdKernel reduce, apply; int smem; };
+template <int ACT, int MODE>
+static BwdPick bwd_pick_one() {
+  static cudaError_t once_r = allow_big_smem(bn_bwd_reduce_kernel<ACT, MODE>, BwdRing<MODE>::kBytes);
+  static cudaError_t once_a = allow_big_smem(bn_bwd_apply_kernel<ACT, MODE>, BwdRing<MODE>::kBytes);
+  if (once_r != cudaSuccess || once_a != cudaSuccess) return BwdPick{nullptr, nullptr, 0};
+  return BwdPick{bn_bwd_reduce_kernel<ACT, MODE>, bn_bwd_apply_kernel<ACT, MODE>, BwdRing<MODE>::kBytes};
+}
+static BwdPick bwd_pick(const BnBwdParams* p) {
+  if (p->act == ACT_NONE) return bwd_pick_one<ACT_NONE, BWD_PLAIN>();
+  if (p->relu_mask != nullptr && p->act == ACT_RELU) return bwd_pick_one<ACT_RELU, BWD_MASK>();
+  const bool res = p->residual != nullptr;
+  if (p->act == ACT_RELU) return res ? bwd_pick_one<ACT_RELU, BWD_RES>() : bwd_pick_one<ACT_RELU, BWD_PLAIN>();
+  return res ? bwd_pick_one<ACT_SILU, BWD_RES>() : bwd_pick_one<ACT_SILU, BWD_PLAIN>();
+}
 extern "C" int b200_bn_bwd_reduce(const BnBwdParams* p, cudaStream_t s) {
-  static cudaError_t once = allow_big_smem(bn_bwd_reduce_kernel, kRingBytes3);
-  if (once != cudaSuccess) return (int)once;
+  const BwdPick k = bwd_pick(p);
+  if (!k.reduce) return (int)cudaErrorInvalidValue;
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b, 2);   // exactly the resident wave: fewer CTAs = fewer contended atomics at the end
-  bn_bwd_reduce_kernel<<<g, b, kRingBytes3, s>>>(*p);
+  k.reduce<<<g, b, k.smem, s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_bwd_apply(const BnBwdParams* p, cudaStream_t s) {
-  static cudaError_t once = allow_big_smem(bn_bwd_apply_kernel, kRingBytes3);
-  if (once != cudaSuccess) return (int)once;
+  const BwdPick k = bwd_pick(p);
+  if (!k.apply) return (int)cudaErrorInvalidValue;
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
-  bn_bwd_apply_kernel<<<g, b, kRingBytes3, s>>>(*p);
+  k.apply<<<g, b, k.smem, s>>>(*p);
   return (int)cudaGetLastError();
 }
+// 32-bit index arithmetic is safe when the element count plus one grid stride cannot wrap
+static inline bool fits32(long long total) { return total < (1ll << 31); }
 static inline int ew_grid(long long total, int block) {
   long long g = (total + block - 1) / block;
   long long cap = 148 * 16;
@@ -804,15 +953,13 @@ static inline int ew_grid(long long total, int block) {
 }
 extern "C" int b200_maxpool_fwd(const void* x, void* out, void* argmax, int N, int H, int W, int C, int P, int Q, int k,
                                 int stride, int pad, cudaStream_t s) {
-  const long long total = (long long)N * P * Q * (C / VEC);
-  maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, (uint8_t*)argmax,
+  maxpool_fwd_kernel<<<ew_grid((long long)N * P * 256, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, (uint8_t*)argmax,
                                                          N, H, W, C, P, Q, k, stride, pad);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_maxpool_bwd(const void* dout, const void* argmax, void* dx, int N, int H, int W, int C, int P, int Q,
                                 int k, int stride, int pad, cudaStream_t s) {
-  const long long total = (long long)N * H * W * (C / VEC);
-  maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (const uint8_t*)argmax,
+  maxpool_bwd_kernel<<<ew_grid((long long)N * H * 256, 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (const uint8_t*)argmax,
                                                          (__nv_bfloat16*)dx, N, H, W, C, P, Q, k, stride, pad);
   return (int)cudaGetLastError();
 }
@@ -821,17 +968,21 @@ extern "C" int b200_gap_fwd(const void* x, void* out, int N, int HW, int C, cuda
   return (int)cudaGetLastError();
 }
 extern "C" int b200_gap_bwd(const void* dout, void* dx, int N, int HW, int C, cudaStream_t s) {
-  gap_bwd_kernel<<<ew_grid((long long)N * HW * (C / VEC), 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, HW, C);
+  const long long total = (long long)N * HW * (C / VEC);
+  if (fits32(total)) gap_bwd_kernel<unsigned><<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, HW, C);
+  else gap_bwd_kernel<long long><<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, HW, C);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_avgpool2_fwd(const void* x, void* out, int N, int H, int W, int C, cudaStream_t s) {
-  avgpool2_fwd_kernel<<<ew_grid((long long)N * (H / 2) * (W / 2) * (C / VEC), 256), 256, 0, s>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, C);
+  const long long total = (long long)N * (H / 2) * (W / 2) * (C / VEC);
+  if (fits32(total)) avgpool2_fwd_kernel<unsigned><<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, C);
+  else avgpool2_fwd_kernel<long long><<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, H, W, C);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_avgpool2_bwd(const void* dout, void* dx, int N, int H, int W, int C, cudaStream_t s) {
-  avgpool2_bwd_kernel<<<ew_grid((long long)N * H * W * (C / VEC), 256), 256, 0, s>>>(
-      (const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, H, W, C);
+  const long long total = (long long)N * H * W * (C / VEC);
+  if (fits32(total)) avgpool2_bwd_kernel<unsigned><<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, H, W, C);
+  else avgpool2_bwd_kernel<long long><<<ew_grid(total, 256), 256, 0, s>>>((const __nv_bfloat16*)dout, (__nv_bfloat16*)dx, N, H, W, C);
   return (int)cudaGetLastError();
 }
 static inline void scale_dims(int HW, int C, int N, dim3& grid, dim3& block) {

@@ -28,8 +28,9 @@ class ConvBnAct(nn.Module):
         self.bn = nn.BatchNorm2d(cout)
         self.act = act
 
-    def forward(self, x, residual=None, act="__default__"):
-        return Fn.conv_bn_act(x, self.conv, self.bn, self.act if act == "__default__" else act, residual)
+    def forward(self, x, residual=None, act="__default__", residual_sink=None, input_grad_to=None):
+        return Fn.conv_bn_act(x, self.conv, self.bn, self.act if act == "__default__" else act, residual,
+                              residual_sink=residual_sink, input_grad_to=input_grad_to)
 
 
 class SEModule(nn.Module):
@@ -55,10 +56,12 @@ class RegBottleneck(nn.Module):
 
     def forward(self, x):
         shortcut = x if self.downsample is None else self.downsample(x)
-        y = self.conv2(self.conv1(x))
+        # gradient-fusion hints (ops.functional.conv_bn_act): conv1 and the shortcut read the same tensor
+        proj = self.downsample.conv if self.downsample is not None else None
+        y = self.conv2(self.conv1(x, input_grad_to=proj))
         if self.se is not None:
             y = self.se(y)
-        return self.conv3(y, residual=shortcut, act="relu")
+        return self.conv3(y, residual=shortcut, act="relu", residual_sink=self.conv1.conv if proj is None else None)
 
 
 class RegStage(nn.Sequential):

@@ -69,7 +69,9 @@ class BasicBlock(nn.Module):
 
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
-        out = Fn.conv_bn_act(x, self.conv1, self.bn1, "relu")
+        # projection shortcut: its conv read x first, so conv1's input gradient is folded into that conv's dgrad
+        proj = self.downsample[0] if isinstance(self.downsample, _Shortcut) else None
+        out = Fn.conv_bn_act(x, self.conv1, self.bn1, "relu", input_grad_to=proj)
         sink = self.conv1 if self.downsample is None else None   # identity shortcut: conv1 reads the same tensor
         return Fn.conv_bn_act(out, self.conv2, self.bn2, "relu", residual=identity, residual_sink=sink)
 
@@ -94,7 +96,9 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         identity = x if self.downsample is None else self.downsample(x)
-        out = Fn.conv_bn_act(x, self.conv1, self.bn1, "relu")
+        # projection shortcut: its conv read x first, so conv1's input gradient is folded into that conv's dgrad
+        proj = self.downsample[0] if isinstance(self.downsample, _Shortcut) else None
+        out = Fn.conv_bn_act(x, self.conv1, self.bn1, "relu", input_grad_to=proj)
         out = Fn.conv_bn_act(out, self.conv2, self.bn2, "relu")
         sink = self.conv1 if self.downsample is None else None   # identity shortcut: conv1 reads the same tensor
         return Fn.conv_bn_act(out, self.conv3, self.bn3, "relu", residual=identity, residual_sink=sink)

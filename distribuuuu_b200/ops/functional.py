@@ -30,15 +30,18 @@ def _act(x, act):
     raise ValueError(f"unknown activation {act!r}")
 
 
-def conv_bn_act(x, conv: nn.Conv2d, bn: nn.Module | None, act: str | None = None, residual=None, residual_sink=None):
+def conv_bn_act(x, conv: nn.Conv2d, bn: nn.Module | None, act: str | None = None, residual=None, residual_sink=None,
+                input_grad_to=None):
     """``act(bn(conv(x)) + residual)``; ``bn``/``act``/``residual`` optional.
 
     ``residual_sink``: the conv module (of the same block) that consumes the *same tensor* as ``residual``; a hint
-    that lets the native engine fold the residual-branch gradient into that conv's dgrad epilogue.  Ignored on the
-    torch path and whenever the tensors do not actually coincide."""
+    that lets the native engine fold the residual-branch gradient into that conv's dgrad epilogue.
+    ``input_grad_to``: a conv module applied EARLIER in this forward to the *same tensor* ``x`` (a projection
+    shortcut); this conv's input gradient is then handed to that conv's dgrad instead of being summed by a separate
+    kernel.  Both are hints: ignored on the torch path and whenever the tensors do not actually coincide."""
     eng = runtime.active_engine()
     if eng is not None:
-        return eng.ops.conv_bn_act(x, conv, bn, act, residual, residual_sink)
+        return eng.ops.conv_bn_act(x, conv, bn, act, residual, residual_sink, input_grad_to)
     y = conv(x)
     if bn is not None:
         y = bn(y)

@@ -36,13 +36,21 @@ class _GradSink:
     """Mailbox between a BnActFn (producer of a residual-branch gradient) and the ConvFn that consumes the same
     block input: the gradient is added inside that conv's dgrad epilogue instead of by a separate add kernel."""
 
-    __slots__ = ("ptr", "pending")
+    __slots__ = ("ptr", "pending", "consumed")
 
     def __init__(self, ptr):
-        self.ptr, self.pending = ptr, None
+        self.ptr, self.pending, self.consumed = ptr, None, False
+
+    def offer(self, grad) -> bool:
+        """Hand a gradient of the shared input to the sink's conv; False if that conv's backward already ran."""
+        if self.consumed or self.pending is not None:
+            return False
+        self.pending = grad
+        return True
 
     def take(self):
         t, self.pending = self.pending, None
+        self.consumed = True
         return t
 
 
@@ -50,7 +58,7 @@ class ConvFn(torch.autograd.Function):
     """Implicit-GEMM convolution (fprop / dgrad / wgrad on tcgen05), optional BN-statistics epilogue."""
 
     @staticmethod
-    def forward(ctx, x, eng, conv, stats, anchor):
+    def forward(ctx, x, eng, conv, stats, anchor, hand_to=None):
         K = eng.K
         xh = _nhwc(x)
         w = eng.w16_krsc(conv.weight)
@@ -64,9 +72,13 @@ class ConvFn(torch.autograd.Function):
         ctx.eng, ctx.conv = eng, conv
         ctx.save_for_backward(xh)
         ctx.x_needs_grad = x.requires_grad
-        # a later BnActFn whose residual IS this input may hand us its residual gradient (fused into our dgrad)
-        ctx.sink = _GradSink(xh.data_ptr()) if (x.requires_grad and s == 1) else None
+        # Another consumer of this very input (a BnActFn whose residual it is, or a sibling conv of the block) may
+        # hand us its gradient contribution: it is added inside our dgrad instead of by a separate add kernel.
+        fusable = s == 1 or (R == 1 and S == 1 and p == 0)
+        ctx.sink = _GradSink(xh.data_ptr()) if (x.requires_grad and fusable) else None
         eng.last_sink[conv] = ctx.sink
+        # ... and we may hand OUR input gradient to a sibling conv's sink (it must read the same tensor)
+        ctx.hand_to = hand_to if (hand_to is not None and x.requires_grad and hand_to.ptr == xh.data_ptr()) else None
         return _nchw_view(y)
 
     @staticmethod
@@ -80,21 +92,26 @@ class ConvFn(torch.autograd.Function):
         dx = None
         if ctx.x_needs_grad:
             w = eng.w16_krsc(conv.weight)
+            addend = ctx.sink.take() if ctx.sink is not None else None
             if s == 1:
                 dxh = torch.empty_like(xh)
-                addend = ctx.sink.take() if ctx.sink is not None else None
                 K.conv_dgrad(dyh, w, dxh, 1, p, d, addend, conv.groups)
             else:
-                dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d, conv.groups)
-            dx = _nchw_view(dxh)
+                dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d, conv.groups, addend)
+            if ctx.hand_to is not None and ctx.hand_to.offer(dxh):
+                dx = None          # the sibling conv's dgrad adds it; autograd treats None as zero
+            else:
+                dx = _nchw_view(dxh)
         # only now: the bucket's fused update overwrites the bf16 weights the dgrad above still reads
         eng.mark_ready(conv.weight)
-        return dx, None, None, None, None
+        return dx, None, None, None, None, None
 
 
-def _strided_dgrad(K, dyh, w, x_shape, s, p, d, groups=1):
+def _strided_dgrad(K, dyh, w, x_shape, s, p, d, groups=1, addend=None):
     """Data gradient of a strided conv: scatter dy onto a zero-filled stride-1 grid, then run the stride-1
-    tcgen05 dgrad (costs s^2 x the FLOPs of the few strided layers; a parity-decomposed kernel is future work)."""
+    tcgen05 dgrad (costs s^2 x the FLOPs of the few strided layers; a parity-decomposed kernel is future work).
+    ``addend`` (1x1 only): a gradient of the same input from a sibling consumer; it is updated in place at the
+    sampled pixels, which replaces a zero fill, a scatter and a full-size add."""
     N, H, W, C = x_shape
     Kc, R, S, _ = w.shape
     if R == 1 and S == 1 and p == 0:
@@ -102,9 +119,13 @@ def _strided_dgrad(K, dyh, w, x_shape, s, p, d, groups=1):
         Pc, Qc = dyh.shape[1], dyh.shape[2]
         compact = torch.empty((N, Pc, Qc, C), dtype=dyh.dtype, device=dyh.device)
         K.conv_dgrad(dyh, w, compact, 1, 0, 1, None, groups)
+        if addend is not None:
+            addend[:, ::s, ::s, :][:, :Pc, :Qc] += compact
+            return addend
         dxh = torch.zeros((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
         dxh[:, ::s, ::s, :][:, :Pc, :Qc] = compact
         return dxh
+    assert addend is None
     P1 = H + 2 * p - d * (R - 1)
     Q1 = W + 2 * p - d * (S - 1)
     up = torch.zeros((N, P1, Q1, Kc), dtype=dyh.dtype, device=dyh.device)
@@ -437,7 +458,7 @@ class NativeOps:
         return F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
 
     # ---- functional surface ----------------------------------------------------------------------
-    def conv_bn_act(self, x, conv, bn, act, residual, residual_sink=None):
+    def conv_bn_act(self, x, conv, bn, act, residual, residual_sink=None, input_grad_to=None):
         eng = self.eng
         training = bn is not None and bn.training
         slot = eng.fwd_slot(bn) if (training and conv.out_channels % 8 == 0) else None
@@ -445,7 +466,8 @@ class NativeOps:
         if self._is_stem(conv, x):
             y = StemConvFn.apply(x, eng, conv, stats, eng.anchor)
         elif self._native_conv_ok(conv, x):
-            y = ConvFn.apply(x, eng, conv, stats, eng.anchor)
+            hand_to = eng.last_sink.get(input_grad_to) if (input_grad_to is not None and torch.is_grad_enabled()) else None
+            y = ConvFn.apply(x, eng, conv, stats, eng.anchor, hand_to)
         elif self._depthwise_ok(conv, x):
             y = DwConvFn.apply(x, eng, conv, stats, eng.anchor)
         else:
