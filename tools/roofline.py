@@ -58,8 +58,16 @@ def launch_table(path):
             rows.append((row["Kernel Name"], float(row["Metric Value"].replace(",", ""))))
         except Exception:
             pass
-    idx = [i for i, (n, v) in enumerate(rows) if "stem_im2col" in n]
-    step = rows[idx[-1]:] if idx else rows
+    # one step = a stem_im2col launch up to the optimizer kernel that follows it; take the LAST COMPLETE one
+    starts = [i for i, (n, v) in enumerate(rows) if "stem_im2col" in n]
+    ends = [i for i, (n, v) in enumerate(rows) if "sgd_local" in n or "allreduce_sgd" in n]
+    step = rows
+    for k in range(len(starts) - 1, -1, -1):
+        limit = starts[k + 1] if k + 1 < len(starts) else len(rows)
+        inside = [e for e in ends if starts[k] < e < limit]
+        if inside:
+            step = rows[starts[k]:inside[-1] + 1]
+            break
     agg = collections.defaultdict(lambda: [0, 0.0])
     for n, v in step:
         short = re.sub(r"\(.*", "", n)
