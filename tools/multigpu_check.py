@@ -140,9 +140,9 @@ def check_engine(dev, rank, world, arch="resnet18", steps=3, batch=8, size=64):
     # deepcopy keeps flat-view parameters; detach them into ordinary storage for the torch engine
     for p in net_b.parameters():
         p.data = p.data.clone().contiguous()
-    opt = eng.make_optimizer(lr=0.05, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    opt = eng.make_optimizer(lr=0.01, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
     ref = TorchEngine(net_b)
-    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-5, nesterov=True)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-5, nesterov=True)
     eng.train(), ref.train()
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     losses = []
