@@ -37,6 +37,9 @@ def parse_args():
     ap.add_argument("--no-syncbn", action="store_true")
     ap.add_argument("--comm", default="peer", choices=["peer", "nccl"])
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--e2e-input", default="fp32", choices=["fp32", "uint8"],
+                    help="dtype of the pinned host batches of the end-to-end run: fp32 = host-normalised images (what the "
+                         "reference's loader yields); uint8 = raw pixels normalised in the stem kernel (B200.INPUT_UINT8)")
     ap.add_argument("--exposed", action="store_true", help="also time the step with the gradient exchange disabled and report the exposed all-reduce ms/step")
     return ap.parse_args()
 
@@ -204,7 +207,10 @@ def run_ours(args):
         # the user-facing path: pinned host batches -> utils.PinnedPrefetcher (H2D of batch i+1 on a side stream while
         # step i computes, exactly what trainer.train_epoch does) -> engine.train_step -> loss read back every step
         from distribuuuu_b200 import utils as b200_utils
-        hx = [torch.randn(B, 3, 224, 224).pin_memory() for _ in range(nbuf)]
+        if args.e2e_input == "uint8":
+            hx = [torch.randint(0, 256, (B, 3, 224, 224), dtype=torch.uint8).pin_memory() for _ in range(nbuf)]
+        else:
+            hx = [torch.randn(B, 3, 224, 224).pin_memory() for _ in range(nbuf)]
         hy = [torch.randint(0, 1000, (B,)).pin_memory() for _ in range(nbuf)]
         sink = []
 
@@ -227,8 +233,8 @@ def run_ours(args):
         dist.barrier()
         sec_e2e = float(ms.item()) / 1e3
         e2e = {"value": world * B * args.steps / sec_e2e, "unit": "images/sec",
-               "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8, "d2h_bytes_per_step": 4,
-               "ms_per_step": sec_e2e * 1e3 / args.steps, "last_loss": sink[-1] if sink else None}
+               "h2d_bytes_per_step": hx[0].numel() * hx[0].element_size() + B * 8, "d2h_bytes_per_step": 4,
+               "input": args.e2e_input, "ms_per_step": sec_e2e * 1e3 / args.steps, "last_loss": sink[-1] if sink else None}
     if rank == 0:
         out = {"metric": "ResNet-50 training images/sec (whole job, device-timed, max over ranks)", "impl": "ours",
                "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

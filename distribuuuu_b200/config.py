@@ -251,6 +251,8 @@ _C.B200.BUCKET_MB = 25
 _C.B200.DUMMY_LEN = 1000
 # generate dummy batches on the device instead of a host tensor + H2D copy
 _C.B200.DUMMY_ON_DEVICE = False
+# keep images uint8 through the loader and the H2D copy; normalise on the GPU (native engine: in the stem kernel)
+_C.B200.INPUT_UINT8 = False
 # read metrics back to the host every N iterations (reference: every iteration)
 _C.B200.METRIC_SYNC_FREQ = 1
 # capture per-phase CUDA-event timings

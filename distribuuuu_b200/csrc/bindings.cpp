@@ -6,6 +6,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <torch/extension.h>
+#include <vector>
 
 #include <mutex>
 #include <unordered_map>
@@ -550,11 +551,21 @@ void nchw_to_nhwc(const at::Tensor& x, at::Tensor& out) {
   TORCH_CHECK(x.scalar_type() == at::kFloat && x.is_contiguous() && out.scalar_type() == at::kBFloat16, "nchw_to_nhwc: fp32 -> bf16");
   B200_CUDA_OK(b200_nchw_to_nhwc(x.data_ptr<float>(), out.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), cur_stream()));
 }
-void stem_im2col(const at::Tensor& x, at::Tensor& patches, int64_t R, int64_t S, int64_t stride, int64_t pad, int64_t P, int64_t Q) {
+void stem_im2col(const at::Tensor& x, at::Tensor& patches, int64_t R, int64_t S, int64_t stride, int64_t pad, int64_t P, int64_t Q,
+                 const std::vector<double>& mean, const std::vector<double>& std_) {
+  // x: NCHW fp32 (already normalised) or NCHW uint8 (raw pixels, normalised here with mean/std given in [0,1] units)
   c10::cuda::CUDAGuard guard(x.device());
-  TORCH_CHECK(x.scalar_type() == at::kFloat && x.is_contiguous() && patches.scalar_type() == at::kBFloat16 && patches.is_contiguous(), "stem_im2col dtypes");
-  B200_CUDA_OK(b200_stem_im2col(x.data_ptr<float>(), patches.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), P, Q, R, S,
-                                stride, pad, patches.size(-1), cur_stream()));
+  const bool u8 = x.scalar_type() == at::kByte;
+  TORCH_CHECK((u8 || x.scalar_type() == at::kFloat) && x.is_contiguous() && patches.scalar_type() == at::kBFloat16 && patches.is_contiguous(),
+              "stem_im2col dtypes");
+  StemNorm norm{};
+  for (int c = 0; c < 8; ++c) { norm.scale[c] = 1.f; norm.bias[c] = 0.f; }
+  if (u8) {
+    TORCH_CHECK((int64_t)mean.size() == x.size(1) && (int64_t)std_.size() == x.size(1), "stem_im2col: uint8 input needs per-channel mean/std");
+    for (size_t c = 0; c < mean.size() && c < 8; ++c) { norm.scale[c] = (float)(1.0 / (255.0 * std_[c])); norm.bias[c] = (float)(-mean[c] / std_[c]); }
+  }
+  B200_CUDA_OK(b200_stem_im2col(x.data_ptr(), u8 ? 1 : 0, patches.data_ptr(), x.size(0), x.size(1), x.size(2), x.size(3), P, Q, R, S,
+                                stride, pad, patches.size(-1), &norm, cur_stream()));
 }
 void pad_rows(const at::Tensor& src, at::Tensor& dst, int64_t rows, int64_t cols, int64_t cols_pad) {
   c10::cuda::CUDAGuard guard(src.device());
@@ -671,7 +682,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("channel_scale_bwd", &channel_scale_bwd);
   m.def("ce_topk", &ce_topk);
   m.def("nchw_to_nhwc", &nchw_to_nhwc);
-  m.def("stem_im2col", &stem_im2col);
+  m.def("stem_im2col", &stem_im2col, py::arg("x"), py::arg("patches"), py::arg("R"), py::arg("S"), py::arg("stride"), py::arg("pad"),
+        py::arg("P"), py::arg("Q"), py::arg("mean") = std::vector<double>{}, py::arg("std") = std::vector<double>{});
   m.def("pad_rows", &pad_rows);
   m.def("unpad_add", &unpad_add);
   m.def("sgd_local", &sgd_local);

@@ -794,8 +794,12 @@ __global__ void nchw_to_nhwc_bf16_kernel(const float* __restrict__ x, __nv_bfloa
   }
 }
 
-__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ x /*NCHW fp32*/, __nv_bfloat16* __restrict__ patches,
-                                   int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad) {
+// T = float (already normalised images) or uint8_t (raw pixels: v * scale[c] + bias[c] is applied while the rows are
+// staged, so real-data batches cross PCIe as bytes and are never materialised in fp32 -- SURVEY G18).
+template <typename T>
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const T* __restrict__ x /*NCHW*/, __nv_bfloat16* __restrict__ patches,
+                                   int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad,
+                                   StemNorm norm) {
   // One CTA per output row (n, p): the R input rows it needs are staged in shared memory once (coalesced reads of the
   // NCHW image, zero-filled borders), then every thread emits 16-byte patch pieces (row layout [r][s][c] + zero
   // padding to Kpad, matching weights [Cout][R][S][C]) with fully coalesced stores.
@@ -808,11 +812,14 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
     const int c = cr / R, r = cr - c * R;
     const int h = ph * stride - pad + r;
     const bool row_ok = (h >= 0 && h < H);
-    const float* src = x + (((long long)n * C + c) * H + (row_ok ? h : 0)) * W;
+    const T* src = x + (((long long)n * C + c) * H + (row_ok ? h : 0)) * W;
     float* dst = tile + cr * Wp;
+    const float sc = norm.scale[c & 7], bi = norm.bias[c & 7];
     for (int wp = lane; wp < Wp; wp += 32) {
       const int w = wp - pad;
-      dst[wp] = (row_ok && w >= 0 && w < W) ? __ldg(src + w) : 0.f;
+      float v = 0.f;   // zero padding lives in the normalised domain, as in Normalize -> Conv2d(padding)
+      if (row_ok && w >= 0 && w < W) v = sizeof(T) == 1 ? fmaf((float)__ldg(src + w), sc, bi) : (float)__ldg(src + w);
+      dst[wp] = v;
     }
   }
   // per-k lookup of the tile offset (c, r, s) -> (c*R + r)*Wp + s, built once per CTA (no div/mod in the hot loop)
@@ -1018,10 +1025,14 @@ extern "C" int b200_nchw_to_nhwc(const float* x, void* out, int N, int C, int H,
   nchw_to_nhwc_bf16_kernel<<<ew_grid((long long)N * C * H * W, 256), 256, 0, s>>>(x, (__nv_bfloat16*)out, N, C, H, W);
   return (int)cudaGetLastError();
 }
-extern "C" int b200_stem_im2col(const float* x, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S,
-                                int stride, int pad, int Kpad, cudaStream_t s) {
-  if (Kpad > 256) return (int)cudaErrorInvalidValue;
-  stem_im2col_kernel<<<N * P, 256, (size_t)C * R * (W + 2 * pad) * sizeof(float), s>>>(x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad);
+extern "C" int b200_stem_im2col(const void* x, int x_is_u8, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S,
+                                int stride, int pad, int Kpad, const StemNorm* norm, cudaStream_t s) {
+  if (Kpad > 256 || C > 8) return (int)cudaErrorInvalidValue;
+  const size_t smem = (size_t)C * R * (W + 2 * pad) * sizeof(float);
+  if (x_is_u8)
+    stem_im2col_kernel<uint8_t><<<N * P, 256, smem, s>>>((const uint8_t*)x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad, *norm);
+  else
+    stem_im2col_kernel<float><<<N * P, 256, smem, s>>>((const float*)x, (__nv_bfloat16*)patches, N, C, H, W, P, Q, R, S, stride, pad, Kpad, *norm);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_pad_rows(const void* src, void* dst, int rows, int cols, int cols_pad, cudaStream_t s) {

@@ -20,6 +20,9 @@ struct PeerCtx {
   int* ticket;                      // [2] local ints: arrival ticket / departure counter
 };
 
+// per-channel affine applied to raw uint8 pixels by the stem im2col: v * scale[c] + bias[c]  (= (v/255 - mean) / std)
+struct StemNorm { float scale[8]; float bias[8]; };
+
 struct BnApplyParams {
   const __nv_bfloat16* y; long long ldy;        // conv output [rows][C]
   const __nv_bfloat16* residual; long long ldr; // optional
@@ -71,7 +74,7 @@ int b200_channel_scale_fwd(const void* x, const void* gate, void* out, int N, in
 int b200_channel_scale_bwd(const void* dout, const void* x, const void* gate, void* dx, float* dgate, int N, int HW, int C, cudaStream_t s);
 int b200_ce_topk(const void* logits, const long long* target, void* dlogits, float* accum, int rows, int ncls, long long ld, int topk, float grad_scale, cudaStream_t s);
 int b200_nchw_to_nhwc(const float* x, void* out, int N, int C, int H, int W, cudaStream_t s);
-int b200_stem_im2col(const float* x, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad, cudaStream_t s);
+int b200_stem_im2col(const void* x, int x_is_u8, void* patches, int N, int C, int H, int W, int P, int Q, int R, int S, int stride, int pad, int Kpad, const StemNorm* norm, cudaStream_t s);
 int b200_pad_rows(const void* src, void* dst, int rows, int cols, int cols_pad, cudaStream_t s);
 int b200_unpad_add(const float* src, float* dst, int rows, int cols, int cols_pad, cudaStream_t s);
 }

@@ -171,8 +171,10 @@ class DwConvFn(torch.autograd.Function):
 
 
 class StemConvFn(torch.autograd.Function):
-    """7x7/2 stem on the raw NCHW fp32 batch: explicit im2col to [pixels, 160] bf16 (K = 147 padded), then the
-    tcgen05 GEMM; wgrad is the same GEMM transposed.  The input needs no gradient."""
+    """7x7/2 stem on the raw NCHW batch: explicit im2col to [pixels, 160] bf16 (K = 147 padded), then the
+    tcgen05 GEMM; wgrad is the same GEMM transposed.  The input needs no gradient.  The batch is either fp32
+    (already normalised, as the reference's loader produces, utils.py:127-135) or uint8 pixels, which the im2col
+    kernel normalises with ``eng.input_mean/std`` while staging them."""
 
     @staticmethod
     def forward(ctx, x_nchw_f32, eng, conv, stats, anchor):
@@ -185,7 +187,10 @@ class StemConvFn(torch.autograd.Function):
         kdim = R * S * C
         kpad = (kdim + 15) // 16 * 16
         patches = torch.empty((N * P * Q, 1, 1, kpad), dtype=torch.bfloat16, device=x_nchw_f32.device)
-        K.stem_im2col(x_nchw_f32.contiguous(), patches, R, S, s, p, P, Q)
+        if x_nchw_f32.dtype == torch.uint8:
+            K.stem_im2col(x_nchw_f32.contiguous(), patches, R, S, s, p, P, Q, list(eng.input_mean), list(eng.input_std))
+        else:
+            K.stem_im2col(x_nchw_f32.contiguous(), patches, R, S, s, p, P, Q)
         wpad = eng.scratch("stem_w", (Kc, 1, 1, kpad), torch.bfloat16)
         K.pad_rows(eng.w16_krsc(conv.weight), wpad, Kc, kdim, kpad)
         y = torch.empty((N * P * Q, 1, 1, Kc), dtype=torch.bfloat16, device=x_nchw_f32.device)
@@ -439,13 +444,16 @@ class NativeOps:
 
     @staticmethod
     def _is_stem(conv: nn.Conv2d, x) -> bool:
-        return (conv.in_channels < 8 and conv.groups == 1 and conv.bias is None and x.dtype == torch.float32
+        return (conv.in_channels < 8 and conv.groups == 1 and conv.bias is None and x.dtype in (torch.float32, torch.uint8)
                 and conv.out_channels % 8 == 0 and conv.dilation[0] == 1)
 
     def _as_act(self, x):
         """Bring an arbitrary input (fp32 NCHW batch) onto the activation convention."""
         if x.dtype == torch.bfloat16:
             return x
+        if x.dtype == torch.uint8:   # raw pixels reaching a non-stem op: normalise with ATen (rare path)
+            from ..utils.data import normalize_uint8
+            x = normalize_uint8(x, self.eng.input_mean, self.eng.input_std)
         N, C, H, W = x.shape
         out = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=x.device)
         self.eng.K.nchw_to_nhwc(x.contiguous(), out)

@@ -128,6 +128,9 @@ class NativeEngine(nn.Module):
         self.comm_stream = torch.cuda.Stream(device)
         # autograd anchor: lets Functions whose tensor inputs carry no grad (first layer) still get a backward call
         self.anchor = torch.zeros((), device=device, requires_grad=True)
+        # normalisation applied to uint8 image batches inside the stem kernel (B200.INPUT_UINT8); [0,1] units
+        from ..utils.data import IMAGENET_MEAN, IMAGENET_STD
+        self.input_mean, self.input_std = tuple(IMAGENET_MEAN), tuple(IMAGENET_STD)
         self._build_flat_storage()
         self._build_bn_slots()
         self._setup_comm()

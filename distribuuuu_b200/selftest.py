@@ -330,7 +330,37 @@ def check_stem():
     out = torch.empty((2, 32, 32, 3), dtype=torch.bfloat16, device="cuda")
     Kmod.nchw_to_nhwc(x, out)
     assert _rel_err(out, x.permute(0, 2, 3, 1).to(torch.bfloat16)) < 1e-6
-    return {"im2col": e}
+    # uint8 pixels, normalised inside the kernel (B200.INPUT_UINT8): same patches as fp32 Normalize + im2col
+    from .utils.data import IMAGENET_MEAN, IMAGENET_STD, normalize_uint8
+    xu = torch.randint(0, 256, (2, 3, 32, 32), device="cuda", dtype=torch.uint8)
+    pu = torch.empty_like(patches)
+    Kmod.stem_im2col(xu, pu, 7, 7, 2, 3, P, Q, list(IMAGENET_MEAN), list(IMAGENET_STD))
+    refu = F.unfold(normalize_uint8(xu), 7, padding=3, stride=2)
+    refu = refu.view(2, 3, 49, P * Q).permute(0, 3, 2, 1).reshape(2 * P * Q, 147)
+    torch.cuda.synchronize()
+    eu = _rel_err(pu.view(-1, 160)[:, :147], refu)
+    assert eu < 1e-2 and float(pu.view(-1, 160)[:, 147:].float().abs().max()) == 0.0, eu
+    return {"im2col": e, "im2col_uint8": eu}
+
+
+def check_uint8_input(arch="resnet18", batch=8, size=64):
+    """The engine fed raw uint8 pixels gives the logits of the same engine fed the host-normalised fp32 batch."""
+    from . import models
+    from .parallel.native_engine import NativeEngine
+    from .utils.data import normalize_uint8
+    dev = torch.device("cuda", torch.cuda.current_device())
+    torch.manual_seed(3)
+    eng = NativeEngine(models.build_model(arch, num_classes=16).to(dev), dev)
+    eng.eval()
+    xu = torch.randint(0, 256, (batch, 3, size, size), device=dev, dtype=torch.uint8)
+    y = torch.randint(0, 16, (batch,), device=dev)
+    with torch.no_grad():
+        la, _, _ = eng.eval_step(xu, y, 5)
+        lb, _, _ = eng.eval_step(normalize_uint8(xu), y, 5)
+    torch.cuda.synchronize()
+    d = abs(float(la) - float(lb)) / max(abs(float(lb)), 1e-3)
+    assert d < 2e-2, f"uint8 vs fp32 input: loss {float(la)} vs {float(lb)}"
+    return {"loss_uint8": float(la), "loss_fp32": float(lb), "rel": d}
 
 
 # ---------------------------------------------------------------------------------------------- end to end

@@ -37,8 +37,13 @@ class TorchEngine(BucketedDataParallel):
     """Reference-semantics step: forward, CE, zero_grad, backward (+bucketed all-reduce),
     optimizer.step -- the sequence at reference trainer.py:42-47."""
 
+    @staticmethod
+    def _prep(inputs):
+        # B200.INPUT_UINT8 batches: ToTensor + Normalize happen here instead of in the loader workers
+        return utils.normalize_uint8(inputs) if inputs.dtype == torch.uint8 else inputs
+
     def train_step(self, inputs, targets, optimizer, topk: int):
-        outputs = self(inputs)
+        outputs = self(self._prep(inputs))
         loss, hits1, hitsk = Fn.cross_entropy_topk(outputs, targets, topk)
         optimizer.zero_grad(set_to_none=True)
         loss.backward()
@@ -48,7 +53,7 @@ class TorchEngine(BucketedDataParallel):
 
     @torch.no_grad()
     def eval_step(self, inputs, targets, topk: int):
-        outputs = self(inputs)
+        outputs = self(self._prep(inputs))
         return Fn.cross_entropy_topk(outputs, targets, topk)
 
 

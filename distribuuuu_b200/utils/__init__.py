@@ -1,8 +1,8 @@
 """Runtime utilities (reference ``distribuuuu/utils.py`` surface, split by concern)."""
 from .checkpoint import (count_parameters, get_checkpoint, get_checkpoint_dir, get_last_checkpoint,
                          has_checkpoint, load_checkpoint, save_checkpoint, unwrap_model)
-from .data import (DummyDataset, PinnedPrefetcher, SyntheticDeviceLoader, construct_train_loader,
-                   construct_val_loader)
+from .data import (IMAGENET_MEAN, IMAGENET_STD, DummyDataset, PinnedPrefetcher, SyntheticDeviceLoader, construct_train_loader,
+                   construct_val_loader, normalize_uint8)
 from .dist import (barrier, broadcast_object, get_rank, get_world_size, is_primary, resolve_backend,
                    resolve_device, scaled_all_reduce, setup_distributed, shutdown)
 from .env import setup_logger, setup_seed

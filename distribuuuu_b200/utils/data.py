@@ -5,7 +5,8 @@ ImageFolder train pipeline (RandomResizedCrop(IM_SIZE) / HFlip / ToTensor / Norm
 DistributedSampler(shuffle), drop_last) and val pipeline (Resize(TEST.IM_SIZE) /
 CenterCrop(224) / ..., padded DistributedSampler, keep last).
 
-New: ``SyntheticDeviceLoader`` generates ImageNet-shaped batches directly on the GPU
+New: ``B200.INPUT_UINT8`` keeps images as uint8 through the loader and the H2D copy (4x fewer bytes) and lets the
+GPU normalise them (native engine: inside the stem im2col kernel); ``SyntheticDeviceLoader`` generates ImageNet-shaped batches directly on the GPU
 (no 602 MB host tensor, no zero-iteration corner when ranks x batch > 1000)
 and ``PinnedPrefetcher`` overlaps the H2D copy of batch i+1 with step i.
 """
@@ -24,13 +25,26 @@ IMAGENET_MEAN = (0.485, 0.456, 0.406)
 IMAGENET_STD = (0.229, 0.224, 0.225)
 
 
-class DummyDataset(Dataset):
-    """``length`` random images of shape ``size``; every label is 0."""
+def normalize_uint8(x: torch.Tensor, mean=IMAGENET_MEAN, std=IMAGENET_STD) -> torch.Tensor:
+    """``(x / 255 - mean) / std`` for a uint8 NCHW batch (what ``ToTensor`` + ``Normalize`` do on the host in the
+    reference, utils.py:127-135).  The native engine does this inside its stem kernel instead; this is the
+    ATen version used by the torch engine and by tests."""
+    m = torch.tensor(mean, dtype=torch.float32, device=x.device).view(1, -1, 1, 1)
+    s = torch.tensor(std, dtype=torch.float32, device=x.device).view(1, -1, 1, 1)
+    return (x.float() / 255.0 - m) / s
 
-    def __init__(self, length: int, size):
+
+class DummyDataset(Dataset):
+    """``length`` random images of shape ``size``; every label is 0.  ``uint8=True`` yields raw-pixel images
+    (for ``B200.INPUT_UINT8``)."""
+
+    def __init__(self, length: int, size, uint8: bool = False):
         self.len = int(length)
         gen = torch.Generator().manual_seed(0)
-        self.data = torch.randn([self.len] + list(size), generator=gen)
+        if uint8:
+            self.data = torch.randint(0, 256, [self.len] + list(size), generator=gen, dtype=torch.uint8)
+        else:
+            self.data = torch.randn([self.len] + list(size), generator=gen)
 
     def __getitem__(self, index):
         return self.data[index], 0
@@ -65,8 +79,12 @@ class SyntheticDeviceLoader:
 
     def __iter__(self):
         for _ in range(self.iters):
-            x = torch.randn(self.batch_size, 3, self.im_size, self.im_size, device=self.device,
-                            dtype=self.dtype, generator=self.gen)
+            if self.dtype == torch.uint8:
+                x = torch.randint(0, 256, (self.batch_size, 3, self.im_size, self.im_size), device=self.device,
+                                  dtype=torch.uint8, generator=self.gen)
+            else:
+                x = torch.randn(self.batch_size, 3, self.im_size, self.im_size, device=self.device,
+                                dtype=self.dtype, generator=self.gen)
             y = torch.randint(0, self.num_classes, (self.batch_size,), device=self.device, generator=self.gen)
             yield x, y
 
@@ -126,17 +144,28 @@ def _use_device_synthetic() -> bool:
     return bool(cfg.MODEL.DUMMY_INPUT and cfg.B200.DUMMY_ON_DEVICE)
 
 
+def _tail_transforms(T):
+    """Last stage of the image pipeline: the reference's ToTensor + Normalize (fp32, 12 bytes/pixel), or -- with
+    ``B200.INPUT_UINT8`` -- the raw uint8 CHW tensor (3 bytes/pixel over PCIe; normalised on the GPU)."""
+    if cfg.B200.INPUT_UINT8:
+        return [T.PILToTensor()]
+    return [T.ToTensor(), T.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)]
+
+
+def _input_dtype():
+    return torch.uint8 if cfg.B200.INPUT_UINT8 else torch.float32
+
+
 def construct_train_loader(device: torch.device | None = None):
     if _use_device_synthetic() and device is not None:
         return SyntheticDeviceLoader(cfg.TRAIN.BATCH_SIZE, cfg.TRAIN.IM_SIZE, cfg.MODEL.NUM_CLASSES,
-                                     cfg.B200.DUMMY_LEN, device, drop_last=True)
+                                     cfg.B200.DUMMY_LEN, device, drop_last=True, dtype=_input_dtype())
     if cfg.MODEL.DUMMY_INPUT:
-        trainset = DummyDataset(cfg.B200.DUMMY_LEN, [3, cfg.TRAIN.IM_SIZE, cfg.TRAIN.IM_SIZE])
+        trainset = DummyDataset(cfg.B200.DUMMY_LEN, [3, cfg.TRAIN.IM_SIZE, cfg.TRAIN.IM_SIZE], uint8=cfg.B200.INPUT_UINT8)
     else:
         T = _transforms()
         trainset = _image_folder(os.path.join(cfg.TRAIN.DATASET, cfg.TRAIN.SPLIT), T.Compose([
-            T.RandomResizedCrop(cfg.TRAIN.IM_SIZE), T.RandomHorizontalFlip(), T.ToTensor(),
-            T.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)]))
+            T.RandomResizedCrop(cfg.TRAIN.IM_SIZE), T.RandomHorizontalFlip()] + _tail_transforms(T)))
     sampler = DistributedSampler(trainset, num_replicas=get_world_size(), rank=get_rank(), shuffle=True)
     return DataLoader(trainset, batch_size=cfg.TRAIN.BATCH_SIZE, num_workers=cfg.TRAIN.WORKERS,
                       pin_memory=cfg.TRAIN.PIN_MEMORY and torch.cuda.is_available(),
@@ -146,15 +175,14 @@ def construct_train_loader(device: torch.device | None = None):
 def construct_val_loader(device: torch.device | None = None):
     if _use_device_synthetic() and device is not None:
         return SyntheticDeviceLoader(cfg.TEST.BATCH_SIZE, 224, cfg.MODEL.NUM_CLASSES,
-                                     cfg.B200.DUMMY_LEN, device, drop_last=False)
+                                     cfg.B200.DUMMY_LEN, device, drop_last=False, dtype=_input_dtype())
     if cfg.MODEL.DUMMY_INPUT:
-        valset = DummyDataset(cfg.B200.DUMMY_LEN, [3, 224, 224])
+        valset = DummyDataset(cfg.B200.DUMMY_LEN, [3, 224, 224], uint8=cfg.B200.INPUT_UINT8)
     else:
         T = _transforms()
         # the reference reads the val split under TRAIN.DATASET (utils.py:157); kept.
         valset = _image_folder(os.path.join(cfg.TRAIN.DATASET, cfg.TEST.SPLIT), T.Compose([
-            T.Resize(cfg.TEST.IM_SIZE), T.CenterCrop(224), T.ToTensor(),
-            T.Normalize(mean=IMAGENET_MEAN, std=IMAGENET_STD)]))
+            T.Resize(cfg.TEST.IM_SIZE), T.CenterCrop(224)] + _tail_transforms(T)))
     sampler = DistributedSampler(valset, num_replicas=get_world_size(), rank=get_rank(), shuffle=False)
     return DataLoader(valset, batch_size=cfg.TEST.BATCH_SIZE, shuffle=False, sampler=sampler,
                       num_workers=cfg.TRAIN.WORKERS, pin_memory=cfg.TRAIN.PIN_MEMORY and torch.cuda.is_available(),

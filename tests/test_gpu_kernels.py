@@ -66,6 +66,11 @@ def test_fused_sgd_matches_torch_optim():
     selftest.check_sgd()
 
 
+def test_engine_accepts_uint8_batches():
+    from distribuuuu_b200 import selftest
+    selftest.check_uint8_input()
+
+
 def test_stem_im2col_and_layout_conversion():
     from distribuuuu_b200 import selftest
     selftest.check_stem()

@@ -125,3 +125,30 @@ def test_dummy_dataset_and_loaders(fresh_cfg):
     assert x.shape == (16, 3, 32, 32) and int(y.sum()) == 0
     pf = utils.PinnedPrefetcher(tl, torch.device("cpu"))
     assert sum(1 for _ in pf) == 2
+
+
+def test_uint8_input_pipeline(fresh_cfg):
+    """B200.INPUT_UINT8: loaders hand out raw uint8 pixels; the torch engine normalises them like ToTensor+Normalize."""
+    from distribuuuu_b200 import models
+    from distribuuuu_b200.trainer import TorchEngine
+    fresh_cfg.MODEL.DUMMY_INPUT = True
+    fresh_cfg.B200.INPUT_UINT8 = True
+    fresh_cfg.B200.DUMMY_LEN = 16
+    fresh_cfg.TRAIN.BATCH_SIZE, fresh_cfg.TEST.BATCH_SIZE, fresh_cfg.TRAIN.WORKERS = 8, 8, 0
+    fresh_cfg.TRAIN.IM_SIZE = 32
+    x, y = next(iter(utils.construct_train_loader()))
+    assert x.dtype == torch.uint8 and x.shape == (8, 3, 32, 32)
+    want = (x.float() / 255.0 - torch.tensor(utils.IMAGENET_MEAN).view(1, 3, 1, 1)) / torch.tensor(utils.IMAGENET_STD).view(1, 3, 1, 1)
+    assert torch.allclose(utils.normalize_uint8(x), want, atol=1e-6)
+    torch.manual_seed(0)
+    eng = TorchEngine(models.build_model("resnet18", num_classes=10))
+    eng.eval()
+    t = torch.zeros(8, dtype=torch.long)
+    la, _, _ = eng.eval_step(x, t, 5)
+    lb, _, _ = eng.eval_step(want, t, 5)
+    assert abs(float(la) - float(lb)) < 1e-5
+    # the image-folder tail keeps PIL -> uint8 CHW without Normalize
+    import torchvision.transforms as T
+    from distribuuuu_b200.utils import data as D
+    tail = D._tail_transforms(T)
+    assert len(tail) == 1 and isinstance(tail[0], T.PILToTensor)

@@ -29,6 +29,7 @@ def registry():
         "ce_topk": st.check_ce_topk,
         "sgd": st.check_sgd,
         "stem": st.check_stem,
+        "uint8_input": st.check_uint8_input,
         "channel_scale": st.check_channel_scale,
         "grouped_regnety": lambda: st.check_grouped_conv(C=224, K=224, G=2),
         "grouped_regnetx_s2": lambda: st.check_grouped_conv(C=512, K=512, G=4, stride=2, H=28, W=28),
