@@ -89,45 +89,95 @@ class SyntheticDeviceLoader:
             yield x, y
 
 
+_SIDE_STREAMS: dict = {}
+
+
+def _side_stream(device: torch.device):
+    """One copy stream per device for the whole process (a fresh stream per loader would also mean a fresh, cold
+    caching-allocator pool per epoch)."""
+    if device.type != "cuda":
+        return None
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream(device)
+    return _SIDE_STREAMS[key]
+
+
 class PinnedPrefetcher:
     """Wraps a host loader: copies batch i+1 to the device on a side stream while the
     caller computes on batch i (replaces the blocking ``inputs.cuda()`` at reference
-    trainer.py:40)."""
+    trainer.py:40).
+
+    Batches land in two persistent device staging slots owned by the prefetcher, so the steady state performs no
+    allocation at all: slot k is overwritten (on the copy stream) only after an event recorded on the compute
+    stream once the step that consumed it has been enqueued.  The yielded tensors are views of those slots and
+    are valid until the batch after next is requested -- i.e. for the whole training/eval step."""
+
+    SLOTS = 2
 
     def __init__(self, loader, device: torch.device):
         self.loader, self.device = loader, device
         self.sampler = getattr(loader, "sampler", _NoopSampler())
-        self.stream = torch.cuda.Stream(device) if device.type == "cuda" else None
+        self.stream = _side_stream(device)
+        self._bufs: dict = {}
+        self._free = [None] * self.SLOTS
 
     def __len__(self):
         return len(self.loader)
 
-    def _stage(self, batch):
+    def _slot(self, k: int, name: str, like: torch.Tensor) -> torch.Tensor:
+        buf = self._bufs.get((k, name))
+        if (buf is None or buf.dtype != like.dtype or buf.shape[1:] != like.shape[1:] or buf.shape[0] < like.shape[0]):
+            buf = torch.empty(like.shape, dtype=like.dtype, device=self.device)   # compute-stream pool, allocated once
+            self._bufs[(k, name)] = buf
+        return buf[: like.shape[0]]
+
+    def _stage(self, batch, k: int):
         x, y = batch
         if not torch.is_tensor(y):
             y = torch.as_tensor(y)
         if self.stream is None:
-            return x.to(self.device), y.to(self.device)
+            return x.to(self.device), y.to(self.device), None
+        bx, by = self._slot(k, "x", x), self._slot(k, "y", y)
         with torch.cuda.stream(self.stream):
-            return x.to(self.device, non_blocking=True), y.to(self.device, non_blocking=True)
+            if self._free[k] is not None:
+                self.stream.wait_event(self._free[k])       # the step that read this slot has been enqueued and finished
+            else:
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))  # first use: order after the allocation
+            bx.copy_(x, non_blocking=True)
+            by.copy_(y, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        return bx, by, done
 
     def __iter__(self):
         it = iter(self.loader)
+        k = 0
         try:
-            nxt = self._stage(next(it))
+            nxt = self._stage(next(it), k)
         except StopIteration:
             return
-        while nxt is not None:
-            if self.stream is not None:
-                torch.cuda.current_stream(self.device).wait_stream(self.stream)
-                for t in nxt:
-                    t.record_stream(torch.cuda.current_stream(self.device))
-            cur = nxt
-            try:
-                nxt = self._stage(next(it))
-            except StopIteration:
-                nxt = None
-            yield cur
+        try:
+            while nxt is not None:
+                x, y, done = nxt
+                cur_k = k
+                if done is not None:
+                    torch.cuda.current_stream(self.device).wait_event(done)
+                k = (k + 1) % self.SLOTS
+                try:
+                    nxt = self._stage(next(it), k)
+                except StopIteration:
+                    nxt = None
+                yield x, y
+                if self.stream is not None:   # the consumer has enqueued its step: after it, slot cur_k may be overwritten
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream(self.device))
+                    self._free[cur_k] = ev
+        finally:
+            # consumer stopped early: order the compute stream after the copy that is still in flight, so the slot
+            # can never be recycled underneath it
+            if nxt is not None and nxt[2] is not None:
+                torch.cuda.current_stream(self.device).wait_event(nxt[2])
 
 
 def _transforms():
