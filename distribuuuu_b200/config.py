@@ -259,6 +259,11 @@ _C.B200.METRIC_SYNC_FREQ = 1
 _C.B200.PROFILE = False
 # stop an epoch after this many iterations (0 = full epoch); used by tests/smoke
 _C.B200.MAX_ITERS = 0
+# failure detection (utils/health.py): process-group timeout, step watchdog, per-rank heartbeat files
+_C.B200.DIST_TIMEOUT_MIN = 30
+_C.B200.WATCHDOG_S = 0          # 0 = off; else seconds without a finished iteration before stacks are dumped
+_C.B200.WATCHDOG_ABORT = False  # exit(3) when the watchdog fires so the launcher restarts the job (AUTO_RESUME)
+_C.B200.HEARTBEAT_FREQ = 0      # 0 = off; else write OUT_DIR/heartbeat/rank_N.json every N iterations
 
 _CFG_DEFAULT = _C.clone()
 _CFG_DEFAULT.freeze()

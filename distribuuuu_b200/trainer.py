@@ -13,7 +13,8 @@ What is different, on purpose:
 * loss / accuracy are accumulated on the device and read back once per
   ``B200.METRIC_SYNC_FREQ`` iterations in a single packed reduction (the reference does
   3 all-reduces + 3 ``.item()`` syncs every iteration);
-* inputs are prefetched to the device on a side stream; timings can be CUDA-event based.
+* inputs are prefetched to the device on a side stream; timings can be CUDA-event based;
+* optional failure detection (``B200.WATCHDOG_S``, ``B200.HEARTBEAT_FREQ``; utils/health.py).
 """
 from __future__ import annotations
 
@@ -111,6 +112,8 @@ def train_epoch(train_loader, engine, optimizer, cur_epoch, start_epoch, tic, de
     metrics = utils.DeviceMetrics(device)
     sync_freq = max(int(cfg.B200.METRIC_SYNC_FREQ), 1)
     timer = utils.StepTimer(device, enabled=bool(cfg.B200.PROFILE))   # CUDA-event phase timing (B200.PROFILE)
+    watchdog = utils.StepWatchdog(cfg.B200.WATCHDOG_S, abort=cfg.B200.WATCHDOG_ABORT, name=f"epoch{cur_epoch + 1}").start()
+    heartbeat = utils.Heartbeat(cfg.OUT_DIR, rank, cfg.B200.HEARTBEAT_FREQ)
     end = time.time()
     for idx, (inputs, targets) in enumerate(train_loader):
         if idx >= n_iters:
@@ -120,6 +123,8 @@ def train_epoch(train_loader, engine, optimizer, cur_epoch, start_epoch, tic, de
         loss, hits1, hitsk = engine.train_step(inputs, targets, optimizer, cfg.TRAIN.TOPK)
         timer.stop("step")
         metrics.update(loss, hits1, hitsk, targets.size(0))
+        watchdog.tick()
+        heartbeat.beat(cur_epoch, idx + 1)
 
         last = (idx + 1) == n_iters
         if (idx + 1) % sync_freq == 0 or last:
@@ -133,6 +138,8 @@ def train_epoch(train_loader, engine, optimizer, cur_epoch, start_epoch, tic, de
         if rank == 0 and ((idx + 1) % cfg.TRAIN.PRINT_FREQ == 0 or last):
             progress.cal_eta(idx + 1, n_iters, tic, cur_epoch, start_epoch)
             progress.display(idx + 1)
+    watchdog.stop()
+    heartbeat.beat(cur_epoch, n_iters, force=True)
     if cfg.B200.PROFILE and rank == 0:
         for name, st in timer.summary().items():
             per_gpu = st["n"] * targets.size(0) / max(st["total_ms"], 1e-9) * 1e3

@@ -6,6 +6,7 @@ from .data import (IMAGENET_MEAN, IMAGENET_STD, DummyDataset, PinnedPrefetcher, 
 from .dist import (barrier, broadcast_object, get_rank, get_world_size, is_primary, resolve_backend,
                    resolve_device, scaled_all_reduce, setup_distributed, shutdown)
 from .env import setup_logger, setup_seed
+from .health import Heartbeat, StepWatchdog, read_heartbeats, stale_ranks
 from .lr import get_epoch_lr, get_lr_fun, lr_fun_cos, lr_fun_steps, set_lr
 from .meters import AverageMeter, DeviceMetrics, ProgressMeter, accuracy, construct_meters
 from .optim import construct_optimizer, sgd_hparams

@@ -83,7 +83,7 @@ def setup_distributed(backend: str | None = None, port: int | str | None = None)
     if device.type == "cuda":
         torch.cuda.set_device(device)
     backend = resolve_backend(device, backend)
-    kwargs = dict(backend=backend, world_size=world, rank=rank, timeout=timedelta(minutes=30))
+    kwargs = dict(backend=backend, world_size=world, rank=rank, timeout=timedelta(minutes=float(cfg.B200.DIST_TIMEOUT_MIN)))
     if device.type == "cuda":
         kwargs["device_id"] = device  # eager NCCL communicator, needed for symmetric memory
     dist.init_process_group(**kwargs)

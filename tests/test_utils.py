@@ -152,3 +152,34 @@ def test_uint8_input_pipeline(fresh_cfg):
     from distribuuuu_b200.utils import data as D
     tail = D._tail_transforms(T)
     assert len(tail) == 1 and isinstance(tail[0], T.PILToTensor)
+
+
+def test_step_watchdog_fires_and_recovers():
+    import time
+    fired = []
+    wd = utils.StepWatchdog(0.15, abort=False, on_timeout=fired.append, name="t").start()
+    for _ in range(5):          # regular ticks: silent
+        time.sleep(0.03)
+        wd.tick()
+    assert wd.fired == 0
+    time.sleep(0.5)             # stall: fires (and would have dumped the stacks / aborted in a real job)
+    wd.stop()
+    assert wd.fired >= 1 and fired and fired[0] >= 0.15
+    off = utils.StepWatchdog(0, name="off").start()   # disabled: no thread at all
+    assert off._thread is None
+    off.stop()
+
+
+def test_heartbeat_files_and_stale_detection(tmp_path):
+    import time
+    hb0, hb1 = utils.Heartbeat(str(tmp_path), 0, 2), utils.Heartbeat(str(tmp_path), 1, 2)
+    hb0.beat(0, 1)               # not a multiple of freq: skipped
+    assert utils.read_heartbeats(str(tmp_path)) == []
+    hb0.beat(0, 2)
+    hb1.beat(0, 2)
+    beats = utils.read_heartbeats(str(tmp_path))
+    assert [b["rank"] for b in beats] == [0, 1] and beats[0]["iter"] == 2
+    assert utils.stale_ranks(str(tmp_path), 60.0) == []
+    assert utils.stale_ranks(str(tmp_path), 60.0, now=time.time() + 120) == [0, 1]
+    utils.Heartbeat(str(tmp_path), 2, 0).beat(0, 2)   # disabled
+    assert len(utils.read_heartbeats(str(tmp_path))) == 2
