@@ -121,10 +121,15 @@ def test_train_resume_test_cli_end_to_end(tmp_path, free_port):
     assert os.path.exists(os.path.join(out, "config.yaml")) and os.path.exists(os.path.join(out, "best.pth.tar"))
     assert "ACCURACY: TOP1" in r.stderr and "TRAIN:  [1]" in r.stderr
 
-    r2 = _run_cli("train_net.py", free_port + 1, out, ["OPTIM.MAX_EPOCH", "2"])
+    # second epoch: auto-resume; also exercises the uint8 input path, the heartbeat files and the (silent) watchdog
+    r2 = _run_cli("train_net.py", free_port + 1, out, ["OPTIM.MAX_EPOCH", "2", "B200.INPUT_UINT8", "True",
+                                                       "B200.HEARTBEAT_FREQ", "1", "B200.WATCHDOG_S", "300"])
     assert r2.returncode == 0, r2.stderr[-2000:]
     assert "LOADED" in r2.stderr and "TRAIN:  [2]" in r2.stderr and "TRAIN:  [1]" not in r2.stderr
     assert os.path.exists(os.path.join(out, "checkpoints", "ckpt_ep_002.pth.tar"))
+    from distribuuuu_b200 import utils
+    beats = utils.read_heartbeats(out)
+    assert [b["rank"] for b in beats] == [0, 1] and all(b["epoch"] == 1 and b["iter"] == 2 for b in beats)
 
     r3 = _run_cli("test_net.py", free_port + 2, out, ["MODEL.WEIGHTS", os.path.join(out, "best.pth.tar")])
     assert r3.returncode == 0, r3.stderr[-2000:]
