@@ -8,7 +8,6 @@ plain torch ops (CPU / reference semantics) or as fused sm_100a kernels (native 
 """
 from __future__ import annotations
 
-import torch
 import torch.nn as nn
 
 from ..ops import functional as Fn

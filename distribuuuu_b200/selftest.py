@@ -367,7 +367,6 @@ def check_uint8_input(arch="resnet18", batch=8, size=64):
 def check_checkpoint_interop(tmpdir="/tmp/b200_ckpt_test"):
     """A checkpoint written from the native engine (flat / fused optimizer) loads into a plain model with
     ``torch.optim.SGD`` and back (reference layout: utils.py:366-410)."""
-    import os
     import shutil
     from . import models, utils
     from .config import cfg

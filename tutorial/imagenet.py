@@ -6,11 +6,9 @@ import os
 
 import torch
 import torch.distributed as dist
-import torch.nn as nn
 
-from common import base_parser, pick_device
+from common import base_parser
 from distribuuuu_b200 import config, models, utils
-from distribuuuu_b200.parallel import BucketedDataParallel
 
 
 def main():
