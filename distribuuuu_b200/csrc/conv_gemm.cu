@@ -146,24 +146,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
       }
+      // All per-iteration address arithmetic below is incremental: this single thread feeds the whole CTA, and an
+      // ncu source-level capture of the 3x3 wgrad showed it spending ~900 instructions per stage (eleven integer
+      // divisions in decode_pixel / tap / box decoding), i.e. the producer -- not TMA or the tensor pipe -- set the
+      // pace.  Divisions now happen once per work item; the reduction-pixel coordinate advances by BK per stage.
+      const int step_p = (p.b_im2col && p.kind == KIND_WGRAD) ? BK / p.im_Q : 0;   // BK pixels = step_p rows + step_q
+      const int step_q = (p.b_im2col && p.kind == KIND_WGRAD) ? BK - step_p * p.im_Q : 0;
       for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
         const WorkItem w = decode_item(p, item, BN);
-        PixelCoord pa{0, 0, 0};
-        if (p.kind != KIND_WGRAD && p.a_im2col) pa = decode_pixel(p, w.m0);
-        for (int it = w.it_begin; it < w.it_end; ++it) {
-          mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-          const uint32_t bar = smem_u32(&full_bar[stage]);
-          const uint32_t dst_a = smem_u32(smem_a + stage * kABytes);
-          const uint32_t dst_b = smem_u32(smem_b + stage * C::kBBytes);
-          mbar_expect_tx(bar, p.kind == KIND_WGRAD ? (uint32_t)(kABytes + w.nbox * kBoxBytes)
-                                                   : (resident ? (uint32_t)kABytes : (uint32_t)C::kStageBytes));
-          if (p.kind != KIND_WGRAD) {
-            const int tap = it / p.kb_per_tap;
-            const int kb = it - tap * p.kb_per_tap;
-            const int r = tap / p.S, s = tap - r * p.S;
-            const int ca = w.g * p.a_cg + kb * BK;         // A channel coordinate (group slice + K block)
+        if (p.kind != KIND_WGRAD) {
+          PixelCoord pa{0, 0, 0};
+          if (p.a_im2col) pa = decode_pixel(p, w.m0);
+          const int ca0 = w.g * p.a_cg;                      // A channel coordinate of this conv group
+          int tap = 0, kb = 0, r = 0, sx = 0;               // it_begin == 0 for fprop / dgrad
+          for (int it = w.it_begin; it < w.it_end; ++it) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t bar = smem_u32(&full_bar[stage]);
+            const uint32_t dst_a = smem_u32(smem_a + stage * kABytes);
+            const uint32_t dst_b = smem_u32(smem_b + stage * C::kBBytes);
+            mbar_expect_tx(bar, resident ? (uint32_t)kABytes : (uint32_t)C::kStageBytes);
+            const int ca = ca0 + kb * BK;                    // group slice + K block
             if (p.a_im2col)
-              tma_load_im2col_4d(dst_a, &map_a, bar, ca, pa.w, pa.h, pa.n, (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
+              tma_load_im2col_4d(dst_a, &map_a, bar, ca, pa.w, pa.h, pa.n, (uint16_t)(sx * p.dil), (uint16_t)(r * p.dil));
             else
               tma_load_3d(dst_a, &map_a, bar, ca, 0, w.m0);
             const int btap = p.b_flip_taps ? (p.taps - 1 - tap) : tap;
@@ -176,25 +180,54 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               for (int j = 0; j < p.b_nbox; ++j)                              // MN-major weights [K][tap][N]
                 tma_load_4d(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + 64 * j, btap, kb * BK, w.g);
             }
-          } else {
+            if (++kb == p.kb_per_tap) { kb = 0; ++tap; if (++sx == p.S) { sx = 0; ++r; } }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
+          }
+        } else {
+          // wgrad: the item's <= 4 virtual B boxes (tap, 64-channel slice of Cin) are fixed; decode them once
+          int box_c[4], box_ow[4], box_oh[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int vb = w.vb0 + (j < w.nbox ? j : 0);
+            const int tap = vb / p.cin_boxes, cbox = vb - tap * p.cin_boxes;
+            const int r = tap / p.S, sx = tap - r * p.S;
+            box_c[j] = w.g * p.a_cg + cbox * 64; box_ow[j] = sx * p.dil; box_oh[j] = r * p.dil;
+          }
+          const int a_c0 = w.g * p.out_cg + w.m0;
+          // reduction-pixel coordinate (q, ph, n) of the item's first block; advanced by BK pixels per stage
+          int q = 0, ph = 0, n = 0;
+          if (p.b_im2col) {
+            const int pix = w.it_begin * BK, pq = p.im_P * p.im_Q;
+            n = pix / pq;
+            const int rem = pix - n * pq;
+            ph = rem / p.im_Q;
+            q = rem - ph * p.im_Q;
+          }
+          for (int it = w.it_begin; it < w.it_end; ++it) {
+            mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+            const uint32_t bar = smem_u32(&full_bar[stage]);
+            const uint32_t dst_a = smem_u32(smem_a + stage * kABytes);
+            const uint32_t dst_b = smem_u32(smem_b + stage * C::kBBytes);
+            mbar_expect_tx(bar, (uint32_t)(kABytes + w.nbox * kBoxBytes));
             const int k0 = it * BK;  // first reduction pixel of this block
             for (int j = 0; j < p.a_nbox; ++j)
-              tma_load_3d(dst_a + j * kBoxBytes, &map_a, bar, w.g * p.out_cg + w.m0 + 64 * j, 0, k0);
-            PixelCoord pb{0, 0, 0};
-            if (p.b_im2col) pb = decode_pixel(p, k0);
-            for (int j = 0; j < w.nbox; ++j) {
-              const int vb = w.vb0 + j;
-              const int tap = vb / p.cin_boxes, cbox = vb - tap * p.cin_boxes;
-              if (p.b_im2col) {
-                const int r = tap / p.S, s = tap - r * p.S;
-                tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, w.g * p.a_cg + cbox * 64, pb.w, pb.h, pb.n,
-                                   (uint16_t)(s * p.dil), (uint16_t)(r * p.dil));
-              } else {
-                tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, w.g * p.a_cg + cbox * 64, 0, k0);
-              }
+              tma_load_3d(dst_a + j * kBoxBytes, &map_a, bar, a_c0 + 64 * j, 0, k0);
+            if (p.b_im2col) {
+              const int cw = q * p.im_stride + p.im_low_w, chh = ph * p.im_stride + p.im_low_h;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < w.nbox)
+                  tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, box_c[j], cw, chh, n, (uint16_t)box_ow[j], (uint16_t)box_oh[j]);
+              q += step_q; ph += step_p;
+              if (q >= p.im_Q) { q -= p.im_Q; ++ph; }
+              while (ph >= p.im_P) { ph -= p.im_P; ++n; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (j < w.nbox) tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, box_c[j], 0, k0);
             }
+            if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
-          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
       }
     }
