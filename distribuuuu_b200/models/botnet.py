@@ -156,3 +156,32 @@ def botnet50(pretrained=False, num_classes=1000, fmap_size=(14, 14), **kwargs):
     stack = BoTStack(dim=1024, fmap_size=fmap_size, stride=1, rel_pos_emb=True)
     return BoTNet(trunk.conv1, trunk.bn1, trunk.relu, trunk.maxpool, trunk.layer1, trunk.layer2, trunk.layer3,
                   stack, nn.AdaptiveAvgPool2d((1, 1)), nn.Flatten(1), nn.Linear(2048, num_classes))
+
+
+def smoke_botnet50(device="cpu"):
+    """Shape check of the full model (reference ``test_botnet50``, botnet.py:293-297; device-agnostic here)."""
+    import torch
+    x = torch.ones(2, 3, 224, 224, device=device)
+    y = botnet50().to(device)(x)
+    assert tuple(y.shape) == (2, 1000)
+    return tuple(y.shape)
+
+
+def smoke_backbone(device="cpu"):
+    """BoTStack dropped into a ResNet-50 trunk keeps the backbone's output shape (reference ``test_backbone``,
+    botnet.py:300-314)."""
+    import torch
+    trunk = resnet50()
+    layers = [trunk.conv1, trunk.bn1, trunk.relu, trunk.maxpool, trunk.layer1, trunk.layer2, trunk.layer3,
+              BoTStack(dim=1024, fmap_size=(14, 14), stride=1, rel_pos_emb=True)]
+    x = torch.ones(2, 3, 224, 224, device=device)
+    net = nn.Sequential(*layers).to(device)
+    y = x
+    for m in net:
+        y = m(y)
+    assert tuple(y.shape) == (2, 2048, 14, 14)
+    return tuple(y.shape)
+
+
+if __name__ == "__main__":
+    print(smoke_backbone())
