@@ -73,3 +73,36 @@ def test_fused_sgd_state_dict_is_torch_sgd_compatible():
     assert opt2.has_momentum_state and opt2.param_groups[0]["lr"] == 0.1
     for pa, pb in zip(eng.params, eng2.params):                          # (alignment padding between parameters is don't-care)
         assert torch.equal(eng.logical_view(eng.flat_mom, pa), eng2.logical_view(eng2.flat_mom, pb))
+
+
+def test_grad_sink_mailbox_protocol():
+    """ops.native._GradSink: one pending gradient at a time; late offers are refused so the producer falls back to
+    returning its gradient through autograd (never a lost or double-counted contribution)."""
+    from distribuuuu_b200.ops.native import _GradSink
+    s = _GradSink(ptr=1234)
+    assert s.take() is None and s.consumed            # consumer ran first ...
+    assert not s.offer(torch.ones(1))                 # ... so a later producer must keep its gradient
+    s = _GradSink(ptr=1234)
+    g = torch.ones(2)
+    assert s.offer(g) and not s.offer(torch.zeros(2))  # second producer is refused while one is pending
+    assert s.take() is g and s.take() is None
+
+
+def test_projection_shortcut_hint_is_ignored_on_the_torch_path():
+    """models pass ``input_grad_to`` / ``residual_sink`` hints; without an engine they must not change results."""
+    import copy
+    from distribuuuu_b200.ops import functional as Fn
+    torch.manual_seed(0)
+    net = build_model("resnet18", num_classes=10)
+    ref = copy.deepcopy(net)
+    x = torch.randn(2, 3, 64, 64)
+    blk, rblk = net.layer2[0], ref.layer2[0]          # block with a projection shortcut
+    h = torch.randn(2, 64, 16, 16, requires_grad=True)
+    h2 = h.detach().clone().requires_grad_(True)
+    out = blk(h)
+    identity = rblk.downsample[1](rblk.downsample[0](h2))
+    want = torch.relu(rblk.bn2(rblk.conv2(torch.relu(rblk.bn1(rblk.conv1(h2))))) + identity)
+    assert torch.allclose(out, want, atol=1e-5)
+    out.sum().backward(); want.sum().backward()
+    assert torch.allclose(h.grad, h2.grad, atol=1e-5)
+    assert Fn.conv_bn_act(x, net.conv1, net.bn1, "relu", input_grad_to=net.conv1).shape == (2, 64, 32, 32)
