@@ -16,17 +16,22 @@ from .utils import load_pretrained
 __all__ = ["ResNet", "BasicBlock", "Bottleneck", "resnet18", "resnet34", "resnet50", "resnet101",
            "resnet152", "resnext50_32x4d", "resnext101_32x8d", "wide_resnet50_2", "wide_resnet101_2"]
 
-model_urls = {
-    "resnet18": "https://download.pytorch.org/models/resnet18-5c106cde.pth",
-    "resnet34": "https://download.pytorch.org/models/resnet34-333f7ec4.pth",
-    "resnet50": "https://download.pytorch.org/models/resnet50-19c8e357.pth",
-    "resnet101": "https://download.pytorch.org/models/resnet101-5d3b4d8f.pth",
-    "resnet152": "https://download.pytorch.org/models/resnet152-b121ed2d.pth",
-    "resnext50_32x4d": "https://download.pytorch.org/models/resnext50_32x4d-7cdf4587.pth",
-    "resnext101_32x8d": "https://download.pytorch.org/models/resnext101_32x8d-8ba56ff5.pth",
-    "wide_resnet50_2": "https://download.pytorch.org/models/wide_resnet50_2-95faca4d.pth",
-    "wide_resnet101_2": "https://download.pytorch.org/models/wide_resnet101_2-32ee1156.pth",
+_HUB = "https://download.pytorch.org/models/"
+
+# arch -> (block name, blocks per stage, constructor overrides, torchvision checkpoint file)
+# (the variants of reference models/resnet.py:315-447 and its URL table :23-33, as data)
+_SPECS = {
+    "resnet18": ("BasicBlock", (2, 2, 2, 2), {}, "resnet18-5c106cde.pth"),
+    "resnet34": ("BasicBlock", (3, 4, 6, 3), {}, "resnet34-333f7ec4.pth"),
+    "resnet50": ("Bottleneck", (3, 4, 6, 3), {}, "resnet50-19c8e357.pth"),
+    "resnet101": ("Bottleneck", (3, 4, 23, 3), {}, "resnet101-5d3b4d8f.pth"),
+    "resnet152": ("Bottleneck", (3, 8, 36, 3), {}, "resnet152-b121ed2d.pth"),
+    "resnext50_32x4d": ("Bottleneck", (3, 4, 6, 3), {"groups": 32, "width_per_group": 4}, "resnext50_32x4d-7cdf4587.pth"),
+    "resnext101_32x8d": ("Bottleneck", (3, 4, 23, 3), {"groups": 32, "width_per_group": 8}, "resnext101_32x8d-8ba56ff5.pth"),
+    "wide_resnet50_2": ("Bottleneck", (3, 4, 6, 3), {"width_per_group": 128}, "wide_resnet50_2-95faca4d.pth"),
+    "wide_resnet101_2": ("Bottleneck", (3, 4, 23, 3), {"width_per_group": 128}, "wide_resnet101_2-32ee1156.pth"),
 }
+model_urls = {arch: _HUB + spec[3] for arch, spec in _SPECS.items()}
 
 
 def conv3x3(cin: int, cout: int, stride: int = 1, groups: int = 1, dilation: int = 1) -> nn.Conv2d:
@@ -170,48 +175,22 @@ class ResNet(nn.Module):
         return Fn.linear(Fn.global_avg_pool(x), self.fc)
 
 
-def _resnet(arch, block, layers, pretrained, progress, **kwargs):
-    model = ResNet(block, layers, **kwargs)
-    if pretrained:
-        load_pretrained(model, model_urls[arch], progress)
-    return model
+def _make_constructor(arch: str):
+    block_name, layers, overrides, _ = _SPECS[arch]
+
+    def build(pretrained: bool = False, progress: bool = True, **kwargs) -> ResNet:
+        kwargs.update(overrides)
+        model = ResNet(globals()[block_name], list(layers), **kwargs)
+        if pretrained:
+            load_pretrained(model, model_urls[arch], progress)
+        return model
+
+    build.__name__ = build.__qualname__ = arch
+    build.__doc__ = (f"{arch}: {block_name} x {layers}" + (f", {overrides}" if overrides else "") +
+                     "; ``pretrained`` loads torchvision's ImageNet weights (needs network access).")
+    return build
 
 
-def resnet18(pretrained=False, progress=True, **kw):
-    return _resnet("resnet18", BasicBlock, [2, 2, 2, 2], pretrained, progress, **kw)
-
-
-def resnet34(pretrained=False, progress=True, **kw):
-    return _resnet("resnet34", BasicBlock, [3, 4, 6, 3], pretrained, progress, **kw)
-
-
-def resnet50(pretrained=False, progress=True, **kw):
-    return _resnet("resnet50", Bottleneck, [3, 4, 6, 3], pretrained, progress, **kw)
-
-
-def resnet101(pretrained=False, progress=True, **kw):
-    return _resnet("resnet101", Bottleneck, [3, 4, 23, 3], pretrained, progress, **kw)
-
-
-def resnet152(pretrained=False, progress=True, **kw):
-    return _resnet("resnet152", Bottleneck, [3, 8, 36, 3], pretrained, progress, **kw)
-
-
-def resnext50_32x4d(pretrained=False, progress=True, **kw):
-    kw.update(groups=32, width_per_group=4)
-    return _resnet("resnext50_32x4d", Bottleneck, [3, 4, 6, 3], pretrained, progress, **kw)
-
-
-def resnext101_32x8d(pretrained=False, progress=True, **kw):
-    kw.update(groups=32, width_per_group=8)
-    return _resnet("resnext101_32x8d", Bottleneck, [3, 4, 23, 3], pretrained, progress, **kw)
-
-
-def wide_resnet50_2(pretrained=False, progress=True, **kw):
-    kw.update(width_per_group=128)
-    return _resnet("wide_resnet50_2", Bottleneck, [3, 4, 6, 3], pretrained, progress, **kw)
-
-
-def wide_resnet101_2(pretrained=False, progress=True, **kw):
-    kw.update(width_per_group=128)
-    return _resnet("wide_resnet101_2", Bottleneck, [3, 4, 23, 3], pretrained, progress, **kw)
+for _arch in _SPECS:
+    globals()[_arch] = _make_constructor(_arch)
+del _arch

@@ -1,13 +1,8 @@
-"""Evaluate a trained model: ``... test_net.py --cfg config/resnet18.yaml MODEL.WEIGHTS path``
-(entry contract of reference test_net.py:6-9)."""
-from distribuuuu_b200 import config, trainer
+"""Evaluate a trained model on the validation split.
 
-
-def main():
-    config.load_cfg_fom_args("Test a classification model.")
-    config.cfg.freeze()
-    trainer.test_model()
-
+    python -m torch.distributed.run --nproc_per_node=8 test_net.py --cfg config/resnet18.yaml MODEL.WEIGHTS best.pth.tar
+"""
+from distribuuuu_b200.cli import main
 
 if __name__ == "__main__":
-    main()
+    main("test")
