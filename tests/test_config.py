@@ -105,3 +105,47 @@ def test_dump_cfg_writes_file(fresh_cfg, tmp_path):
     config.dump_cfg()
     loaded = CfgNode.load_cfg(open(tmp_path / "o" / "config.yaml"))
     assert loaded.MODEL.ARCH == "resnet18"
+
+
+# ---- property tests: the KEY VALUE override parser and the dump/load round trip -------------------------------
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(lr=st.floats(min_value=1e-6, max_value=10, allow_nan=False, allow_infinity=False),
+       epochs=st.integers(min_value=1, max_value=10_000),
+       steps=st.lists(st.integers(min_value=0, max_value=500), min_size=0, max_size=5),
+       syncbn=st.booleans(),
+       arch=st.sampled_from(["resnet18", "resnet50", "botnet50", "regnety_160", "efficientnet_b0"]))
+def test_override_strings_parse_to_typed_values(lr, epochs, steps, syncbn, arch):
+    """Every value arrives as a string on the command line (reference config.py:95-100) and must come back typed."""
+    from distribuuuu_b200 import config
+    config.reset_cfg()
+    c = config.cfg
+    c.merge_from_list(["OPTIM.BASE_LR", repr(lr), "OPTIM.MAX_EPOCH", str(epochs), "OPTIM.STEPS", str(steps),
+                       "MODEL.SYNCBN", str(syncbn), "MODEL.ARCH", arch])
+    assert isinstance(c.OPTIM.BASE_LR, float) and c.OPTIM.BASE_LR == lr
+    assert isinstance(c.OPTIM.MAX_EPOCH, int) and c.OPTIM.MAX_EPOCH == epochs
+    assert list(c.OPTIM.STEPS) == steps and c.MODEL.SYNCBN is syncbn and c.MODEL.ARCH == arch
+    # dump -> load reproduces the node exactly
+    again = config.CfgNode.load_cfg(c.dump()) if hasattr(config.CfgNode, "load_cfg") else None
+    if again is not None:
+        assert again.OPTIM.BASE_LR == lr and again.OPTIM.MAX_EPOCH == epochs and list(again.OPTIM.STEPS) == steps
+    config.reset_cfg()
+
+
+@settings(max_examples=40, deadline=None)
+@given(e=st.integers(min_value=0, max_value=299), warm=st.integers(min_value=0, max_value=20),
+       base=st.floats(min_value=1e-4, max_value=5.0), min_frac=st.floats(min_value=0.0, max_value=0.5))
+def test_cosine_lr_is_bounded_and_monotone_after_warmup(e, warm, base, min_frac):
+    """lr(e) stays within [MIN_LR*BASE_LR, BASE_LR] and never increases once warm-up is over (reference utils.py:286-310)."""
+    from distribuuuu_b200 import config, utils
+    config.reset_cfg()
+    c = config.cfg
+    c.OPTIM.LR_POLICY, c.OPTIM.MAX_EPOCH, c.OPTIM.BASE_LR = "cos", 300, base
+    c.OPTIM.WARMUP_EPOCHS, c.OPTIM.MIN_LR = warm, min_frac
+    lr0, lr1 = utils.get_epoch_lr(e), utils.get_epoch_lr(e + 1)
+    assert 0.0 <= lr0 <= base * (1 + 1e-9)
+    if e >= warm:
+        assert lr1 <= lr0 * (1 + 1e-9) and lr0 >= base * min_frac * (1 - 1e-9)
+    config.reset_cfg()
