@@ -22,7 +22,9 @@ def run(mode: str, argv: Optional[Sequence[str]] = None):
     config.load_cfg_fom_args(description, argv=argv)
     config.cfg.freeze()
     try:
-        return getattr(trainer, entry)()
+        result = getattr(trainer, entry)()
+        utils.barrier()          # success path: nobody tears the group down while a peer is still reducing metrics
+        return result
     finally:
         utils.shutdown()
 
