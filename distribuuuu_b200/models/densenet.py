@@ -11,6 +11,7 @@ pre-allocated NHWC buffer instead of copying.
 """
 from __future__ import annotations
 
+import functools
 import re
 from collections import OrderedDict
 
@@ -19,6 +20,7 @@ import torch.nn as nn
 import torch.utils.checkpoint as cp
 
 from ..ops import functional as Fn
+from ..ops import runtime
 from .utils import load_state_dict_from_url
 
 __all__ = ["DenseNet", "densenet121", "densenet169", "densenet201", "densenet161"]
@@ -49,10 +51,17 @@ class _DenseLayer(nn.Module):
         x = Fn.concat_channels(features)
         return Fn.conv2d(Fn.bn_act(x, self.norm1, "relu"), self.conv1)
 
+    def _bottleneck_on(self, engine, *features):
+        # The recomputation runs during backward -- outside the engine's forward scope and, on CUDA, on autograd's
+        # worker thread -- so the execution path chosen in the forward pass is re-entered explicitly; otherwise the
+        # recomputed graph (ATen ops) would not match the recorded one (native ops).
+        with runtime.native_scope(engine):
+            return self._bottleneck(*features)
+
     def forward(self, features):
         feats = [features] if torch.is_tensor(features) else list(features)
         if self.memory_efficient and any(f.requires_grad for f in feats):
-            mid = cp.checkpoint(self._bottleneck, *feats, use_reentrant=False)
+            mid = cp.checkpoint(functools.partial(self._bottleneck_on, runtime.active_engine()), *feats, use_reentrant=False)
         else:
             mid = self._bottleneck(*feats)
         new = Fn.conv2d(Fn.bn_act(mid, self.norm2, "relu"), self.conv2)

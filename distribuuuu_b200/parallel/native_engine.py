@@ -225,7 +225,9 @@ class NativeEngine(nn.Module):
         # (activation-checkpoint recomputation, a BN module applied twice) must start from zero again
         key = (bn, which)
         if key in self._slots_used:
-            view.zero_()
+            # through .data: the slot shares one allocation (and therefore one autograd version counter) with the
+            # bf16 weights; a tracked in-place write here would invalidate every weight view saved for backward
+            view.data.zero_()
         self._slots_used.add(key)
         return _Slot(view, self.stats_sym_base + base)
 

@@ -1,0 +1,287 @@
+"""Plain-PyTorch emulation of the sm_100a kernel module (``distribuuuu_b200/_ext/b200_kernels``), same call
+signatures, same memory conventions (bf16 NHWC activations, KRSC weights, fp32 flat gradients that are ACCUMULATED
+into, [2][C] statistic slots, 1-bit ReLU masks, uint8 max-pool tap indices).
+
+It lets the CPU test suite run the native engine's *host* logic end to end -- autograd Functions, gradient mailboxes
+between block branches, strided-dgrad decompositions, BN slot bookkeeping, flat-buffer views, the fused optimizer
+step -- and compare a training step against the fp32 torch path.  It says nothing about the CUDA kernels themselves;
+those are checked against fp32 PyTorch on the GPU box (tests/test_gpu_kernels.py).
+"""
+import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
+ACT_NONE, ACT_RELU, ACT_SILU = 0, 1, 2
+
+
+def _raw(t):
+    """Alias of ``t`` with its own autograd version counter: kernels write through raw pointers, so a write into
+    one region of the engine's big allocation (statistics slots, bf16 weights, staging share it) must not look like
+    a modification of every other view of it."""
+    return t.data
+
+
+def _nchw(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2).float()
+
+
+def _act(z, act):
+    return torch.relu(z) if act == ACT_RELU else (F.silu(z) if act == ACT_SILU else z)
+
+
+def _act_grad(z, act):
+    if act == ACT_RELU:
+        return (z > 0).float()
+    if act == ACT_SILU:
+        s = torch.sigmoid(z)
+        return s * (1 + z * (1 - s))
+    return torch.ones_like(z)
+
+
+def _pack_mask(positive):           # [rows, C] bool -> [rows, C/8] uint8, bit i = channel cv*8+i
+    rows, C = positive.shape
+    w = (2 ** torch.arange(8, dtype=torch.int32)).view(1, 1, 8)
+    return (positive.view(rows, C // 8, 8).int() * w).sum(-1).to(torch.uint8)
+
+
+def _unpack_mask(mask, C):
+    bits = (mask.int().unsqueeze(-1) >> torch.arange(8, dtype=torch.int32)) & 1
+    return bits.view(mask.shape[0], C).float()
+
+
+class FakeKernels:
+    calls: dict
+
+    def __init__(self):
+        self.calls = {}
+
+    def _count(self, name):
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+    # ---------------------------------------------------------------- layout / casts
+    def cast_bf16(self, src, dst):
+        _raw(dst).copy_(src.to(BF16))
+
+    def nchw_to_nhwc(self, x, out):
+        _raw(out).copy_(x.permute(0, 2, 3, 1).to(BF16))
+
+    def stem_im2col(self, x, patches, R, S, stride, pad, P, Q, mean=(), std=()):
+        self._count("stem_im2col")
+        if x.dtype == torch.uint8:
+            m = torch.tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+            s = torch.tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+            x = (x.float() / 255.0 - m) / s
+        N, C = x.shape[:2]
+        cols = F.unfold(x.float(), (R, S), padding=pad, stride=stride)            # [N, C*R*S, L], ordered (c, r, s)
+        cols = cols.view(N, C, R * S, P * Q).permute(0, 3, 2, 1).reshape(N * P * Q, R * S * C)   # -> (r, s, c)
+        flat = _raw(patches).view(N * P * Q, -1)
+        flat.zero_()
+        flat[:, : R * S * C] = cols.to(BF16)
+
+    def pad_rows(self, src, dst, rows, cols, cols_pad):
+        d = _raw(dst).view(rows, cols_pad)
+        d.zero_()
+        d[:, :cols] = src.reshape(rows, cols)
+
+    def unpad_add(self, src, dst, rows, cols, cols_pad):
+        _raw(dst.view(rows, cols)).add_(src.view(rows, cols_pad)[:, :cols])
+
+    # ---------------------------------------------------------------- convolutions (implicit GEMM on the GPU)
+    def conv_fprop(self, x, w, y, stats, bias, stride, pad, dil, groups=1):
+        self._count("conv_fprop")
+        out = F.conv2d(_nchw(x), w.permute(0, 3, 1, 2).float(), bias.float() if bias is not None else None,
+                       stride, pad, dil, groups)
+        yb = out.permute(0, 2, 3, 1).to(BF16)
+        _raw(y).copy_(yb.reshape(y.shape))
+        if stats is not None:
+            K = w.shape[0]
+            f = yb.float().reshape(-1, K)
+            _raw(stats)[:K] += f.sum(0)
+            _raw(stats)[K:2 * K] += (f * f).sum(0)
+
+    def conv_dgrad(self, dy, w, dx, stride, pad, dil, addend=None, groups=1):
+        self._count("conv_dgrad" + ("+addend" if addend is not None else ""))
+        assert stride == 1
+        g = F.conv_transpose2d(_nchw(dy), w.permute(0, 3, 1, 2).float(), None, 1, pad, 0, groups, dil)
+        g = g.permute(0, 2, 3, 1)
+        if addend is not None:
+            g = g + addend.float().reshape(g.shape)
+        _raw(dx).copy_(g.to(BF16).reshape(dx.shape))
+
+    def conv_wgrad(self, dy, x, dw, stride, pad, dil, groups=1):
+        self._count("conv_wgrad")
+        K, R, S, Cg = dw.shape
+        gw = torch.nn.grad.conv2d_weight(_nchw(x), (K, Cg, R, S), _nchw(dy), stride, pad, dil, groups)
+        _raw(dw).add_(gw.permute(0, 2, 3, 1))
+
+    # ---------------------------------------------------------------- depthwise (CUDA-core direct conv on the GPU)
+    def dw_fprop(self, x, w, y, stats, k, s, p):
+        self._count("dw_fprop")
+        C = x.shape[3]
+        out = F.conv2d(_nchw(x), w.float().view(C, 1, k, k), None, s, p, 1, C)
+        yb = out.permute(0, 2, 3, 1).to(BF16)
+        _raw(y).copy_(yb)
+        if stats is not None:
+            f = yb.float().reshape(-1, C)
+            _raw(stats)[:C] += f.sum(0)
+            _raw(stats)[C:2 * C] += (f * f).sum(0)
+
+    def dw_dgrad(self, dy, w, dx, k, s, p):
+        self._count("dw_dgrad")
+        C = dy.shape[3]
+        H, W = dx.shape[1], dx.shape[2]
+        P, Q = dy.shape[1], dy.shape[2]
+        oph, opw = H - ((P - 1) * s - 2 * p + k), W - ((Q - 1) * s - 2 * p + k)
+        g = F.conv_transpose2d(_nchw(dy), w.float().view(C, 1, k, k), None, s, p, (oph, opw), C)
+        _raw(dx).copy_(g.permute(0, 2, 3, 1).to(BF16))
+
+    def dw_wgrad(self, dy, x, dw, k, s, p):
+        self._count("dw_wgrad")
+        C = x.shape[3]
+        gw = torch.nn.grad.conv2d_weight(_nchw(x), (C, 1, k, k), _nchw(dy), s, p, 1, C)
+        _raw(dw).add_(gw.view(C, k, k))
+
+    # ---------------------------------------------------------------- batch norm
+    def bn_stats(self, y2, stats):
+        C = y2.shape[1]
+        f = y2.float()
+        _raw(stats)[:C] += f.sum(0)
+        _raw(stats)[C:2 * C] += (f * f).sum(0)
+
+    def bn_apply(self, y2, res2, out2, stats, sym_offset, gamma, beta, rm, rv, save_mean, save_invstd, count, eps,
+                 momentum, act, training, peer, relu_mask=None):
+        self._count("bn_apply")
+        assert peer is None
+        C = y2.shape[1]
+        yf = y2.float()
+        if training:
+            mean = stats[:C] / count
+            var = (stats[C:2 * C] / count - mean * mean).clamp_min(0)
+            invstd = torch.rsqrt(var + eps)
+            _raw(save_mean).copy_(mean)
+            _raw(save_invstd).copy_(invstd)
+            if rm is not None:
+                _raw(rm).mul_(1 - momentum).add_(momentum * mean)
+                _raw(rv).mul_(1 - momentum).add_(momentum * var * (count / max(count - 1.0, 1.0)))
+        else:
+            mean, invstd = rm, torch.rsqrt(rv + eps)
+        g = gamma if gamma is not None else torch.ones(C)
+        b = beta if beta is not None else torch.zeros(C)
+        z = (yf - mean) * invstd * g + b
+        if res2 is not None:
+            z = z + res2.float()
+        o = _act(z, act)
+        _raw(out2).copy_(o.to(BF16))
+        if relu_mask is not None:
+            _raw(relu_mask).copy_(_pack_mask(o > 0))
+
+    def bn_backward(self, y, dout, residual, dy, dresidual, sums, sym_offset, gamma, beta, save_mean, save_invstd,
+                    dgamma, dbeta, count, act, peer, relu_mask=None, phase=3):
+        self._count("bn_backward" + ("+mask" if relu_mask is not None else ""))
+        assert peer is None and phase == 3
+        C = y.shape[1]
+        yf, d = y.float(), dout.float()
+        g = gamma if gamma is not None else torch.ones(C)
+        b = beta if beta is not None else torch.zeros(C)
+        xhat = (yf - save_mean) * save_invstd
+        if relu_mask is not None:
+            dz = d * _unpack_mask(relu_mask, C)
+        elif act != ACT_NONE:
+            z = xhat * g + b
+            if residual is not None:
+                z = z + residual.float()
+            dz = d * _act_grad(z, act)
+        else:
+            dz = d
+        s0, s1 = dz.sum(0), (dz * xhat).sum(0)
+        _raw(sums)[:C] += s0
+        _raw(sums)[C:2 * C] += s1
+        if dgamma is not None:
+            _raw(dgamma).add_(s1)
+            _raw(dbeta).add_(s0)
+        _raw(dy).copy_(((dz - s0 / count - xhat * (s1 / count)) * g * save_invstd).to(BF16))
+        if dresidual is not None:
+            _raw(dresidual).copy_(dz.to(BF16))
+
+    # ---------------------------------------------------------------- pooling
+    def maxpool_fwd(self, x, out, arg, k, s, p):
+        self._count("maxpool_fwd")
+        N, H, W, C = x.shape
+        o, idx = F.max_pool2d(_nchw(x), k, s, p, return_indices=True)             # idx = h * W + w
+        _raw(out).copy_(o.permute(0, 2, 3, 1).to(BF16))
+        if arg is not None:
+            P, Q = o.shape[2], o.shape[3]
+            h, w = idx // W, idx % W
+            ph = torch.arange(P).view(1, 1, P, 1)
+            q = torch.arange(Q).view(1, 1, 1, Q)
+            tap = (h - (ph * s - p)) * k + (w - (q * s - p))
+            _raw(arg).copy_(tap.permute(0, 2, 3, 1).to(torch.uint8))
+
+    def maxpool_bwd(self, dout, arg, dx, k, s, p):
+        self._count("maxpool_bwd")
+        N, H, W, C = dx.shape
+        P, Q = dout.shape[1], dout.shape[2]
+        tap = arg.long()
+        ph = torch.arange(P).view(1, P, 1, 1)
+        q = torch.arange(Q).view(1, 1, Q, 1)
+        h = ph * s - p + tap // k
+        w = q * s - p + tap % k
+        n = torch.arange(N).view(N, 1, 1, 1).expand_as(tap)
+        c = torch.arange(C).view(1, 1, 1, C).expand_as(tap)
+        acc = torch.zeros((N, H, W, C), dtype=torch.float32)
+        acc.index_put_((n, h, w, c), dout.float(), accumulate=True)
+        _raw(dx).copy_(acc.to(BF16))
+
+    def avgpool2_fwd(self, x, out):
+        _raw(out).copy_(F.avg_pool2d(_nchw(x), 2).permute(0, 2, 3, 1).to(BF16))
+
+    def avgpool2_bwd(self, dout, dx):
+        g = _nchw(dout).repeat_interleave(2, 2).repeat_interleave(2, 3) * 0.25
+        full = torch.zeros(dx.shape[0], dx.shape[3], dx.shape[1], dx.shape[2])
+        full[:, :, : g.shape[2], : g.shape[3]] = g
+        _raw(dx).copy_(full.permute(0, 2, 3, 1).to(BF16))
+
+    def gap_fwd(self, x, out):
+        _raw(out).copy_(x.float().mean(dim=(1, 2)).to(BF16))
+
+    def gap_bwd(self, dout, dx):
+        N, H, W, C = dx.shape
+        _raw(dx).copy_((dout.float() / (H * W)).view(N, 1, 1, C).expand(N, H, W, C).to(BF16))
+
+    def channel_scale_fwd(self, x, gate, out):
+        _raw(out).copy_((x.float() * gate.float().view(gate.shape[0], 1, 1, -1)).to(BF16))
+
+    def channel_scale_bwd(self, dout, x, gate, dx, dgate):
+        d = dout.float()
+        _raw(dx).copy_((d * gate.float().view(gate.shape[0], 1, 1, -1)).to(BF16))
+        _raw(dgate).add_((d * x.float()).sum(dim=(1, 2)))
+
+    # ---------------------------------------------------------------- loss / optimizer
+    def ce_topk(self, logits, target, dlogits, accum, topk, grad_scale):
+        self._count("ce_topk")
+        lf = logits.float()
+        logp = F.log_softmax(lf, dim=1)
+        _raw(accum)[0] += -logp.gather(1, target.view(-1, 1)).sum()
+        top = lf.topk(topk, dim=1).indices
+        _raw(accum)[1] += (top[:, :1] == target.view(-1, 1)).any(1).float().sum()
+        _raw(accum)[2] += (top == target.view(-1, 1)).any(1).float().sum()
+        if dlogits is not None:
+            g = logp.exp()
+            g[torch.arange(lf.shape[0]), target] -= 1.0
+            _raw(dlogits).copy_((g * grad_scale).to(BF16))
+
+    def sgd_local(self, master, mom, grad, w16, off, n, lr, momentum, dampening, wd, nesterov, first, grad_scale, zero_grad):
+        self._count("sgd_local")
+        m, v, g = _raw(master)[off:off + n], _raw(mom)[off:off + n], _raw(grad)[off:off + n]
+        d = g * grad_scale + wd * m
+        if momentum != 0:
+            if first:
+                v.copy_(d)
+            else:
+                v.mul_(momentum).add_(d, alpha=1 - dampening)
+            d = d + momentum * v if nesterov else v
+        m.add_(d, alpha=-lr)
+        if w16 is not None:
+            _raw(w16[off:off + n]).copy_(m.to(BF16))
+        if zero_grad:
+            g.zero_()
