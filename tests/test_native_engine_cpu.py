@@ -96,10 +96,11 @@ def test_training_steps_match_the_torch_path(cpu_engine, arch, size):
 
 
 @pytest.mark.parametrize("arch,size,batch", [("efficientnet_b0", 128, 16), ("densenet121", 64, 8), ("regnety_160", 64, 4),
-                                             ("resnext50_32x4d", 64, 8)])
+                                             ("resnext50_32x4d", 64, 8), ("botnet50", 224, 2)])
 def test_other_model_families_step_like_the_torch_path(cpu_engine, arch, size, batch):
     """Depthwise + SE + SiLU (EfficientNet), pre-activation BN + concat + avg-pool (DenseNet), wide grouped convs +
-    SE (RegNetY), thin groups on the ATen fallback with gradients folded into the flat buffers (ResNeXt)."""
+    SE (RegNetY), thin groups on the ATen fallback with gradients folded into the flat buffers (ResNeXt), the
+    relative-position attention core on bf16 ATen ops between native projections (BoTNet, fixed 224x224 input)."""
     eng, ref, fake = cpu_engine(arch, num_classes=16)
     # same batch / resolution / tolerance as the GPU parity checks (tools/gpu_selftest.py): small BN sample counts
     # make these nets sensitive to bf16 rounding, so the bound is on the loss trajectory, not per tensor
