@@ -241,6 +241,11 @@ class BnActFn(torch.autograd.Function):
                    bn.momentum if bn.momentum is not None else 0.1, ACT[act], training, peer, mask)
         if training and bn.track_running_stats:
             eng.note_bn_step(bn)
+        ctx.frozen = not training
+        if ctx.frozen and (y.requires_grad or (residual is not None and residual.requires_grad)):
+            # BN in eval mode inside a training step (frozen statistics): backward needs the constants it used
+            save[0].copy_(bn.running_mean)
+            save[1].copy_(torch.rsqrt(bn.running_var + bn.eps))
         ctx.eng, ctx.bn, ctx.act, ctx.count = eng, bn, act, count
         ctx.has_res = residual is not None
         ctx.res_needs_grad = residual is not None and residual.requires_grad
@@ -259,6 +264,8 @@ class BnActFn(torch.autograd.Function):
         y2, res2, save, mask = ctx.saved_tensors
         N, H, W, C = ctx.shape
         d2 = _nhwc(dout).view(-1, C)
+        if ctx.frozen:
+            return _frozen_bn_backward(ctx, y2, res2, save, d2)
         dy = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dout.device)
         dres = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dout.device) if ctx.res_needs_grad else None
         slot = eng.bwd_slot(bn)
@@ -275,6 +282,41 @@ class BnActFn(torch.autograd.Function):
             ctx.sink.pending = dres      # consumed by the dgrad of the conv that reads the same block input
             dres = None
         return _nchw_view(dy), (_nchw_view(dres) if dres is not None else None), None, None, None, None, None, None, None
+
+
+def _frozen_bn_backward(ctx, y2, res2, save, d2):
+    """Backward of BN applied with its running statistics (module in eval mode during training, e.g. fine-tuning
+    with frozen BN): the statistics are constants, so dy = dz * gamma * invstd without the batch-mean corrections of
+    the training-mode kernel.  Rare path, plain ATen ops on the saved bf16 tensors."""
+    eng, bn = ctx.eng, ctx.bn
+    N, H, W, C = ctx.shape
+    mean, invstd = save[0], save[1]
+    g = eng.master_view(bn.weight).detach().float() if bn.affine else torch.ones(C, device=y2.device)
+    b = eng.master_view(bn.bias).detach().float() if bn.affine else torch.zeros(C, device=y2.device)
+    xhat = (y2.float() - mean) * invstd
+    dz = d2.float()
+    if ctx.act is not None:
+        z = xhat * g + b
+        if res2 is not None:
+            z = z + res2.float()
+        if ctx.act == "relu":
+            dz = dz * (z > 0)
+        elif ctx.act == "silu":
+            sg = torch.sigmoid(z)
+            dz = dz * (sg * (1 + z * (1 - sg)))
+        else:
+            raise NotImplementedError(ctx.act)
+    if bn.affine:
+        eng.grad_flat_view(bn.weight).add_((dz * xhat).sum(0))
+        eng.grad_flat_view(bn.bias).add_(dz.sum(0))
+        eng.mark_ready(bn.weight)
+        eng.mark_ready(bn.bias)
+    dy = (dz * (g * invstd)).to(torch.bfloat16).view(N, H, W, C)
+    dres = dz.to(torch.bfloat16).view(N, H, W, C) if ctx.res_needs_grad else None
+    if ctx.sink is not None and dres is not None:
+        ctx.sink.pending = dres
+        dres = None
+    return _nchw_view(dy), (_nchw_view(dres) if dres is not None else None), None, None, None, None, None, None, None
 
 
 class LinearFn(torch.autograd.Function):

@@ -96,8 +96,77 @@ def _check_syncbn_matches_global_bn(rank, world):
     assert torch.allclose(gw, bn.weight.grad, atol=1e-4)
 
 
+def _check_native_engine_bucket_schedule(rank, world):
+    """The native engine's multi-rank host logic on gloo + the emulated kernel module (tests/fake_kernels.py):
+    rank-0 weights are broadcast, every bucket's fused update is launched from inside backward as soon as its last
+    gradient exists (roughly reverse registration order, identical on all ranks), left-over buckets are flushed,
+    and the result equals one process
+    training on the concatenated batch (B200.COMM=nccl code path: library all-reduce + local fused update)."""
+    import contextlib
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from fake_kernels import FakeKernels
+    from distribuuuu_b200.models import build_model
+    from distribuuuu_b200.ops import build
+    from distribuuuu_b200.parallel import native_engine
+
+    class _Dummy:                       # stands in for CUDA streams / events
+        def __init__(self, *a, **k): pass
+        def wait_event(self, *a): pass
+        def wait_stream(self, *a): pass
+        def record(self, *a): pass
+
+    fake = FakeKernels()
+    build.load = lambda *a, **k: fake
+    torch.cuda.Stream = torch.cuda.Event = _Dummy
+    torch.cuda.current_stream = lambda *a, **k: _Dummy()
+    torch.cuda.stream = lambda s: contextlib.nullcontext()
+    torch.cuda.synchronize = lambda *a, **k: None
+
+    def make(seed):
+        torch.manual_seed(seed)
+        net = build_model("resnet18", num_classes=10)
+        for m in net.modules():         # per-shard batch statistics differ from the global ones: eval-mode BN
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+        return net
+
+    ref = make(100)
+    eng = native_engine.NativeEngine(make(100 + rank), torch.device("cpu"), comm="nccl", bucket_cap_mb=4)
+    assert eng.world == 2 and eng.comm_mode == "nccl" and len(eng.buckets) >= 3
+    launched = []
+    real_launch = eng._launch_bucket
+    eng._launch_bucket = lambda b: (launched.append((eng.buckets.index(b), eng._in_train_step)), real_launch(b))
+    opt = eng.make_optimizer(lr=0.05, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.05, momentum=0.9, nesterov=True, weight_decay=5e-5)
+    g = torch.Generator().manual_seed(5)
+    x, y = torch.randn(8, 3, 32, 32, generator=g), torch.randint(0, 10, (8,), generator=g)
+    for _ in range(2):
+        launched.clear()
+        eng.train_step(x[rank * 4:(rank + 1) * 4], y[rank * 4:(rank + 1) * 4], opt, 5)
+        ropt.zero_grad()
+        torch.nn.functional.cross_entropy(ref(x), y).backward()
+        ropt.step()
+        order = [i for i, _ in launched]
+        assert sorted(order) == list(range(len(eng.buckets))), order                    # every bucket exactly once
+        assert order[0] == 0 and order != sorted(order)   # classifier first; projection shortcuts finish out of order
+        orders = [None] * world
+        dist.all_gather_object(orders, order)
+        assert orders[0] == orders[1]                      # collectives are issued in the same order on every rank
+        assert sum(1 for _, inside in launched if inside) >= len(eng.buckets) - 1       # overlapped with backward
+    mine = eng.flat_master.clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    assert torch.equal(mine, other), float((mine - other).abs().max())                  # ranks stay bit-identical
+    dot = na = nb = 0.0
+    init = make(100)
+    for (n, a), b, i in zip(eng.module.named_parameters(), ref.parameters(), init.parameters()):
+        da, db = (a.detach() - i.detach()).flatten(), (b.detach() - i.detach()).flatten()
+        dot, na, nb = dot + float(da @ db), na + float(da @ da), nb + float(db @ db)
+    assert dot / (na ** 0.5 * nb ** 0.5) > 0.95 and 0.9 < (na / nb) ** 0.5 < 1.1      # bf16 compute vs fp32 reference
+
+
 @pytest.mark.parametrize("fn", [_check_scaled_all_reduce, _check_ddp_matches_large_batch,
-                                _check_syncbn_matches_global_bn])
+                                _check_syncbn_matches_global_bn, _check_native_engine_bucket_schedule])
 def test_two_rank_gloo(fn, free_port):
     _spawn(fn, 2, free_port)
 

@@ -123,6 +123,34 @@ def test_activation_checkpointing_recomputes_on_the_native_path(cpu_engine):
     assert int(sd_a[k]) == int(sd_b[k]) == 4
 
 
+def test_frozen_batchnorm_in_a_training_step(cpu_engine):
+    """BN modules left in eval mode while training (fine-tuning with frozen statistics): running statistics are
+    used and stay untouched, gradients flow without the batch-mean terms."""
+    eng, ref, _ = cpu_engine("resnet18", num_classes=16)
+    eng.train(), ref.train()
+    for net in (eng.module, ref):
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.eval()
+                m.running_var.fill_(4.0)
+    before = eng.module.bn1.running_mean.clone()
+    opt = eng.make_optimizer(lr=0.01, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=True)
+    ropt = torch.optim.SGD(ref.parameters(), lr=0.01, momentum=0.9, nesterov=True)
+    init = {k: v.clone() for k, v in ref.state_dict().items()}
+    x, y = torch.randn(8, 3, 64, 64), torch.randint(0, 16, (8,))
+    la, _, _ = eng.train_step(x, y, opt, 5)
+    lb, _, _ = Fn.cross_entropy_topk(ref(x), y, 5)
+    ropt.zero_grad()
+    lb.backward()
+    ropt.step()
+    assert abs(float(la.detach()) - float(lb.detach())) / float(lb.detach()) < 0.03
+    assert torch.equal(eng.module.bn1.running_mean, before) and int(eng.module.bn1.num_batches_tracked) == 0
+    sa, sb = eng.module.state_dict(), ref.state_dict()
+    for k in ("conv1.weight", "layer2.0.downsample.0.weight", "layer4.1.bn2.weight", "fc.weight"):
+        da, db = (sa[k].float() - init[k]).flatten(), (sb[k] - init[k]).flatten()
+        assert float(torch.dot(da, db) / (da.norm() * db.norm())) > 0.9, k
+
+
 def test_uint8_batches_match_host_normalisation(cpu_engine):
     from distribuuuu_b200.utils.data import normalize_uint8
     eng, _, fake = cpu_engine("resnet18", num_classes=16)
