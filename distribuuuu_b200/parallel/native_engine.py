@@ -120,6 +120,8 @@ class NativeEngine(nn.Module):
         self.optimizer: FusedSGD | None = None
         self.comm_mode = comm if self.world > 1 else "local"
         self._scratch: Dict[str, torch.Tensor] = {}
+        self._views: Dict[tuple, torch.Tensor] = {}
+        self._slot_cache: Dict[tuple, "_Slot"] = {}
         self._leaves: Dict[nn.Parameter, torch.Tensor] = {}
         self._bn_stepped: List[torch.Tensor] = []
         self.last_sink: Dict[nn.Module, object] = {}   # conv module -> gradient mailbox of its latest forward
@@ -163,25 +165,38 @@ class NativeEngine(nn.Module):
             return flat[off:off + n].view(O, H, W, I).permute(0, 3, 1, 2)
         return flat[off:off + n].view(p.shape)
 
+    # The flat buffers are allocated once, so views into them are created once per parameter and reused: a
+    # training step asks for ~600 of them, and slicing + reshaping in Python was a measurable part of the
+    # per-step host time.
+    def _cached(self, kind: str, p, make):
+        views = self.__dict__.get("_views")
+        if views is None:
+            views = self.__dict__["_views"] = {}
+        key = (kind, id(p))
+        v = views.get(key)
+        if v is None:
+            v = views[key] = make()
+        return v
+
     def master_view(self, p):
         return p.data
 
     def grad_flat_view(self, p):
         off, n = self.index[p]
-        return self.flat_grad[off:off + n]
+        return self._cached("g", p, lambda: self.flat_grad[off:off + n])
 
     def grad_krsc(self, p):
         O, I, H, W = p.shape
-        return self.grad_flat_view(p).view(O, H, W, I)
+        return self._cached("gk", p, lambda: self.grad_flat_view(p).view(O, H, W, I))
 
     def w16_view(self, p):
         off, n = self.index[p]
-        return self.flat_w16[off:off + n].view(p.shape)
+        return self._cached("w", p, lambda: self.flat_w16[off:off + n].view(p.shape))
 
     def w16_krsc(self, p):
         off, n = self.index[p]
         O, I, H, W = p.shape
-        return self.flat_w16[off:off + n].view(O, H, W, I)
+        return self._cached("wk", p, lambda: self.flat_w16[off:off + n].view(O, H, W, I))
 
     def w16_leaf(self, p):
         """bf16 leaf (logical shape) for torch fallback ops; its gradient is folded into the flat buffer."""
@@ -218,18 +233,21 @@ class NativeEngine(nn.Module):
         self.stats_len = (off + 63) // 64 * 64
 
     def _slot(self, bn, which: int) -> _Slot:
-        n = 2 * bn.num_features
-        base = self._step_parity * self.stats_len + self.bn_offsets[bn] + which * n
-        view = self.stats_buf[base:base + n]
+        ck = (id(bn), which, self._step_parity)
+        slot = self._slot_cache.get(ck)
+        if slot is None:
+            n = 2 * bn.num_features
+            base = self._step_parity * self.stats_len + self.bn_offsets[bn] + which * n
+            slot = self._slot_cache[ck] = _Slot(self.stats_buf[base:base + n], self.stats_sym_base + base)
         # all slots are zeroed in one memset at the start of a step; a second use within the same step
         # (activation-checkpoint recomputation, a BN module applied twice) must start from zero again
-        key = (bn, which)
+        key = (id(bn), which)
         if key in self._slots_used:
             # through .data: the slot shares one allocation (and therefore one autograd version counter) with the
             # bf16 weights; a tracked in-place write here would invalidate every weight view saved for backward
-            view.data.zero_()
+            slot.tensor.data.zero_()
         self._slots_used.add(key)
-        return _Slot(view, self.stats_sym_base + base)
+        return slot
 
     def fwd_slot(self, bn) -> _Slot:
         return self._slot(bn, 0)
