@@ -172,3 +172,36 @@ def test_eval_matches_torch_in_eval_mode(cpu_engine):
         la, _, _ = eng.eval_step(x, y, 5)
         lb, _, _ = Fn.cross_entropy_topk(ref(x), y, 5)
     assert abs(float(la) - float(lb)) / abs(float(lb)) < 0.03
+
+
+def test_checkpoints_interchange_with_plain_torch(cpu_engine, fresh_cfg, tmp_path):
+    """utils.save_checkpoint / load_checkpoint with the native engine and its fused optimizer: reference layout
+    (utils.py:366-410), torch.optim.SGD-format optimizer state, and a lossless round trip through a plain model."""
+    from distribuuuu_b200 import utils
+    fresh_cfg.OUT_DIR = str(tmp_path)
+    eng, _, _ = cpu_engine("resnet18", num_classes=16)
+    opt = eng.make_optimizer(lr=0.05, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    eng.train()
+    x, y = torch.randn(4, 3, 64, 64), torch.randint(0, 16, (4,))
+    for _ in range(2):
+        eng.train_step(x, y, opt, 5)
+    path = utils.save_checkpoint(eng, opt, 0, 1.0, True)
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) == {"epoch", "state_dict", "optimizer", "best_acc1"}
+    assert not any(k.startswith("module.") for k in ck["state_dict"])
+    plain = build_model("resnet18", num_classes=16)
+    popt = torch.optim.SGD(plain.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+    assert utils.load_checkpoint(path, plain, popt) == (1, 1.0)
+    first = next(iter(plain.parameters()))
+    assert popt.state[first]["momentum_buffer"].shape == first.shape
+    # ... and back into a fresh engine: masters, momentum and bf16 compute weights are restored exactly
+    eng2, _, _ = cpu_engine("resnet18", num_classes=16)
+    opt2 = eng2.make_optimizer(lr=0.05, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    torch.save({"epoch": 0, "state_dict": plain.state_dict(), "optimizer": popt.state_dict(), "best_acc1": 1.0}, path)
+    utils.load_checkpoint(path, eng2, opt2)
+    assert torch.equal(eng2.flat_master, eng.flat_master) and torch.equal(eng2.flat_mom, eng.flat_mom)
+    assert torch.equal(eng2.flat_w16, eng.flat_w16)
+    # the restored engine continues exactly like the original
+    la, _, _ = eng.train_step(x, y, opt, 5)
+    lb, _, _ = eng2.train_step(x, y, opt2, 5)
+    assert float(la.detach()) == float(lb.detach()) and torch.equal(eng.flat_master, eng2.flat_master)
