@@ -29,7 +29,8 @@ def main():
     demangle = subprocess.run(["c++filt"] + list(kernels), capture_output=True, text=True).stdout.splitlines()
     lines = ["# SASS evidence (tools/sass_summary.py over distribuuuu_b200/_ext/b200_kernels.so, sm_100a), per kernel: instruction-class counts",
              "# UTCHMMA = tcgen05.mma, LDTM = tcgen05.ld, UTCBAR = tcgen05.commit, UTCATOMSWS = TMEM alloc, UTMALDG / UTMASTG = TMA load / store",
-             "# (IM2COL = im2col mode), SYNCS = mbarrier ops, LDGSTS / LDGDEPBAR = cp.async, REDG = red.global (F32x4 = vector), *MC* = multimem", ""]
+             "# (IM2COL = im2col mode), SYNCS = mbarrier ops, LDGSTS / LDGDEPBAR = cp.async, REDG = red.global (F32x4 = vector),",
+             "# LDGMC...HPADD = multimem.ld_reduce (multimem.st compiles to a plain STG.E.128 on the multicast address and is not listed)", ""]
     for (mangled, ins), pretty in zip(kernels.items(), demangle):
         if "b200" not in mangled:
             continue
