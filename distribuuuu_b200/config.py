@@ -236,7 +236,8 @@ _C.B200 = CN()
 _C.B200.DEVICE = "auto"
 # "auto": nccl on cuda, gloo on cpu. Reference hard-codes nccl (utils.py:19).
 _C.B200.DIST_BACKEND = "auto"
-# compute dtype of the native path: "bf16" (tcgen05) or "fp32" (reference semantics)
+# compute dtype: "bf16" = native tcgen05 kernels with fp32 master weights; "fp32" = reference semantics, which
+# B200.ENGINE=auto routes to the torch engine (the native engine has no fp32 compute path)
 _C.B200.PRECISION = "bf16"
 # "native": sm_100a kernels + peer-memory collectives; "torch": reference-semantics path
 # (torch ops + bucketed all_reduce). "auto" = native on cuda, torch on cpu.

@@ -404,7 +404,7 @@ void dw_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64_t
 struct PeerState {
   int world = 1, rank = 0, slot_base = 0;
   std::vector<int64_t> signal_pads, sym_bufs;
-  int64_t ticket = 0;
+  int64_t ticket = 0, mc_stats = 0, reduced = 0, ready = 0, wait_ns = 0;
   uint32_t epoch = 0;
   PeerCtx make() {
     PeerCtx c{};
@@ -418,6 +418,11 @@ struct PeerState {
       c.epoch = ++epoch;
     }
     c.ticket = reinterpret_cast<int*>(ticket);
+    c.mc_stats = reinterpret_cast<float*>(mc_stats);
+    c.reduced = reinterpret_cast<float*>(reduced);
+    c.ready = reinterpret_cast<uint32_t*>(ready);
+    c.wait_ns = reinterpret_cast<unsigned long long*>(wait_ns);
+    if (world > 1) TORCH_CHECK(reduced != 0 && ready != 0, "PeerState needs the `reduced` scratch and the `ready` flag");
     return c;
   }
 };
@@ -653,6 +658,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("world", &PeerState::world).def_readwrite("rank", &PeerState::rank)
       .def_readwrite("slot_base", &PeerState::slot_base).def_readwrite("signal_pads", &PeerState::signal_pads)
       .def_readwrite("sym_bufs", &PeerState::sym_bufs).def_readwrite("ticket", &PeerState::ticket)
+      .def_readwrite("mc_stats", &PeerState::mc_stats).def_readwrite("reduced", &PeerState::reduced)
+      .def_readwrite("ready", &PeerState::ready).def_readwrite("wait_ns", &PeerState::wait_ns)
       .def_readwrite("epoch", &PeerState::epoch);
   py::class_<CommState>(m, "CommState")
       .def(py::init<>())

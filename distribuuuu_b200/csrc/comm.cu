@@ -167,31 +167,54 @@ __global__ void __launch_bounds__(256, 4) allreduce_sgd_kernel(AllreduceSgdParam
     b0 = per * c.rank < p.n8 ? per * c.rank : p.n8;
     b1 = b0 + per < p.n8 ? b0 + per : p.n8;
   }
-  for (long long i = b0 + tid; i < b1; i += nthreads) {
-    const long long v = p.off8 + i;
-    F8 g;
+  // four 16-byte reductions in flight per thread: one NVLink round trip (~2 us) per multimem.ld_reduce made the
+  // single-load loop latency-bound (305 GB/s bus on 12 MiB buckets in round 1)
+  constexpr int U = 4;
+  for (long long i0 = b0 + tid; i0 < b1; i0 += U * nthreads) {
+    uint4 raw[U];
     if (c.mc_stage != nullptr) {
-      g = unpack8(multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(c.mc_stage) + v));
-    } else {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
-      for (int r = 0; r < c.world; ++r) {
-        const F8 t = unpack8(reinterpret_cast<const uint4*>(c.stage[r])[v]);  // P2P load over NVLink
-#pragma unroll
-        for (int k = 0; k < 8; ++k) g.v[k] += t.v[k];
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * nthreads;
+        if (i < b1) raw[u] = multimem_ld_reduce_bf16x8(reinterpret_cast<const uint4*>(c.mc_stage) + p.off8 + i);
       }
     }
-    F8 w = ld_f8(p.master + v * 8), m = ld_f8(p.mom + v * 8);
-    sgd_math(w, m, g, p.hyper);
-    st_f8(p.master + v * 8, w);
-    st_f8(p.mom + v * 8, m);
-    const uint4 wb = pack8(w);
-    if (p.one_shot) {
-      reinterpret_cast<uint4*>(c.w16[c.rank])[v] = wb;
-    } else if (c.mc_w16 != nullptr) {
-      multimem_st_16B(reinterpret_cast<uint4*>(c.mc_w16) + v, wb);              // in-switch broadcast
-    } else {
-      for (int r = 0; r < c.world; ++r) reinterpret_cast<uint4*>(c.w16[r])[v] = wb;  // P2P stores
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const long long i = i0 + u * nthreads;
+      if (i >= b1) break;
+      const long long v = p.off8 + i;
+      F8 g;
+      if (c.mc_stage != nullptr) {
+        g = unpack8(raw[u]);
+      } else {
+        uint4 t[kCommMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kCommMaxPeers; ++r)      // P2P loads over NVLink, all issued before the first add
+          if (r < c.world) t[r] = reinterpret_cast<const uint4*>(c.stage[r])[v];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) g.v[k] = 0.f;
+#pragma unroll
+        for (int r = 0; r < kCommMaxPeers; ++r) {
+          if (r < c.world) {
+            const F8 f = unpack8(t[r]);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) g.v[k] += f.v[k];
+          }
+        }
+      }
+      F8 w = ld_f8(p.master + v * 8), m = ld_f8(p.mom + v * 8);
+      sgd_math(w, m, g, p.hyper);
+      st_f8(p.master + v * 8, w);
+      st_f8(p.mom + v * 8, m);
+      const uint4 wb = pack8(w);
+      if (p.one_shot) {
+        reinterpret_cast<uint4*>(c.w16[c.rank])[v] = wb;
+      } else if (c.mc_w16 != nullptr) {
+        multimem_st_16B(reinterpret_cast<uint4*>(c.mc_w16) + v, wb);              // in-switch broadcast
+      } else {
+        for (int r = 0; r < c.world; ++r) reinterpret_cast<uint4*>(c.w16[r])[v] = wb;  // P2P stores
+      }
     }
   }
   rank_barrier(c, p.epoch + 2);

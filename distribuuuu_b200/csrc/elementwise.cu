@@ -60,55 +60,110 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   return v;
 }
 
-__device__ void peer_exchange_wait(const PeerCtx& pc) {
-  // One CTA (the first to take a ticket) announces; every CTA waits.
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// in-switch (NVLS) sum over every rank's copy of 4 consecutive floats of the symmetric statistics buffer
+__device__ __forceinline__ float4 multimem_ld_reduce_f32x4(const float* mc_addr) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(mc_addr)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+// Cross-rank reduction of one layer's [2][C] statistics, once per launch instead of once per CTA:
+//   * the first CTA to take a ticket is the *designated* CTA: it tells every peer "my statistics for exchange
+//     #epoch are final" (flags on the signal pads), waits for the peers' flags, sums the statistics of all ranks
+//     -- ONE multimem.ld_reduce per 16 bytes (the NVSwitch adds the eight copies), or P2P loads from every peer
+//     issued back to back when there is no multicast mapping -- into the local `reduced` scratch and releases a
+//     device-local flag;
+//   * every other CTA only spins on that local flag (its activation loads are already in flight) and then reads
+//     `reduced` from L2.
+// Round 1 had every CTA poll all peer flags and then do `world` dependent P2P loads per thread (592 CTAs x 8 peers
+// per launch, ~40 us per exchange at 8 GPUs); this is one NVLink round trip issued by 256 threads.
+__device__ void peer_exchange_reduce(const PeerCtx& pc, long long sym_offset, int C) {
   __shared__ int s_ticket;
-  if (threadIdx.x == 0 && threadIdx.y == 0) s_ticket = atomicAdd(pc.ticket, 1);
-  __syncthreads();
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
-  if (s_ticket == 0 && tid < pc.world) {
-    __threadfence_system();
-    st_release_sys(pc.signal_pads[tid] + pc.slot_base + pc.rank, pc.epoch);
-  }
-  if (tid < pc.world) {
-    const uint32_t* flag = pc.signal_pads[pc.rank] + pc.slot_base + tid;
-    long long t0 = clock64();
-    while ((int)(ld_acquire_sys(flag) - pc.epoch) < 0) {
-      if (clock64() - t0 > B200_SPIN_LIMIT_CYCLES * 4) {
-        printf("b200: peer exchange timed out (rank %d waiting for %d, epoch %u)\n", pc.rank, tid, pc.epoch);
-        __trap();
+  const int nthreads = blockDim.x * blockDim.y;
+  if (tid == 0) s_ticket = atomicAdd(pc.ticket, 1);
+  __syncthreads();
+  if (s_ticket == 0) {
+    unsigned long long t_begin = 0;
+    if (tid == 0 && pc.wait_ns) t_begin = global_timer_ns();
+    if (tid < pc.world) {
+      __threadfence_system();
+      st_release_sys(pc.signal_pads[tid] + pc.slot_base + pc.rank, pc.epoch);
+      const uint32_t* flag = pc.signal_pads[pc.rank] + pc.slot_base + tid;
+      long long t0 = clock64();
+      while ((int)(ld_acquire_sys(flag) - pc.epoch) < 0) {
+        if (clock64() - t0 > B200_SPIN_LIMIT_CYCLES * 20) {
+          printf("b200: peer exchange timed out (rank %d waiting for %d, epoch %u)\n", pc.rank, tid, pc.epoch);
+          __trap();
+        }
       }
     }
+    __syncthreads();
+    const int nvec = C / 2;                        // float4 vectors in [2][C]
+    if (pc.mc_stats != nullptr) {
+      for (int i = tid; i < nvec; i += nthreads)
+        reinterpret_cast<float4*>(pc.reduced)[i] = multimem_ld_reduce_f32x4(pc.mc_stats + sym_offset + 4 * (long long)i);
+    } else {
+      for (int i = tid; i < nvec; i += nthreads) {
+        float4 v[kMaxPeers];
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)          // all peers' loads are in flight before the first add
+          if (r < pc.world) v[r] = reinterpret_cast<const float4*>(pc.sym_bufs[r] + sym_offset)[i];
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kMaxPeers; ++r)
+          if (r < pc.world) { acc.x += v[r].x; acc.y += v[r].y; acc.z += v[r].z; acc.w += v[r].w; }
+        reinterpret_cast<float4*>(pc.reduced)[i] = acc;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release_gpu(pc.ready, pc.epoch);
+      if (pc.wait_ns) atomicAdd(pc.wait_ns, global_timer_ns() - t_begin);
+    }
+  } else {
+    if (tid == 0) {
+      long long t0 = clock64();
+      while ((int)(ld_acquire_gpu(pc.ready) - pc.epoch) < 0) {
+        if (clock64() - t0 > B200_SPIN_LIMIT_CYCLES * 24) { printf("b200: SyncBN local release timed out\n"); __trap(); }
+      }
+    }
+    __syncthreads();
   }
-  __syncthreads();
   // last CTA out resets the ticket for the next launch that uses it
-  if (threadIdx.x == 0 && threadIdx.y == 0) {
+  if (tid == 0) {
     int done = atomicAdd(pc.ticket + 1, 1);
     if (done == (int)(gridDim.x * gridDim.y) - 1) { pc.ticket[0] = 0; pc.ticket[1] = 0; __threadfence(); }
   }
 }
 
-// Sum the [2][C] statistics of this thread's 8 channels over all ranks (local only when world == 1).
+// The [2][C] statistics of this thread's 8 channels: the local sums when world == 1, else the cross-rank sums the
+// designated CTA published (L2 loads: another CTA of this launch wrote them).
 __device__ __forceinline__ void gather_stats(const PeerCtx& pc, const float* local, long long sym_offset, int C, int c0,
                                              float (&s0)[8], float (&s1)[8]) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) { s0[i] = 0.f; s1[i] = 0.f; }
-  if (pc.world <= 1) {
-    const float4* a = reinterpret_cast<const float4*>(local + c0);
-    const float4* b = reinterpret_cast<const float4*>(local + C + c0);
-    float4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
-    s0[0] = a0.x; s0[1] = a0.y; s0[2] = a0.z; s0[3] = a0.w; s0[4] = a1.x; s0[5] = a1.y; s0[6] = a1.z; s0[7] = a1.w;
-    s1[0] = b0.x; s1[1] = b0.y; s1[2] = b0.z; s1[3] = b0.w; s1[4] = b1.x; s1[5] = b1.y; s1[6] = b1.z; s1[7] = b1.w;
-    return;
-  }
-  for (int r = 0; r < pc.world; ++r) {
-    const float* base = pc.sym_bufs[r] + sym_offset;  // peer pointer: this is a load over NVLink for r != rank
-    const float4* a = reinterpret_cast<const float4*>(base + c0);
-    const float4* b = reinterpret_cast<const float4*>(base + C + c0);
-    float4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
-    s0[0] += a0.x; s0[1] += a0.y; s0[2] += a0.z; s0[3] += a0.w; s0[4] += a1.x; s0[5] += a1.y; s0[6] += a1.z; s0[7] += a1.w;
-    s1[0] += b0.x; s1[1] += b0.y; s1[2] += b0.z; s1[3] += b0.w; s1[4] += b1.x; s1[5] += b1.y; s1[6] += b1.z; s1[7] += b1.w;
-  }
+  const float* base = (pc.world <= 1) ? local : pc.reduced;
+  const float4* a = reinterpret_cast<const float4*>(base + c0);
+  const float4* b = reinterpret_cast<const float4*>(base + C + c0);
+  const float4 a0 = __ldcg(a), a1 = __ldcg(a + 1), b0 = __ldcg(b), b1 = __ldcg(b + 1);
+  s0[0] = a0.x; s0[1] = a0.y; s0[2] = a0.z; s0[3] = a0.w; s0[4] = a1.x; s0[5] = a1.y; s0[6] = a1.z; s0[7] = a1.w;
+  s1[0] = b0.x; s1[1] = b0.y; s1[2] = b0.z; s1[3] = b0.w; s1[4] = b1.x; s1[5] = b1.y; s1[6] = b1.z; s1[7] = b1.w;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -150,7 +205,7 @@ __global__ void __launch_bounds__(256, 2) bn_apply_kernel(BnApplyParams p) {
   long long r_issue = row0;
 #pragma unroll
   for (int st = 0; st < D - 1; ++st) { issue(st, r_issue); r_issue += rstride; }
-  if (p.peer.world > 1 && p.training) peer_exchange_wait(p.peer);
+  if (p.peer.world > 1 && p.training) peer_exchange_reduce(p.peer, p.sym_offset, p.C);
   if (!active) { cp_async_wait<0>(); return; }
   float scale[8], shift[8];
   {
@@ -439,7 +494,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdParams p) {
   long long k_issue = k0;
 #pragma unroll
   for (int st = 0; st < D - 1; ++st) { issue(st, k_issue, mq[st], true); k_issue += rstride; }
-  if (p.peer.world > 1) peer_exchange_wait(p.peer);
+  if (p.peer.world > 1) peer_exchange_reduce(p.peer, p.sym_offset, p.C);
   if (!active) { cp_async_wait<0>(); return; }
   // dy = (dz - mean(dz) - xhat*mean(dz*xhat)) * gamma*invstd  ==  dz*scale + y*ca + cb
   float scale[8], shift[8], ca[8], cb[8];

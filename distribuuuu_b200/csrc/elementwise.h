@@ -18,6 +18,10 @@ struct PeerCtx {
   uint32_t* signal_pads[kMaxPeers]; // signal pad of every rank
   float* sym_bufs[kMaxPeers];       // statistics buffer of every rank
   int* ticket;                      // [2] local ints: arrival ticket / departure counter
+  float* mc_stats;                  // NVLS multicast alias of the statistics buffers (nullptr: P2P loads from every peer)
+  float* reduced;                   // local scratch [2][C]: the cross-rank sums published by the designated CTA
+  uint32_t* ready;                  // local flag: `reduced` holds exchange #epoch
+  unsigned long long* wait_ns;      // optional: accumulated ns the designated CTA spent in the exchange (profiling)
 };
 
 // per-channel affine applied to raw uint8 pixels by the stem im2col: v * scale[c] + bias[c]  (= (v/255 - mean) / std)

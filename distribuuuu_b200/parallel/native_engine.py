@@ -14,7 +14,12 @@ What replaces what (reference call sites -> here):
 * ``optimizer.zero_grad()`` (trainer.py:45; G14)                 -> folded into the same kernel.
 * ``nn.SyncBatchNorm`` all_gather / all_reduce per layer (K5/K6) -> statistics exchanged by P2P loads inside
   the BN kernels (``csrc/elementwise.cu``), one flag exchange per layer per direction.
-* per-iteration DDP buffer broadcast (K3)                        -> dropped: running statistics stay local.
+* per-iteration DDP buffer broadcast (K3)                        -> not per iteration: with SyncBN the running
+  statistics are identical on every rank by construction; without it ``sync_buffers()`` broadcasts rank 0's
+  before every validation / checkpoint, which is where the reference's broadcast becomes observable.
+* parameters that are frozen (``requires_grad=False``) when the engine is built are kept out of the fused update,
+  like ``torch.optim.SGD`` skips them; a *trainable* parameter that receives no gradient in some step still gets
+  weight decay and momentum applied (the fused kernel runs over whole flat ranges) -- documented difference.
 
 Checkpoints stay reference-compatible: ``module.state_dict()`` reads fp32 views of the flat master and
 ``FusedSGD.state_dict()`` emits ``torch.optim.SGD`` format (sharded state is gathered first).
@@ -141,13 +146,31 @@ class NativeEngine(nn.Module):
 
     # ------------------------------------------------------------------------------ storage
     def _build_flat_storage(self):
+        """Flat layout = [trainable weights with >= 2 dims | trainable 1-D parameters | frozen parameters], each
+        region in registration order.
+
+        Why the 1-D parameters (BN gamma/beta, biases) have their own region: the BN and bias kernels consume them
+        in fp32 straight from the master buffer, and a two-shot bucket only keeps the *owner's* shard of the master
+        up to date (every rank gets the new bf16 weights, not the fp32 ones).  Their region is therefore covered
+        by one-shot buckets, where every rank reduces the whole bucket and updates its full fp32 replica.
+        Frozen parameters (``requires_grad=False`` when the engine is built) sit past ``trainable_total`` and are
+        never touched by the fused update -- ``torch.optim.SGD`` skips them too."""
         self.params = [p for p in self.module.parameters()]
+        trainable = [p for p in self.params if p.requires_grad]
+        self._region_big = [p for p in trainable if p.dim() >= 2]
+        self._region_1d = [p for p in trainable if p.dim() < 2]
+        frozen = [p for p in self.params if not p.requires_grad]
         self.index: Dict[nn.Parameter, tuple] = {}
         off = 0
-        for p in self.params:
-            self.index[p] = (off, p.numel())
-            off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
-        self.total = off
+        for region in (self._region_big, self._region_1d, frozen):
+            for p in region:
+                self.index[p] = (off, p.numel())
+                off += (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN
+            if region is self._region_big:
+                self.big_total = off
+            elif region is self._region_1d:
+                self.trainable_total = off
+        self.total = max(off, _ALIGN)
         dev = self.device
         self.flat_master = torch.zeros(self.total, dtype=torch.float32, device=dev)
         self.flat_mom = torch.zeros(self.total, dtype=torch.float32, device=dev)
@@ -315,6 +338,15 @@ class NativeEngine(nn.Module):
             ps.signal_pads = [p + layout["flags"] for p in ptrs]
             ps.sym_bufs = [p + layout["stats"] for p in ptrs]
             ps.ticket = self._local_sync[8:].data_ptr()
+            # SyncBN: one designated CTA per BN launch reduces the layer's statistics over all ranks (in the switch
+            # when the buffer has a multicast mapping) into `reduced` and releases `ready`; the rest read it locally
+            max_c = max([m.num_features for m in self.bn_offsets] + [8])
+            self._bn_reduced = torch.zeros(2 * max_c, dtype=torch.float32, device=dev)
+            self.syncbn_wait_ns = torch.zeros(1, dtype=torch.int64, device=dev)
+            ps.mc_stats = mc + layout["stats"] if mc else 0
+            ps.reduced = self._bn_reduced.data_ptr()
+            ps.ready = self._local_sync[12:].data_ptr()
+            ps.wait_ns = self.syncbn_wait_ns.data_ptr()
             self.peer_state = ps
             self.has_multicast = bool(mc)
             dist.barrier()
@@ -323,33 +355,41 @@ class NativeEngine(nn.Module):
                             f"symmetric bytes={nbytes}")
 
     def _plan_buckets(self, cap_bytes: int):
-        """Contiguous flat ranges in reverse parameter order (the order gradients become ready); first bucket 1 MiB."""
+        """Contiguous flat ranges in reverse parameter order (the order gradients become ready); first bucket 1 MiB.
+        The 1-D region is cut into one-shot buckets (see ``_build_flat_storage``)."""
         self.buckets: List[_Bucket] = []
         self.bucket_of: Dict[nn.Parameter, _Bucket] = {}
-        cap = 1 << 20
-        cur: List[nn.Parameter] = []
-        cur_bytes = 0
 
-        def close():
-            nonlocal cur, cur_bytes, cap
-            if not cur:
-                return
-            lo = self.index[cur[-1]][0]
-            last_off, last_n = self.index[cur[0]]
-            hi = (last_off + last_n + _ALIGN - 1) // _ALIGN * _ALIGN
-            b = _Bucket(off=lo, n=hi - lo, params=list(cur), one_shot=(hi - lo) * 2 <= _ONE_SHOT_BYTES)
-            for p in cur:
-                self.bucket_of[p] = b
-            self.buckets.append(b)
-            cur, cur_bytes, cap = [], 0, cap_bytes
+        def plan(region, first_cap, cap, force_one_shot):
+            cur: List[nn.Parameter] = []
+            cur_bytes = 0
+            limit = first_cap
 
-        for p in reversed(self.params):
-            nbytes = p.numel() * 4
-            if cur and cur_bytes + nbytes > cap:
-                close()
-            cur.append(p)
-            cur_bytes += nbytes
-        close()
+            def close():
+                nonlocal cur, cur_bytes, limit
+                if not cur:
+                    return
+                lo = self.index[cur[-1]][0]
+                last_off, last_n = self.index[cur[0]]
+                hi = (last_off + last_n + _ALIGN - 1) // _ALIGN * _ALIGN
+                b = _Bucket(off=lo, n=hi - lo, params=list(cur),
+                            one_shot=force_one_shot or (hi - lo) * 2 <= _ONE_SHOT_BYTES)
+                for q in cur:
+                    self.bucket_of[q] = b
+                self.buckets.append(b)
+                cur, cur_bytes, limit = [], 0, cap
+
+            for p in reversed(region):
+                nbytes = (p.numel() + _ALIGN - 1) // _ALIGN * _ALIGN * 4
+                if cur and cur_bytes + nbytes > limit:
+                    close()
+                cur.append(p)
+                cur_bytes += nbytes
+            close()
+
+        plan(self._region_big, 1 << 20, cap_bytes, False)
+        # one-shot buckets are bounded by the bf16 staging footprint (_ONE_SHOT_BYTES), i.e. 2x that in fp32 bytes
+        plan(self._region_1d, 2 * _ONE_SHOT_BYTES, 2 * _ONE_SHOT_BYTES, True)
         self._reset_pending()
 
     def _reset_pending(self):
@@ -362,6 +402,24 @@ class NativeEngine(nn.Module):
             for buf in self.module.buffers():
                 dist.broadcast(buf, src=0)
         self.refresh_compute_weights()
+
+    @torch.no_grad()
+    def sync_buffers(self):
+        """Rank 0's buffers (BN running statistics) win -- what reference DDP's ``broadcast_buffers`` does on the
+        first eval forward after training (trainer.py:134).  Called by ``validate`` so that the logged accuracy is
+        the accuracy of the checkpoint rank 0 writes; with SyncBN the statistics are identical already and the
+        broadcast is a no-op in effect."""
+        if self.world == 1:
+            return
+        bufs = [b for b in self.module.buffers() if b.is_floating_point() and b.numel()]
+        if not bufs:
+            return
+        flat = torch.cat([b.reshape(-1).float() for b in bufs])
+        dist.broadcast(flat, src=0)
+        off = 0
+        for b in bufs:
+            b.copy_(flat[off:off + b.numel()].view(b.shape))
+            off += b.numel()
 
     def refresh_compute_weights(self):
         self.K.cast_bf16(self.flat_master, self.flat_w16)
@@ -459,8 +517,9 @@ class NativeEngine(nn.Module):
             torch._foreach_add_(self._bn_stepped, 1)
         lr, mom, damp, wd, nest, first = optimizer.hyper()
         if self.world == 1 or self.debug_skip_comm:
-            self.K.sgd_local(self.flat_master, self.flat_mom, self.flat_grad, self.flat_w16, 0, self.total,
-                             lr, mom, damp, wd, nest, first, 1.0, True)
+            if self.trainable_total:
+                self.K.sgd_local(self.flat_master, self.flat_mom, self.flat_grad, self.flat_w16, 0,
+                                 self.trainable_total, lr, mom, damp, wd, nest, first, 1.0, True)
         else:
             for b in self.buckets:  # parameters that produced no gradient this step still take part
                 if b.pending > 0:

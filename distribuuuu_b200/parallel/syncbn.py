@@ -5,7 +5,7 @@ Parity: reference ``trainer.py:131`` converts every BatchNorm to
 and issues one all_gather (fwd) + one all_reduce (bwd) per layer.  This
 implementation reduces ``[sum, sum_sq, count]`` with a single all_reduce per direction, so
 it also serves the CPU/gloo configuration; the native engine replaces it with the
-peer-memory kernel (``csrc/syncbn.cu``).  State-dict keys equal ``nn.BatchNorm2d``'s.
+peer-memory exchange inside the BN kernels (``csrc/elementwise.cu``: ``peer_exchange_reduce``).  State-dict keys equal ``nn.BatchNorm2d``'s.
 """
 from __future__ import annotations
 

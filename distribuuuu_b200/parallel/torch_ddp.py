@@ -103,6 +103,13 @@ class BucketedDataParallel(nn.Module):
                 b.copy_(flat[off:off + b.numel()].view(b.shape))
                 off += b.numel()
 
+    def sync_buffers(self):
+        """Make every rank evaluate / checkpoint with rank 0's buffers.  Reference DDP does this implicitly on the
+        first eval forward after training (``require_forward_param_sync`` is still set, trainer.py:134), so the
+        accuracy it logs is reproducible from the checkpoint rank 0 writes."""
+        self._sync_buffers()
+        self._need_buffer_sync = False
+
     # -- gradient path ------------------------------------------------------------------
     def _on_grad_ready(self, p: nn.Parameter):
         b, i = self._where[p]

@@ -60,10 +60,17 @@ class TorchEngine(BucketedDataParallel):
 
 def _select_engine(device: torch.device) -> str:
     choice = cfg.B200.ENGINE
+    precision = str(cfg.B200.PRECISION).lower()
+    if precision not in ("bf16", "fp32"):
+        raise ValueError(f"B200.PRECISION must be 'bf16' or 'fp32', got {cfg.B200.PRECISION!r}")
     if choice == "auto":
-        choice = "native" if device.type == "cuda" else "torch"
+        # the native kernels compute in bf16 (fp32 masters); fp32 compute is the reference-semantics torch path
+        choice = "native" if (device.type == "cuda" and precision == "bf16") else "torch"
     if choice == "native" and device.type != "cuda":
         raise RuntimeError("B200.ENGINE=native requires a CUDA device")
+    if choice == "native" and precision != "bf16":
+        raise ValueError("B200.ENGINE=native computes in bf16; use B200.PRECISION=bf16, or B200.ENGINE=torch/auto "
+                         "for fp32 compute")
     return choice
 
 
@@ -155,6 +162,8 @@ def validate(val_loader, engine, device=None):
     batch_time, data_time, losses, top1, topk = utils.construct_meters()
     n_iters = len(val_loader) if not cfg.B200.MAX_ITERS else min(len(val_loader), cfg.B200.MAX_ITERS)
     progress = utils.ProgressMeter(n_iters, [batch_time, data_time, losses, top1, topk], prefix="VAL:  ")
+    if hasattr(engine, "sync_buffers"):
+        engine.sync_buffers()   # every rank validates (and rank 0 checkpoints) the same running statistics
     engine.eval()
     metrics = utils.DeviceMetrics(device)
     sync_freq = max(int(cfg.B200.METRIC_SYNC_FREQ), 1)
@@ -221,11 +230,16 @@ def train_model():
     tic = time.time()
     acc1 = acck = 0.0
     for epoch in range(start_epoch, cfg.OPTIM.MAX_EPOCH):
+        # Host-side rendezvous before any peer-memory kernel of the epoch is launched: the device-side waits of the
+        # native engine are bounded (they trap instead of hanging the GPU), so skew from a slow checkpoint write or
+        # a stalled loader has to be absorbed here, under the process group's DIST_TIMEOUT.
+        utils.barrier()
         train_epoch(train_loader, engine, optimizer, epoch, start_epoch, tic, device)
         acc1, acck = validate(val_loader, engine, device)
         is_best = acc1 > best_acc1
         best_acc1 = max(acc1, best_acc1)
         checkpoint_file = utils.save_checkpoint(engine, optimizer, epoch, best_acc1, is_best)
+        utils.barrier()         # nobody starts the next epoch's peer kernels while rank 0 is still writing
         if rank == 0:
             logger.info(f"ACCURACY: TOP1 {acc1:.3f}(BEST {best_acc1:.3f}) | "
                         f"TOP{cfg.TRAIN.TOPK} {acck:.3f} | SAVED {checkpoint_file}")

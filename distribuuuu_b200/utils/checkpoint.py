@@ -36,7 +36,8 @@ def _list_checkpoints():
     d = get_checkpoint_dir()
     if not os.path.isdir(d):
         return []
-    return sorted(f for f in os.listdir(d) if _NAME_PREFIX in f)
+    # complete files only: a crash during a save leaves ``.<name>.tmp`` behind, which must never be resumed from
+    return sorted(f for f in os.listdir(d) if f.startswith(_NAME_PREFIX) and f.endswith(".pth.tar"))
 
 
 def get_last_checkpoint() -> str:
@@ -67,6 +68,14 @@ def _cpu_state_dict(model) -> dict:
             for k, v in unwrap_model(model).state_dict().items()}
 
 
+def _atomic_save(obj, path: str):
+    """Write to a hidden temporary name (no ``ckpt_ep_`` prefix, so AUTO_RESUME never sees it) and rename."""
+    d, name = os.path.split(path)
+    tmp = os.path.join(d, f".{name}.tmp")
+    torch.save(obj, tmp)
+    os.replace(tmp, path)
+
+
 def save_checkpoint(model, optimizer, epoch: int, best_acc1: float, best: bool):
     """Rank 0 writes ``ckpt_ep_{epoch+1:03d}`` (+ ``best.pth.tar``); others return None.
 
@@ -79,11 +88,9 @@ def save_checkpoint(model, optimizer, epoch: int, best_acc1: float, best: bool):
     os.makedirs(get_checkpoint_dir(), exist_ok=True)
     state = _cpu_state_dict(model)
     path = get_checkpoint(epoch + 1)
-    tmp = path + ".tmp"
-    torch.save({"epoch": epoch, "state_dict": state, "optimizer": opt_state, "best_acc1": best_acc1}, tmp)
-    os.replace(tmp, path)
+    _atomic_save({"epoch": epoch, "state_dict": state, "optimizer": opt_state, "best_acc1": best_acc1}, path)
     if best:
-        torch.save(state, os.path.join(cfg.OUT_DIR, "best.pth.tar"))
+        _atomic_save(state, os.path.join(cfg.OUT_DIR, "best.pth.tar"))
     return path
 
 

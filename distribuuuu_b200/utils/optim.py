@@ -3,7 +3,7 @@
 Parity: reference ``utils.py:187-196`` -- Nesterov SGD over a single parameter group
 (weight decay on every parameter, BN and bias included).  On the reference-semantics
 path this is ``torch.optim.SGD``; the native engine substitutes
-``parallel.fused_sgd.FusedSGD``, which exposes the same ``param_groups`` /
+``parallel.native_engine.FusedSGD``, which exposes the same ``param_groups`` /
 ``state_dict`` / ``load_state_dict`` surface.
 """
 from __future__ import annotations

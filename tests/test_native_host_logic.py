@@ -42,13 +42,43 @@ def test_buckets_cover_all_parameters_in_reverse_order():
     net = build_model("resnet50")
     eng = _HostEngine(net)
     eng._plan_buckets(25 * 1024 * 1024)
-    assert (eng.buckets[0].n * 4) <= (1 << 20) + 4 * 2048 * 1000        # first bucket ~1 MiB (fc bias + ...)
+    assert (eng.buckets[0].n * 4) <= (1 << 20) + 4 * 2048 * 1000        # first bucket ~1 MiB (fc weight + ...)
     covered = sorted((b.off, b.off + b.n) for b in eng.buckets)
-    assert covered[0][0] == 0 and covered[-1][1] == eng.total
+    assert covered[0][0] == 0 and covered[-1][1] == eng.trainable_total == eng.total
     assert all(a[1] == b[0] for a, b in zip(covered, covered[1:]))      # contiguous, non-overlapping
-    assert eng.buckets[0].params[0] is eng.params[-1]                    # gradients become ready last-layer first
+    assert eng.buckets[0].params[0] is net.fc.weight                     # gradients become ready last-layer first
     assert sum(len(b.params) for b in eng.buckets) == len(eng.params)
     assert all(b.n % 8 == 0 and b.off % 8 == 0 for b in eng.buckets)    # 16-byte vectors in the fused kernel
+
+
+def test_one_dimensional_parameters_live_in_one_shot_buckets():
+    """BN gamma/beta and biases are consumed in fp32 from the master buffer by the BN / bias kernels, and only a
+    one-shot bucket keeps every rank's fp32 replica current (a two-shot bucket updates the owner's shard and
+    broadcasts bf16) -- so no 1-D parameter may ever share a two-shot bucket."""
+    for arch in ("resnet50", "regnety_160", "efficientnet_b0"):
+        net = build_model(arch)
+        eng = _HostEngine(net)
+        eng._plan_buckets(25 * 1024 * 1024)
+        for p in eng.params:
+            b = eng.bucket_of[p]
+            if p.dim() < 2:
+                assert b.one_shot and b.n * 2 <= 2 * 512 * 1024 + 128, (arch, b.n)
+                assert eng.index[p][0] >= eng.big_total
+            else:
+                assert eng.index[p][0] < eng.big_total
+        assert any(not b.one_shot for b in eng.buckets)                  # the conv weights still go two-shot
+
+
+def test_frozen_parameters_are_outside_the_fused_update_range():
+    net = build_model("resnet18", num_classes=10)
+    for p in net.layer1.parameters():
+        p.requires_grad_(False)
+    eng = _HostEngine(net)
+    eng._plan_buckets(25 * 1024 * 1024)
+    frozen = [p for p in eng.params if not p.requires_grad]
+    assert frozen and all(eng.index[p][0] >= eng.trainable_total for p in frozen)
+    assert all(p not in eng.bucket_of for p in frozen)
+    assert max(b.off + b.n for b in eng.buckets) == eng.trainable_total < eng.total
 
 
 def test_fused_sgd_state_dict_is_torch_sgd_compatible():
