@@ -41,7 +41,8 @@ def parse_args():
                     help="dtype of the pinned host batches of the end-to-end run: uint8 = raw pixels normalised in the stem "
                          "kernel (B200.INPUT_UINT8, the framework's real-data path); fp32 = host-normalised images (what the "
                          "reference's loader yields); both = uint8 is reported as e2e, fp32 as e2e_fp32_input")
-    ap.add_argument("--exposed", action="store_true", help="also time the step with the gradient exchange disabled and report the exposed all-reduce ms/step")
+    ap.add_argument("--exposed", action="store_true", help="(kept for compatibility) the multi-GPU attribution runs -- step without gradient exchange, step without SyncBN -- are now always done when N > 1")
+    ap.add_argument("--attr-steps", type=int, default=10, help="steps of each multi-GPU attribution run (N > 1)")
     return ap.parse_args()
 
 
@@ -184,24 +185,42 @@ def run_ours(args):
     sampler = ClockSampler(local)
     sampler.start()
     counter.count = 0
+    if getattr(eng, "syncbn_wait_ns", None) is not None:
+        eng.syncbn_wait_ns.zero_()
     sec = _timed(dev, step, args.steps)
     launches = counter.count
     clocks = sampler.stop()
     value = world * B * args.steps / sec
 
+    # Multi-GPU attribution (N > 1), outside the timed region above: the same step with (a) the gradient exchange
+    # disabled and (b) SyncBN's cross-rank statistic exchange disabled, plus the device-side counter of the time the
+    # designated CTAs spent inside the SyncBN exchanges during the timed region.
     exposed = None
-    if args.exposed and world > 1:
+    if world > 1:
+        ksteps = max(3, min(args.attr_steps, args.steps))
+        wait_ns = float(eng.syncbn_wait_ns.item()) if getattr(eng, "syncbn_wait_ns", None) is not None else None
+        ms_full = sec * 1e3 / args.steps
         eng.debug_skip_comm = True
         for i in range(2):
             step(i)
-        sec_nocomm = _timed(dev, step, args.steps)
+        ms_nocomm = _timed(dev, step, ksteps) * 1e3 / ksteps
         eng.debug_skip_comm = False
-        eng.refresh_compute_weights()  # ranks diverged during the no-comm loop: restore a consistent state
-        if dist.get_world_size() > 1:
-            dist.broadcast(eng.flat_master, src=0)
-            eng.refresh_compute_weights()
-        exposed = {"ms_per_step_with_comm": sec * 1e3 / args.steps, "ms_per_step_without_comm": sec_nocomm * 1e3 / args.steps,
-                   "exposed_allreduce_ms_per_step": (sec - sec_nocomm) * 1e3 / args.steps}
+        dist.broadcast(eng.flat_master, src=0)   # ranks diverged during the no-comm loop: restore a consistent state
+        eng.refresh_compute_weights()
+        ms_nosync = None
+        if eng.sync_bn:
+            eng.sync_bn = False
+            for i in range(2):
+                step(i)
+            ms_nosync = _timed(dev, step, ksteps) * 1e3 / ksteps
+            eng.sync_bn = True
+            eng.sync_buffers()
+        exposed = {"ms_per_step": ms_full, "ms_per_step_without_grad_exchange": ms_nocomm,
+                   "exposed_allreduce_ms_per_step": ms_full - ms_nocomm,
+                   "ms_per_step_without_syncbn_exchange": ms_nosync,
+                   "syncbn_wait_ms_per_step": (ms_full - ms_nosync) if ms_nosync is not None else None,
+                   "syncbn_exchange_device_ms_per_step": (wait_ns / 1e6 / args.steps) if wait_ns is not None else None,
+                   "attr_steps": ksteps}
 
     e2e = e2e_alt = None
     if not args.skip_e2e:
@@ -241,9 +260,11 @@ def run_ours(args):
                     "h2d_bytes_per_step": hx[0].numel() * hx[0].element_size() + B * 8, "d2h_bytes_per_step": 4,
                     "input": note, "ms_per_step": sec_e2e * 1e3 / args.steps, "last_loss": sink[-1] if sink else None}
 
+        # primary e2e = host-normalised fp32 images, i.e. exactly what the reference arm is fed; the uint8 path (the
+        # framework's own real-data path, 4x fewer PCIe bytes) is reported next to it
         if args.e2e_input == "both":
-            e2e = measure_e2e("uint8")
-            e2e_alt = measure_e2e("fp32")
+            e2e = measure_e2e("fp32")
+            e2e_alt = measure_e2e("uint8")
         else:
             e2e = measure_e2e(args.e2e_input)
     if rank == 0:
@@ -259,9 +280,11 @@ def run_ours(args):
         if e2e is not None:
             out["e2e"] = e2e
         if e2e_alt is not None:
-            out["e2e_fp32_input"] = e2e_alt
+            out["e2e_uint8_input"] = e2e_alt
         if exposed is not None:
-            out["exposed_allreduce"] = exposed
+            out["multi_gpu_attribution"] = exposed
+            out["exposed_allreduce_ms"] = exposed["exposed_allreduce_ms_per_step"]
+            out["syncbn_wait_ms"] = exposed["syncbn_wait_ms_per_step"]
         _emit(out)
     dist.barrier()
     dist.destroy_process_group()
@@ -329,31 +352,49 @@ def run_reference(args):
     dev = torch.device("cuda", local)
     ref_utils.setup_logger(rank, local)
     torch.backends.cudnn.benchmark = rcfg.CUDNN.BENCHMARK
-    net = ref_models.build_model(arch=rcfg.MODEL.ARCH, pretrained=False, num_classes=rcfg.MODEL.NUM_CLASSES)
-    net = nn.SyncBatchNorm.convert_sync_batchnorm(net) if rcfg.MODEL.SYNCBN else net   # trainer.py:131
-    net = net.to(dev)
-    if args.ref_variant == "amp":
-        net = net.to(memory_format=torch.channels_last)
-    net = DDP(net, device_ids=[local], output_device=local)                              # trainer.py:134
-    criterion = nn.CrossEntropyLoss().to(dev)
-    optimizer = ref_utils.construct_optimizer(net)
-
     B, nb = args.batch, args.warmup + args.steps
     torch.manual_seed(100 + rank)
     pool = [(torch.randn(B, 3, 224, 224).pin_memory(), torch.randint(0, 1000, (B,)).pin_memory()) for _ in range(2)]
-    loader = _TimedLoader([pool[i % 2] for i in range(nb)], args.warmup, dev)
-    sampler = ClockSampler(local)
-    loader.on_start = sampler.start
-    if args.ref_variant == "amp":
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            ref_trainer.train_epoch(loader, net, criterion, optimizer, 0, 0, time.time())
-    else:
-        ref_trainer.train_epoch(loader, net, criterion, optimizer, 0, 0, time.time())   # UNMODIFIED hot loop
-    clocks = sampler.stop()
-    ms = torch.tensor([loader.e0.elapsed_time(loader.e1)], device=dev)
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    sec = float(ms.item()) / 1e3
+
+    def run_variant(variant):
+        """The reference's own model / SyncBN conversion / DDP / optimizer / UNMODIFIED train_epoch.  ``amp`` is the
+        precision-matched context arm: the very same loop under bf16 autocast with a channels_last model."""
+        net = ref_models.build_model(arch=rcfg.MODEL.ARCH, pretrained=False, num_classes=rcfg.MODEL.NUM_CLASSES)
+        net = nn.SyncBatchNorm.convert_sync_batchnorm(net) if rcfg.MODEL.SYNCBN else net   # trainer.py:131
+        net = net.to(dev)
+        if variant == "amp":
+            net = net.to(memory_format=torch.channels_last)
+        net = DDP(net, device_ids=[local], output_device=local)                              # trainer.py:134
+        criterion = nn.CrossEntropyLoss().to(dev)
+        optimizer = ref_utils.construct_optimizer(net)
+        loader = _TimedLoader([pool[i % 2] for i in range(nb)], args.warmup, dev)
+        sampler = ClockSampler(local)
+        loader.on_start = sampler.start
+        if variant == "amp":
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                ref_trainer.train_epoch(loader, net, criterion, optimizer, 0, 0, time.time())
+        else:
+            ref_trainer.train_epoch(loader, net, criterion, optimizer, 0, 0, time.time())   # UNMODIFIED hot loop
+        clk = sampler.stop()
+        ms = torch.tensor([loader.e0.elapsed_time(loader.e1)], device=dev)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        sec_ = float(ms.item()) / 1e3
+        del net, optimizer
+        torch.cuda.empty_cache()
+        return sec_, clk
+
+    sec, clocks = run_variant(args.ref_variant)
     value = world * B * args.steps / sec
+    amp = None
+    if args.ref_variant == "stock":
+        # same box, same run: the reference loop at OUR compute precision (context for the headline ratio)
+        try:
+            sec_amp, clocks_amp = run_variant("amp")
+            amp = {"value": world * B * args.steps / sec_amp, "unit": "images/sec", "ms_per_step": sec_amp * 1e3 / args.steps,
+                   "dtype": "bf16 autocast + channels_last", "clocks": clocks_amp,
+                   "note": "the reference's unmodified train_epoch under torch.autocast(bf16); not the reference as written"}
+        except Exception as exc:  # never let the context arm break the stock number
+            amp = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
         out = {"metric": "ResNet-50 training images/sec (whole job, device-timed, max over ranks)", "impl": "reference",
                "variant": args.ref_variant, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
@@ -366,6 +407,8 @@ def run_reference(args):
                "e2e": {"value": value, "unit": "images/sec", "h2d_bytes_per_step": B * 3 * 224 * 224 * 4 + B * 8,
                        "d2h_bytes_per_step": 12, "note": "the reference loop is end-to-end by construction"},
                "clocks": clocks, "gpu_launches": 0}
+        if amp is not None:
+            out["amp"] = amp
         _emit(out)
     dist.barrier()
     dist.destroy_process_group()

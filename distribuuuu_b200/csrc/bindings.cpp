@@ -15,6 +15,7 @@
 #include "conv_gemm.h"
 #include "dwconv.h"
 #include "elementwise.h"
+#include "extras.h"
 
 namespace {
 
@@ -254,51 +255,61 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &mo, &p, bn, grid, cur_stream()));
 }
 
-// ---------------------------------------------------------------------------------------------- conv dgrad (stride 1)
-// dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C].
-void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64_t stride, int64_t pad, int64_t dil,
-                const c10::optional<at::Tensor>& addend, int64_t groups) {
-  check_bf16_contig(dy, "dy"); check_bf16_contig(w, "w"); check_bf16_contig(dx, "dx");
-  TORCH_CHECK(stride == 1, "tcgen05 dgrad handles stride 1 (strided layers use the zero-insertion path)");
-  c10::cuda::CUDAGuard guard(dy.device());
-  const int N = dx.size(0), H = dx.size(1), W = dx.size(2), C = dx.size(3);
-  const int K = w.size(0), R = w.size(1), S = w.size(2);
-  const int P = dy.size(1), Q = dy.size(2);
+// ---------------------------------------------------------------------------------------------- conv dgrad
+// Generic launcher: out [N,Ho,Wo,C] (compact, contiguous) = sum over a virtual Rv x Sv window of dy [N,P,Q,K]:
+//   out[n,a,b,:] = sum_{r',s'} dy[n, a + low_h + r'*dil, b + low_w + s'*dil, :] . W[:, tap(r',s'), :]
+// where tap(r',s') is either the flipped tap (ordinary stride-1 dgrad) or given by a look-up table (one parity
+// class of a strided dgrad).  Reads outside dy are zero-filled by the im2col TMA.
+struct DgradGeom {
+  int Ho, Wo;            // output grid
+  int Rv, Sv;            // virtual window
+  int low_h, low_w;      // offset of window tap 0 relative to the output coordinate
+  int dil;
+  const unsigned char* lut;   // nullptr: flipped taps of the full RxS filter (Rv == R, Sv == S)
+};
+void dgrad_launch(const at::Tensor& dy, const at::Tensor& w, at::Tensor& out, const DgradGeom& gm,
+                  const c10::optional<at::Tensor>& addend, int64_t groups) {
+  const int N = dy.size(0), P = dy.size(1), Q = dy.size(2), K = dy.size(3);
+  const int R = w.size(1), S = w.size(2);
+  const int C = out.size(3);
   const int G = groups, cin_g = C / G, cout_g = K / G;
-  TORCH_CHECK(dy.size(3) == K && w.size(3) == cin_g, "dgrad shape mismatch");
-  TORCH_CHECK(P == H + 2 * pad - dil * (R - 1) && Q == W + 2 * pad - dil * (S - 1), "dgrad: dy spatial size inconsistent");
+  TORCH_CHECK(w.size(0) == K && w.size(3) == cin_g && out.size(0) == N && out.size(1) == gm.Ho && out.size(2) == gm.Wo, "dgrad shape mismatch");
   TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8");
-  const int M = N * H * W;
-  const TilePlan plan = plan_tiles(cin_g, R * S * ((cout_g + 63) / 64), (M + 127) / 128, G, num_sms());
+  const int taps_v = gm.Rv * gm.Sv;
+  TORCH_CHECK(taps_v >= 1 && taps_v <= 25, "virtual window too large");
+  const int M = N * gm.Ho * gm.Wo;
+  const TilePlan plan = plan_tiles(cin_g, taps_v * ((cout_g + 63) / 64), (M + 127) / 128, G, num_sms());
   const int bn = plan.bn;
-  const bool pointwise = (R == 1 && S == 1 && pad == 0);
-  const int padp_h = dil * (R - 1) - pad, padp_w = dil * (S - 1) - pad;  // padding of the transposed problem
+  const bool pointwise = (taps_v == 1 && gm.low_h == 0 && gm.low_w == 0 && gm.Ho == P && gm.Wo == Q);
   ConvGemmParams p{};
   p.b_resident = plan.resident; p.res_stages = plan.res_stages;
   p.kind = KIND_DGRAD; p.epi = EPI_BF16;
   p.M = M; p.N = cin_g;
   p.groups = G; p.a_cg = cout_g; p.out_cg = cin_g;
   p.m_blocks = (M + 127) / 128; p.n_blocks = (cin_g + bn - 1) / bn;
-  p.taps = R * S; p.S = S; p.kb_per_tap = (cout_g + 63) / 64; p.dil = dil;
+  p.taps = taps_v; p.S = gm.Sv; p.kb_per_tap = (cout_g + 63) / 64; p.dil = gm.dil;
   p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
   p.b_im2col = 0; p.b_nbox = bn / 64; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
-  p.b_flip_taps = 1;
+  p.b_flip_taps = gm.lut ? 0 : 1;
+  if (gm.lut) { p.tap_lut_on = 1; for (int t = 0; t < taps_v; ++t) p.tap_lut[t] = gm.lut[t]; }
   p.idesc = idesc_bf16(128, bn, 0, 1);
-  p.im_P = H; p.im_Q = W; p.im_stride = 1; p.im_low_w = -padp_w; p.im_low_h = -padp_h;
+  p.im_P = gm.Ho; p.im_Q = gm.Wo; p.im_stride = 1; p.im_low_w = gm.low_w; p.im_low_h = gm.low_h;
   p.splits = 1;
-  p.out = dx.data_ptr(); p.ldo = C;
+  p.out = out.data_ptr(); p.ldo = C;
   p.total_items = p.m_blocks * p.n_blocks * G;
+  // bounding box of the base pixel: Wo (Ho) positions starting at low  =>  upper corner = Wo - Q + low
   CUtensorMap ma = pointwise ? tiled_map_3d(dy.data_ptr(), K, 1, M, K, K, 64, 1, 128)
-                             : im2col_map_4d(dy.data_ptr(), N, P, Q, K, -padp_w, -padp_h, padp_w - (S - 1) * dil,
-                                             padp_h - (R - 1) * dil, 1, 64, 128);
+                             : im2col_map_4d(dy.data_ptr(), N, P, Q, K, gm.low_w, gm.low_h, gm.Wo - Q + gm.low_w,
+                                             gm.Ho - P + gm.low_h, 1, 64, 128);
   // weights viewed as (C inner, taps, K): MN-major B boxes of [64 k-rows (Cout)][64 n (Cin)]
-  CUtensorMap mb = tiled_map_4d(w.data_ptr(), cin_g, p.taps, cout_g, G, cin_g, (uint64_t)p.taps * cin_g,
-                                (uint64_t)p.taps * cin_g * cout_g, 64, 1, 64, 1);
-  CUtensorMap mo = tiled_map_3d(dx.data_ptr(), cin_g, M, G, C, cin_g, 64, 32, 1);
+  const int taps_w = R * S;
+  CUtensorMap mb = tiled_map_4d(w.data_ptr(), cin_g, taps_w, cout_g, G, cin_g, (uint64_t)taps_w * cin_g,
+                                (uint64_t)taps_w * cin_g * cout_g, 64, 1, 64, 1);
+  CUtensorMap mo = tiled_map_3d(out.data_ptr(), cin_g, M, G, C, cin_g, 64, 32, 1);
   CUtensorMap md = mo;
   if (addend.has_value()) {
     check_bf16_contig(*addend, "addend");
-    TORCH_CHECK(addend->numel() == dx.numel(), "addend must have dx's shape");
+    TORCH_CHECK(addend->numel() == out.numel(), "addend must have dx's shape");
     p.addend = 1;
     p.epi = EPI_BF16_ADD;
     md = tiled_map_3d(addend->data_ptr(), cin_g, M, G, C, cin_g, 64, 32, 1);
@@ -306,6 +317,59 @@ void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64
   int grid = std::min(p.total_items, num_sms());
   if (p.b_resident) grid = (grid / p.n_blocks) * p.n_blocks;
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &md, &p, bn, grid, cur_stream()));
+}
+
+// dy [N,P,Q,K], w [K,R,S,C] -> dx [N,H,W,C], stride 1.
+void conv_dgrad(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64_t stride, int64_t pad, int64_t dil,
+                const c10::optional<at::Tensor>& addend, int64_t groups) {
+  check_bf16_contig(dy, "dy"); check_bf16_contig(w, "w"); check_bf16_contig(dx, "dx");
+  TORCH_CHECK(stride == 1, "conv_dgrad handles stride 1; strided layers go through conv_dgrad_s2");
+  c10::cuda::CUDAGuard guard(dy.device());
+  const int H = dx.size(1), W = dx.size(2);
+  const int R = w.size(1), S = w.size(2);
+  const int P = dy.size(1), Q = dy.size(2);
+  TORCH_CHECK(P == H + 2 * pad - dil * (R - 1) && Q == W + 2 * pad - dil * (S - 1), "dgrad: dy spatial size inconsistent");
+  const int padp_h = dil * (R - 1) - pad, padp_w = dil * (S - 1) - pad;  // padding of the transposed problem
+  DgradGeom gm{H, W, R, S, -padp_h, -padp_w, (int)dil, nullptr};
+  dgrad_launch(dy, w, dx, gm, addend, groups);
+}
+
+// Stride-2 data gradient without zero insertion: dx is split into its four (row parity, column parity) classes; class
+// (ph, pw) only receives the taps r = (ph + pad) mod 2, s = (pw + pad) mod 2 (mod 2), so it is a compact stride-1
+// dgrad over dy with a 1- or 2-wide virtual window -- exactly the real FLOPs (the zero-insertion path of round 1 ran
+// 4x as many) -- and the classes are interleaved into dx by one pass (extras.cu), optionally adding `addend`.
+void conv_dgrad_s2(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, int64_t pad, const c10::optional<at::Tensor>& addend,
+                   int64_t groups) {
+  check_bf16_contig(dy, "dy"); check_bf16_contig(w, "w"); check_bf16_contig(dx, "dx");
+  c10::cuda::CUDAGuard guard(dy.device());
+  const int N = dx.size(0), H = dx.size(1), W = dx.size(2), C = dx.size(3);
+  const int R = w.size(1), S = w.size(2);
+  const int P = dy.size(1), Q = dy.size(2);
+  TORCH_CHECK(P == (H + 2 * pad - R) / 2 + 1 && Q == (W + 2 * pad - S) / 2 + 1, "dgrad_s2: dy spatial size inconsistent");
+  TORCH_CHECK(R <= 5 && S <= 5, "dgrad_s2: filter too large");
+  at::Tensor parts[4];
+  const void* src[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int ph = 0; ph < 2; ++ph) {
+    for (int pw = 0; pw < 2; ++pw) {
+      const int Hc = (H - ph + 1) / 2, Wc = (W - pw + 1) / 2;
+      if (Hc <= 0 || Wc <= 0) continue;
+      // taps of this class, in order of increasing dy offset: r = r_max, r_max - 2, ...
+      int r_max = -1, s_max = -1;
+      for (int r = R - 1; r >= 0; --r) if (((ph + pad - r) & 1) == 0) { r_max = r; break; }
+      for (int sx = S - 1; sx >= 0; --sx) if (((pw + pad - sx) & 1) == 0) { s_max = sx; break; }
+      if (r_max < 0 || s_max < 0) continue;                     // no tap reaches this class: it stays zero
+      const int Rv = r_max / 2 + 1, Sv = s_max / 2 + 1;
+      unsigned char lut[28];
+      for (int rv = 0; rv < Rv; ++rv)
+        for (int sv = 0; sv < Sv; ++sv) lut[rv * Sv + sv] = (unsigned char)((r_max - 2 * rv) * S + (s_max - 2 * sv));
+      DgradGeom gm{Hc, Wc, Rv, Sv, ((int)(ph + pad) - r_max) / 2, ((int)(pw + pad) - s_max) / 2, 1, lut};
+      parts[ph * 2 + pw] = at::empty({N, Hc, Wc, C}, dx.options());
+      dgrad_launch(dy, w, parts[ph * 2 + pw], gm, c10::nullopt, groups);
+      src[ph * 2 + pw] = parts[ph * 2 + pw].data_ptr();
+    }
+  }
+  if (addend.has_value()) { check_bf16_contig(*addend, "addend"); TORCH_CHECK(addend->numel() == dx.numel(), "addend must have dx's shape"); }
+  B200_CUDA_OK(b200_parity_interleave(src, addend.has_value() ? addend->data_ptr() : nullptr, dx.data_ptr(), N, H, W, C, cur_stream()));
 }
 
 // ---------------------------------------------------------------------------------------------- conv wgrad
@@ -581,6 +645,65 @@ void unpad_add(const at::Tensor& src, at::Tensor& dst, int64_t rows, int64_t col
   B200_CUDA_OK(b200_unpad_add(src.data_ptr<float>(), dst.data_ptr<float>(), rows, cols, cols_pad, cur_stream()));
 }
 
+// ---------------------------------------------------------------------------------------------- extras
+void colsum_add(const at::Tensor& d, at::Tensor& out) {
+  c10::cuda::CUDAGuard guard(d.device());
+  TORCH_CHECK(d.dim() == 2 && d.stride(1) == 1 && d.scalar_type() == at::kBFloat16 && d.size(1) % 8 == 0, "colsum_add: bf16 [rows, C], C % 8 == 0");
+  TORCH_CHECK(out.scalar_type() == at::kFloat && out.is_contiguous() && out.numel() >= d.size(1), "colsum_add: fp32 [C] output");
+  B200_CUDA_OK(b200_colsum_add(d.data_ptr(), d.size(0), d.size(1), d.stride(0), out.data_ptr<float>(), cur_stream()));
+}
+void strided_add_inplace(at::Tensor& dx, const at::Tensor& compact, int64_t stride) {
+  check_bf16_contig(dx, "dx"); check_bf16_contig(compact, "compact");
+  c10::cuda::CUDAGuard guard(dx.device());
+  TORCH_CHECK(dx.size(3) == compact.size(3) && dx.size(3) % 8 == 0 && (compact.size(1) - 1) * stride < dx.size(1) &&
+              (compact.size(2) - 1) * stride < dx.size(2), "strided_add_inplace shapes");
+  B200_CUDA_OK(b200_strided_add_inplace(dx.data_ptr(), compact.data_ptr(), dx.size(0), dx.size(1), dx.size(2), dx.size(3), compact.size(1),
+                                        compact.size(2), stride, cur_stream()));
+}
+void blockdiag_pack(const at::Tensor& thin, at::Tensor& dense) {
+  check_bf16_contig(thin, "thin"); check_bf16_contig(dense, "dense");
+  c10::cuda::CUDAGuard guard(thin.device());
+  const int K = thin.size(0), taps = thin.size(1) * thin.size(2), cg = thin.size(3);
+  TORCH_CHECK(64 % cg == 0 && K % 64 == 0 && dense.numel() == (int64_t)K * taps * 64, "blockdiag_pack: cg must divide 64, K % 64 == 0");
+  B200_CUDA_OK(b200_blockdiag_pack(thin.data_ptr(), dense.data_ptr(), K, taps, cg, cur_stream()));
+}
+void blockdiag_unpack_add(const at::Tensor& dense, at::Tensor& thin) {
+  c10::cuda::CUDAGuard guard(thin.device());
+  TORCH_CHECK(dense.scalar_type() == at::kFloat && thin.scalar_type() == at::kFloat && dense.is_contiguous() && thin.is_contiguous(), "fp32 contiguous");
+  const int K = thin.size(0), taps = thin.size(1) * thin.size(2), cg = thin.size(3);
+  TORCH_CHECK(64 % cg == 0 && dense.numel() == (int64_t)K * taps * 64, "blockdiag_unpack_add shapes");
+  B200_CUDA_OK(b200_blockdiag_unpack_add(dense.data_ptr<float>(), thin.data_ptr<float>(), K, taps, cg, cur_stream()));
+}
+// s [N,C] bf16 pooled input, w1 [r,C] bf16, w2 [C,r] bf16, biases fp32 (optional) -> pre1 [N,r] fp32, gate [N,C] bf16
+void se_gate_fwd(const at::Tensor& sp, const at::Tensor& w1, const c10::optional<at::Tensor>& b1, const at::Tensor& w2,
+                 const c10::optional<at::Tensor>& b2, at::Tensor& pre1, at::Tensor& gate, int64_t act) {
+  check_bf16_contig(sp, "s"); check_bf16_contig(w1, "w1"); check_bf16_contig(w2, "w2"); check_bf16_contig(gate, "gate");
+  c10::cuda::CUDAGuard guard(sp.device());
+  const int N = sp.size(0), C = sp.size(1), r = w1.numel() / C;
+  TORCH_CHECK(w2.numel() == (int64_t)C * r && pre1.numel() == (int64_t)N * r && pre1.scalar_type() == at::kFloat && gate.numel() == sp.numel(), "se_gate_fwd shapes");
+  TORCH_CHECK((size_t)4 * (C + r) * 4 <= 200 * 1024, "se_gate_fwd: layer too wide for the shared-memory staging");
+  B200_CUDA_OK(b200_se_gate_fwd(sp.data_ptr(), w1.data_ptr(), fptr(b1), w2.data_ptr(), fptr(b2), pre1.data_ptr<float>(), gate.data_ptr(), N, C, r,
+                                act, cur_stream()));
+}
+void se_gate_bwd(const at::Tensor& dgate, const at::Tensor& gate, const at::Tensor& sp, const at::Tensor& pre1, const at::Tensor& w1,
+                 const at::Tensor& w2, at::Tensor& dw1, c10::optional<at::Tensor> db1, at::Tensor& dw2, c10::optional<at::Tensor> db2,
+                 at::Tensor& ds, at::Tensor& scratch, int64_t act) {
+  c10::cuda::CUDAGuard guard(sp.device());
+  const int N = sp.size(0), C = sp.size(1), r = w1.numel() / C;
+  TORCH_CHECK(dgate.scalar_type() == at::kFloat && dgate.is_contiguous() && ds.scalar_type() == at::kFloat && ds.numel() == (int64_t)N * C, "se_gate_bwd: fp32 dgate / ds");
+  TORCH_CHECK(dw1.scalar_type() == at::kFloat && dw2.scalar_type() == at::kFloat && dw1.numel() == (int64_t)C * r && dw2.numel() == (int64_t)C * r, "se_gate_bwd: fp32 weight gradients");
+  TORCH_CHECK(scratch.scalar_type() == at::kFloat && scratch.numel() >= (int64_t)N * C + 2LL * N * r, "se_gate_bwd: scratch too small");
+  B200_CUDA_OK(b200_se_gate_bwd(dgate.data_ptr<float>(), gate.data_ptr(), sp.data_ptr(), pre1.data_ptr<float>(), w1.data_ptr(), w2.data_ptr(),
+                                dw1.data_ptr<float>(), fptr_mut(db1), dw2.data_ptr<float>(), fptr_mut(db2), ds.data_ptr<float>(),
+                                scratch.data_ptr<float>(), N, C, r, act, cur_stream()));
+}
+void channel_add_bcast(at::Tensor& dx, const at::Tensor& ds, double scale) {
+  check_bf16_contig(dx, "dx");
+  c10::cuda::CUDAGuard guard(dx.device());
+  TORCH_CHECK(ds.scalar_type() == at::kFloat && ds.is_contiguous() && ds.numel() == dx.size(0) * dx.size(3) && dx.size(3) % 8 == 0, "channel_add_bcast shapes");
+  B200_CUDA_OK(b200_channel_add_bcast(dx.data_ptr(), ds.data_ptr<float>(), dx.size(0), dx.size(1) * dx.size(2), dx.size(3), (float)scale, cur_stream()));
+}
+
 // ---------------------------------------------------------------------------------------------- optimizer / comm
 SgdHyper hyper(double lr, double momentum, double dampening, double wd, bool nesterov, bool first) {
   SgdHyper h; h.lr = lr; h.momentum = momentum; h.dampening = dampening; h.weight_decay = wd; h.nesterov = nesterov; h.first_step = first;
@@ -651,6 +774,15 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv_dgrad", &conv_dgrad, "tcgen05 implicit-GEMM data gradient (stride 1), optional fused addend",
         py::arg("dy"), py::arg("w"), py::arg("dx"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("addend") = py::none(),
         py::arg("groups") = 1);
+  m.def("conv_dgrad_s2", &conv_dgrad_s2, "stride-2 data gradient by parity classes (no zero insertion)", py::arg("dy"), py::arg("w"),
+        py::arg("dx"), py::arg("pad"), py::arg("addend") = py::none(), py::arg("groups") = 1);
+  m.def("colsum_add", &colsum_add);
+  m.def("strided_add_inplace", &strided_add_inplace);
+  m.def("blockdiag_pack", &blockdiag_pack);
+  m.def("blockdiag_unpack_add", &blockdiag_unpack_add);
+  m.def("se_gate_fwd", &se_gate_fwd);
+  m.def("se_gate_bwd", &se_gate_bwd);
+  m.def("channel_add_bcast", &channel_add_bcast);
   m.def("conv_wgrad", &conv_wgrad, "tcgen05 split-K weight gradient (fp32 accumulate)", py::arg("dy"), py::arg("x"), py::arg("dw"),
         py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("groups") = 1);
   py::class_<PeerState>(m, "PeerState")

@@ -137,7 +137,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         mbar_expect_tx(bb, (uint32_t)(k_iters_fd * C::kBBytes));
         for (int it = 0; it < k_iters_fd; ++it) {
           const int tap = it / p.kb_per_tap, kb = it - tap * p.kb_per_tap;
-          const int btap = p.b_flip_taps ? (p.taps - 1 - tap) : tap;
+          const int btap = p.tap_lut_on ? (int)p.tap_lut[tap] : (p.b_flip_taps ? (p.taps - 1 - tap) : tap);
           const uint32_t dst = smem_u32(smem_b + it * C::kBBytes);
           if (p.kind == KIND_FPROP) {
             tma_load_4d(dst, &map_b, bb, kb * BK, btap, w0.n0, 0);
@@ -170,7 +170,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
               tma_load_im2col_4d(dst_a, &map_a, bar, ca, pa.w, pa.h, pa.n, (uint16_t)(sx * p.dil), (uint16_t)(r * p.dil));
             else
               tma_load_3d(dst_a, &map_a, bar, ca, 0, w.m0);
-            const int btap = p.b_flip_taps ? (p.taps - 1 - tap) : tap;
+            const int btap = p.tap_lut_on ? (int)p.tap_lut[tap] : (p.b_flip_taps ? (p.taps - 1 - tap) : tap);
             // weights are mapped as (Cin/g, taps, Cout/g, groups): anything past a group's extent is zero-filled
             if (resident) {
               // B slab already in shared memory

@@ -24,6 +24,8 @@ struct ConvGemmParams {
   uint32_t b_kstep16;
   uint64_t b_desc_hi;
   int b_flip_taps;
+  int tap_lut_on;               // dgrad parity classes: weight tap of virtual tap t is tap_lut[t] (overrides b_flip_taps)
+  unsigned char tap_lut[28];
   uint32_t idesc;
   int im_P, im_Q, im_stride, im_low_w, im_low_h;  // pixel enumeration of the im2col operand
   int k_blocks_total, splits;                     // wgrad: 64-pixel reduction blocks and split-K factor

@@ -9,9 +9,9 @@ gradients are written by the kernels *directly* into the engine's flat fp32 grad
 is ready so the fused all-reduce + SGD kernel can start while backward is still running.
 
 What still runs as plain torch ops on the same bf16 NHWC tensors (their parameter gradients are routed into the
-same flat buffer by a hook, see ``NativeEngine.w16_leaf``): very thin grouped convs (ResNeXt's 4-8 channels per
-group), convs / BN whose channel count is not a multiple of 8, the attention core of BoTNet's MHSA (QK^T +
-relative-position logits + softmax + PV) and the tiny activation / sigmoid ops of squeeze-excite.
+same flat buffer by a hook, see ``NativeEngine.w16_leaf``): convs / BN whose channel count is not a multiple of 8
+and convolutions with a bias or asymmetric geometry -- none of which occurs in the zoo's ``config/*.yaml`` models
+(``NativeOps.fallbacks`` counts every such call; tests assert it stays empty for them).
 """
 from __future__ import annotations
 
@@ -54,6 +54,32 @@ class _GradSink:
         return t
 
 
+def _thin_group_width(conv) -> int:
+    """Channels per group if ``conv`` is a thin-group convolution (ResNeXt: 4..16 channels per group, as many outputs
+    as inputs per group) that runs as a 64-channel block-diagonal grouped conv on the tcgen05 path, else 0."""
+    g = conv.groups
+    if g == 1:
+        return 0
+    cin_g, cout_g = conv.in_channels // g, conv.out_channels // g
+    if cin_g == cout_g and cin_g < 32 and 64 % cin_g == 0 and conv.in_channels % 64 == 0:
+        return cin_g
+    return 0
+
+
+def _conv_weight(eng, conv):
+    """bf16 KRSC weight and group count the kernels see.  Thin groups: the [K,R,S,cg] weight is scattered into a
+    [K,R,S,64] block-diagonal one (zeros off the diagonal blocks) and the conv runs with C/64 groups of 64 channels --
+    16x (cg=4) more MACs than strictly needed, but on the tensor cores instead of a library fallback."""
+    cg = _thin_group_width(conv)
+    w = eng.w16_krsc(conv.weight)
+    if not cg:
+        return w, conv.groups
+    Kc, R, S, _ = w.shape
+    dense = eng.scratch(f"blockdiag_w_{id(conv)}", (Kc, R, S, 64), torch.bfloat16)
+    eng.K.blockdiag_pack(w, dense)
+    return dense, conv.in_channels // 64
+
+
 class ConvFn(torch.autograd.Function):
     """Implicit-GEMM convolution (fprop / dgrad / wgrad on tcgen05), optional BN-statistics epilogue."""
 
@@ -61,20 +87,20 @@ class ConvFn(torch.autograd.Function):
     def forward(ctx, x, eng, conv, stats, anchor, hand_to=None):
         K = eng.K
         xh = _nhwc(x)
-        w = eng.w16_krsc(conv.weight)
+        w, groups = _conv_weight(eng, conv)
         N, H, W, C = xh.shape
         Kc, R, S, _ = w.shape
         s, p, d = conv.stride[0], conv.padding[0], conv.dilation[0]
         P = (H + 2 * p - d * (R - 1) - 1) // s + 1
         Q = (W + 2 * p - d * (S - 1) - 1) // s + 1
         y = torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
-        K.conv_fprop(xh, w, y, stats, None, s, p, d, conv.groups)
+        K.conv_fprop(xh, w, y, stats, None, s, p, d, groups)
         ctx.eng, ctx.conv = eng, conv
         ctx.save_for_backward(xh)
         ctx.x_needs_grad = x.requires_grad
         # Another consumer of this very input (a BnActFn whose residual it is, or a sibling conv of the block) may
         # hand us its gradient contribution: it is added inside our dgrad instead of by a separate add kernel.
-        fusable = s == 1 or (R == 1 and S == 1 and p == 0)
+        fusable = s == 1 or (s == 2 and d == 1 and R <= 5 and S <= 5)
         ctx.sink = _GradSink(xh.data_ptr()) if (x.requires_grad and fusable) else None
         eng.last_sink[conv] = ctx.sink
         # ... and we may hand OUR input gradient to a sibling conv's sink (it must read the same tensor)
@@ -88,16 +114,26 @@ class ConvFn(torch.autograd.Function):
         (xh,) = ctx.saved_tensors
         dyh = _nhwc(dy)
         s, p, d = conv.stride[0], conv.padding[0], conv.dilation[0]
-        K.conv_wgrad(dyh, xh, eng.grad_krsc(conv.weight), s, p, d, conv.groups)
+        cg = _thin_group_width(conv)
+        if cg:
+            # weights were packed in forward (unchanged since: the bucket update is gated on mark_ready below)
+            Kc, _, R, S = conv.weight.shape
+            w, groups = eng.scratch(f"blockdiag_w_{id(conv)}", (Kc, R, S, 64), torch.bfloat16), conv.in_channels // 64
+            dwd = eng.scratch("blockdiag_dw", (Kc, R, S, 64), torch.float32)
+            dwd.zero_()
+            K.conv_wgrad(dyh, xh, dwd, s, p, d, groups)
+            K.blockdiag_unpack_add(dwd, eng.grad_krsc(conv.weight))
+        else:
+            w, groups = eng.w16_krsc(conv.weight), conv.groups
+            K.conv_wgrad(dyh, xh, eng.grad_krsc(conv.weight), s, p, d, groups)
         dx = None
         if ctx.x_needs_grad:
-            w = eng.w16_krsc(conv.weight)
             addend = ctx.sink.take() if ctx.sink is not None else None
             if s == 1:
                 dxh = torch.empty_like(xh)
-                K.conv_dgrad(dyh, w, dxh, 1, p, d, addend, conv.groups)
+                K.conv_dgrad(dyh, w, dxh, 1, p, d, addend, groups)
             else:
-                dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d, conv.groups, addend)
+                dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d, groups, addend)
             if ctx.hand_to is not None and ctx.hand_to.offer(dxh):
                 dx = None          # the sibling conv's dgrad adds it; autograd treats None as zero
             else:
@@ -108,24 +144,31 @@ class ConvFn(torch.autograd.Function):
 
 
 def _strided_dgrad(K, dyh, w, x_shape, s, p, d, groups=1, addend=None):
-    """Data gradient of a strided conv: scatter dy onto a zero-filled stride-1 grid, then run the stride-1
-    tcgen05 dgrad (costs s^2 x the FLOPs of the few strided layers; a parity-decomposed kernel is future work).
-    ``addend`` (1x1 only): a gradient of the same input from a sibling consumer; it is updated in place at the
-    sampled pixels, which replaces a zero fill, a scatter and a full-size add."""
+    """Data gradient of a strided conv.  Stride 2 (every strided layer of the zoo): ``conv_dgrad_s2`` computes the four
+    (row, column) parity classes of dx as compact stride-1 tcgen05 dgrads over the taps that reach them and interleaves
+    them in one pass -- the real FLOPs, no zero insertion, no ATen scatter.  ``addend``: a gradient of the same input
+    from a sibling consumer; it is summed in the interleave pass, or -- 1x1 stride-2 projection -- updated in place at
+    the sampled pixels only.  Other strides keep the zero-insertion fallback (stride^2 x the FLOPs)."""
     N, H, W, C = x_shape
     Kc, R, S, _ = w.shape
+    if s == 2 and d == 1 and R <= 5 and S <= 5:
+        if R == 1 and S == 1 and p == 0 and addend is not None:
+            Pc, Qc = dyh.shape[1], dyh.shape[2]
+            compact = torch.empty((N, Pc, Qc, C), dtype=dyh.dtype, device=dyh.device)
+            K.conv_dgrad(dyh, w, compact, 1, 0, 1, None, groups)
+            K.strided_add_inplace(addend, compact, s)
+            return addend
+        dxh = torch.empty((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
+        K.conv_dgrad_s2(dyh, w, dxh, p, addend, groups)
+        return dxh
+    assert addend is None
     if R == 1 and S == 1 and p == 0:
-        # 1x1 strided conv: only the sampled pixels receive gradient -> compact pointwise dgrad + strided scatter
         Pc, Qc = dyh.shape[1], dyh.shape[2]
         compact = torch.empty((N, Pc, Qc, C), dtype=dyh.dtype, device=dyh.device)
         K.conv_dgrad(dyh, w, compact, 1, 0, 1, None, groups)
-        if addend is not None:
-            addend[:, ::s, ::s, :][:, :Pc, :Qc] += compact
-            return addend
         dxh = torch.zeros((N, H, W, C), dtype=dyh.dtype, device=dyh.device)
         dxh[:, ::s, ::s, :][:, :Pc, :Qc] = compact
         return dxh
-    assert addend is None
     P1 = H + 2 * p - d * (R - 1)
     Q1 = W + 2 * p - d * (S - 1)
     up = torch.zeros((N, P1, Q1, Kc), dtype=dyh.dtype, device=dyh.device)
@@ -343,7 +386,7 @@ class LinearFn(torch.autograd.Function):
         Kc = d2.shape[1]
         K.conv_wgrad(d2.view(B, 1, 1, Kc), x2.view(B, 1, 1, Cin), eng.grad_flat_view(fc.weight).view(Kc, 1, 1, Cin), 1, 0, 1)
         if fc.bias is not None:
-            eng.grad_flat_view(fc.bias).add_(d2.float().sum(0))
+            K.colsum_add(d2, eng.grad_flat_view(fc.bias))
         dx = torch.empty((B, 1, 1, Cin), dtype=torch.bfloat16, device=dout.device)
         K.conv_dgrad(d2.view(B, 1, 1, Kc), eng.w16_view(fc.weight).view(Kc, 1, 1, Cin), dx, 1, 0, 1, None)
         eng.mark_ready(fc.weight)
@@ -429,6 +472,57 @@ class ChannelScaleFn(torch.autograd.Function):
         return _nchw_view(dx), dg.to(g.dtype), None
 
 
+class SeFn(torch.autograd.Function):
+    """Squeeze-excite block as one autograd node: global average pool -> (fc1 + bias -> act -> fc2 + bias -> sigmoid)
+    in ONE kernel for any squeeze width (EfficientNet's 4/6/10/20/28, RegNetY's 308, ...) -> channel scaling.
+    Backward: one pass for dx = dout * gate and the gate gradient, the MLP backward (data part per sample group,
+    weight part with one owner thread per weight: no atomics), and the pooled-input gradient broadcast-added into dx
+    in place -- no ATen op, no full-size add of two dx tensors (reference reaches timm's SqueezeExcite)."""
+
+    @staticmethod
+    def forward(ctx, x, eng, fc1, fc2, act, anchor):
+        K = eng.K
+        xh = _nhwc(x)
+        N, H, W, C = xh.shape
+        r = fc1.out_channels
+        pooled = torch.empty((N, C), dtype=torch.bfloat16, device=x.device)
+        K.gap_fwd(xh, pooled)
+        pre1 = torch.empty((N, r), dtype=torch.float32, device=x.device)
+        gate = torch.empty((N, C), dtype=torch.bfloat16, device=x.device)
+        K.se_gate_fwd(pooled, eng.w16_view(fc1.weight).view(r, C), eng.master_view(fc1.bias) if fc1.bias is not None else None,
+                      eng.w16_view(fc2.weight).view(C, r), eng.master_view(fc2.bias) if fc2.bias is not None else None,
+                      pre1, gate, ACT[act])
+        out = torch.empty_like(xh)
+        K.channel_scale_fwd(xh, gate, out)
+        ctx.eng, ctx.fcs, ctx.act = eng, (fc1, fc2), act
+        ctx.save_for_backward(xh, pooled, gate, pre1)
+        return _nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng = ctx.eng
+        K = eng.K
+        fc1, fc2 = ctx.fcs
+        xh, pooled, gate, pre1 = ctx.saved_tensors
+        N, H, W, C = xh.shape
+        r = fc1.out_channels
+        dx = torch.empty_like(xh)
+        dgate = torch.zeros((N, C), dtype=torch.float32, device=xh.device)
+        K.channel_scale_bwd(_nhwc(dout), xh, gate, dx, dgate)
+        ds = torch.empty((N, C), dtype=torch.float32, device=xh.device)
+        scratch = eng.scratch("se_bwd", (N * C + 2 * N * r,), torch.float32)
+        K.se_gate_bwd(dgate, gate, pooled, pre1, eng.w16_view(fc1.weight).view(r, C), eng.w16_view(fc2.weight).view(C, r),
+                      eng.grad_flat_view(fc1.weight), eng.grad_flat_view(fc1.bias) if fc1.bias is not None else None,
+                      eng.grad_flat_view(fc2.weight), eng.grad_flat_view(fc2.bias) if fc2.bias is not None else None,
+                      ds, scratch, ACT[ctx.act])
+        K.channel_add_bcast(dx, ds, 1.0 / (H * W))
+        for fc in (fc1, fc2):
+            eng.mark_ready(fc.weight)
+            if fc.bias is not None:
+                eng.mark_ready(fc.bias)
+        return _nchw_view(dx), None, None, None, None, None
+
+
 class CeTopkFn(torch.autograd.Function):
     """softmax-CE + top-1/top-k counts + dlogits in one kernel (reference trainer.py:43,50 + utils.py:265-277)."""
 
@@ -462,6 +556,11 @@ class NativeOps:
 
     def __init__(self, engine):
         self.eng = engine
+        # calls that left the sm_100a kernels for an ATen / library op, by kind; stays empty for every config/*.yaml model
+        self.fallbacks: dict = {}
+
+    def _fell_back(self, kind: str):
+        self.fallbacks[kind] = self.fallbacks.get(kind, 0) + 1
 
     # ---- helpers -------------------------------------------------------------------------------
     @staticmethod
@@ -469,13 +568,14 @@ class NativeOps:
         kh, kw = conv.kernel_size
         g = conv.groups
         cin_g, cout_g = conv.in_channels // g, conv.out_channels // g
-        # grouped convs run as `g` independent implicit GEMMs in one launch; very thin groups (ResNeXt's 4-8
-        # channels) would waste the 64-wide K block, they stay on the library path
-        group_ok = g == 1 or (cin_g >= 32 and cout_g >= 32)
-        return (group_ok and conv.bias is None and kh == kw and conv.stride[0] == conv.stride[1]
+        # grouped convs run as `g` independent implicit GEMMs in one launch; thin groups (ResNeXt's 4-16 channels)
+        # are regrouped into 64-channel block-diagonal groups (``_conv_weight``)
+        thin = _thin_group_width(conv) > 0
+        group_ok = g == 1 or (cin_g >= 32 and cout_g >= 32) or thin
+        width_ok = thin or (cin_g % 8 == 0 and cout_g % 8 == 0)
+        return (group_ok and width_ok and conv.bias is None and kh == kw and conv.stride[0] == conv.stride[1]
                 and conv.padding[0] == conv.padding[1] and conv.dilation[0] == conv.dilation[1]
-                and isinstance(conv.padding, tuple) and cin_g % 8 == 0 and cout_g % 8 == 0
-                and x.dtype == torch.bfloat16 and conv.padding_mode == "zeros")
+                and isinstance(conv.padding, tuple) and x.dtype == torch.bfloat16 and conv.padding_mode == "zeros")
 
     @staticmethod
     def _depthwise_ok(conv: nn.Conv2d, x) -> bool:
@@ -502,6 +602,7 @@ class NativeOps:
         return _nchw_view(out)
 
     def _torch_conv(self, x, conv):
+        self._fell_back("conv")
         x = self._as_act(x)
         w = self.eng.w16_leaf(conv.weight)
         b = self.eng.w16_leaf(conv.bias) if conv.bias is not None else None
@@ -530,6 +631,7 @@ class NativeOps:
                 y = y + residual
             return _torch_act(y, act)
         if y.shape[1] % 8 != 0:
+            self._fell_back("batch_norm")
             w = eng.w16_leaf(bn.weight) if bn.affine else None
             b = eng.w16_leaf(bn.bias) if bn.affine else None
             y = F.batch_norm(y, bn.running_mean, bn.running_var, w, b, bn.training, bn.momentum or 0.1, bn.eps)
@@ -543,6 +645,7 @@ class NativeOps:
         eng = self.eng
         x = self._as_act(x)
         if x.shape[1] % 8 != 0:  # kernels are 8-channel vectorised; odd widths take the ATen path
+            self._fell_back("batch_norm")
             w = eng.w16_leaf(bn.weight) if bn.affine else None
             b = eng.w16_leaf(bn.bias) if bn.affine else None
             y = F.batch_norm(x, bn.running_mean, bn.running_var, w, b, bn.training, bn.momentum or 0.1, bn.eps)
@@ -557,6 +660,7 @@ class NativeOps:
     def linear(self, x, fc):
         if x.dtype == torch.bfloat16 and fc.in_features % 8 == 0 and fc.out_features % 8 == 0:
             return LinearFn.apply(x, self.eng, fc, self.eng.anchor)
+        self._fell_back("linear")
         w = self.eng.w16_leaf(fc.weight)
         b = self.eng.w16_leaf(fc.bias) if fc.bias is not None else None
         return F.linear(x.to(torch.bfloat16), w, b)
@@ -564,16 +668,19 @@ class NativeOps:
     def max_pool2d(self, x, k, s, p):
         if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
             return MaxPoolFn.apply(x, self.eng, k, s, p)
+        self._fell_back("max_pool2d")
         return F.max_pool2d(x, k, s, p)
 
     def avg_pool2d(self, x, k, s):
         if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0 and k == 2 and s == 2 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0:
             return AvgPool2Fn.apply(x, self.eng)
+        self._fell_back("avg_pool2d")
         return F.avg_pool2d(x, k, s)
 
     def global_avg_pool(self, x):
         if x.dtype == torch.bfloat16 and x.shape[1] % 8 == 0:
             return GapFn.apply(x, self.eng)
+        self._fell_back("global_avg_pool")
         return x.mean(dim=(2, 3))
 
     def _se_fc(self, v, conv):
@@ -585,9 +692,13 @@ class NativeOps:
 
     def squeeze_excite(self, x, fc1, fc2, act):
         if x.dtype != torch.bfloat16 or x.shape[1] % 8 != 0:
+            self._fell_back("squeeze_excite")
             s = x.mean(dim=(2, 3), keepdim=True)
             s = _torch_act(self._torch_conv(s, fc1), act)
             return x * torch.sigmoid(self._torch_conv(s, fc2))
+        if (fc1.groups == 1 and fc2.groups == 1 and fc1.kernel_size == (1, 1) and fc2.kernel_size == (1, 1)
+                and x.shape[1] + fc1.out_channels <= 12000):
+            return SeFn.apply(x, self.eng, fc1, fc2, act, self.eng.anchor)
         s = self.global_avg_pool(x)                                   # [N, C]  (native pooling kernel)
         h = _torch_act(self._se_fc(s, fc1), act)                      # [N, r]
         gate = torch.sigmoid(self._se_fc(h, fc2))                     # [N, C]

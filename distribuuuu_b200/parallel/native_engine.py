@@ -294,6 +294,7 @@ class NativeEngine(nn.Module):
         self.peer_state = None
         self.comm_state = None
         self.symm_handle = None
+        self.syncbn_wait_ns = None
         raw = None
         if self.world > 1 and self.comm_mode == "peer":
             try:

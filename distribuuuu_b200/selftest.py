@@ -138,6 +138,15 @@ CONV_CASES = {
     "wgrad_3x3": ("wgrad", dict(N=4, H=14, W=14, C=256, K=256, R=3, pad=1)),
     "wgrad_3x3_s2": ("wgrad", dict(N=2, H=28, W=28, C=128, K=128, R=3, stride=2, pad=1)),
     "wgrad_1x1_s2": ("wgrad", dict(N=2, H=28, W=28, C=256, K=512, R=1, stride=2, pad=0)),
+    # the benchmark's own shapes (batch 256: M = 802 816 rows, > 6 000 tiles per launch, split-K over 12 544 blocks)
+    "prod_fprop_1x1_l1": ("fprop", dict(N=256, H=56, W=56, C=64, K=256, R=1, pad=0)),
+    "prod_fprop_3x3_l1": ("fprop", dict(N=256, H=56, W=56, C=64, K=64, R=3, pad=1)),
+    "prod_dgrad_3x3_l1": ("dgrad", dict(N=256, H=56, W=56, C=64, K=64, R=3, pad=1)),
+    "prod_wgrad_3x3_l1": ("wgrad", dict(N=256, H=56, W=56, C=64, K=64, R=3, pad=1, tol=3e-2)),
+    "prod_wgrad_1x1_l1": ("wgrad", dict(N=256, H=56, W=56, C=256, K=64, R=1, pad=0, tol=3e-2)),
+    "prod_fprop_3x3_l4": ("fprop", dict(N=256, H=7, W=7, C=512, K=512, R=3, pad=1)),
+    "prod_dgrad_1x1_l4": ("dgrad", dict(N=256, H=7, W=7, C=512, K=2048, R=1, pad=0)),
+    "prod_wgrad_3x3_l4": ("wgrad", dict(N=256, H=7, W=7, C=512, K=512, R=3, pad=1, tol=3e-2)),
 }
 
 
@@ -297,6 +306,123 @@ def check_depthwise(N=4, H=14, W=14, C=96, k=5, stride=2):
             "stats_sq": _rel_err(st[C:], (yf * yf).sum(0))}
     assert all(v < 2e-2 for v in errs.values()), errs
     return errs
+
+
+def check_dgrad_s2(N=2, H=28, W=28, C=128, K=128, R=3, pad=1, G=1, with_addend=False, tol=2e-2):
+    """Stride-2 data gradient by parity classes (conv_dgrad_s2) vs conv_transpose2d, incl. odd sizes / 1x1 / groups."""
+    Kmod = _K()
+    P, Q = (H + 2 * pad - R) // 2 + 1, (W + 2 * pad - R) // 2 + 1
+    cin_g = C // G
+    dy = _bf16(N, P, Q, K, seed=51)
+    w = _bf16(K, R, R, cin_g, scale=(K // G * R * R) ** -0.5, seed=52)
+    add = _bf16(N, H, W, C, seed=53) if with_addend else None
+    dx = torch.full((N, H, W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    Kmod.conv_dgrad_s2(dy, w, dx, pad, add, G)
+    torch.cuda.synchronize()
+    oph, opw = H - ((P - 1) * 2 - 2 * pad + R), W - ((Q - 1) * 2 - 2 * pad + R)
+    ref = F.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.float().permute(0, 3, 1, 2), None, 2, pad, (oph, opw), G, 1)
+    ref = ref.permute(0, 2, 3, 1)
+    if add is not None:
+        ref = ref + add.float()
+    err = _rel_err(dx, ref)
+    assert err < tol, f"conv_dgrad_s2 mismatch rel_err={err}"
+    out = {"rel_err": err}
+    if R == 1 and pad == 0:           # in-place variant used when the projection joins an existing gradient
+        base = _bf16(N, H, W, C, seed=54)
+        compact = torch.empty((N, P, Q, C), dtype=torch.bfloat16, device="cuda")
+        Kmod.conv_dgrad(dy, w, compact, 1, 0, 1, None, G)
+        want = base.float().clone()
+        want[:, ::2, ::2, :][:, :P, :Q] += compact.float()
+        Kmod.strided_add_inplace(base, compact, 2)
+        torch.cuda.synchronize()
+        out["inplace"] = _rel_err(base, want)
+        assert out["inplace"] < 1e-2, out
+    return out
+
+
+def check_thin_groups(N=2, H=14, W=14, C=128, G=32, R=3, stride=1, pad=1, tol=2e-2):
+    """ResNeXt-style thin groups through the 64-channel block-diagonal path: pack -> grouped tcgen05 conv (fprop,
+    dgrad, wgrad) -> unpack, against F.conv2d(groups=G)."""
+    Kmod = _K()
+    cg = C // G
+    P = (H + 2 * pad - R) // stride + 1
+    x = _bf16(N, H, W, C, seed=61)
+    w = _bf16(C, R, R, cg, scale=(cg * R * R) ** -0.5, seed=62)
+    dy = _bf16(N, P, P, C, seed=63)
+    dense = torch.full((C, R, R, 64), float("nan"), dtype=torch.bfloat16, device="cuda")
+    Kmod.blockdiag_pack(w, dense)
+    g2 = C // 64
+    y = torch.full((N, P, P, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2 * C, device="cuda")
+    Kmod.conv_fprop(x, dense, y, st, None, stride, pad, 1, g2)
+    dwd = torch.zeros((C, R, R, 64), device="cuda")
+    Kmod.conv_wgrad(dy, x, dwd, stride, pad, 1, g2)
+    dw = torch.zeros((C, R, R, cg), device="cuda")
+    Kmod.blockdiag_unpack_add(dwd, dw)
+    dx = torch.full((N, H, W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    if stride == 1:
+        Kmod.conv_dgrad(dy, dense, dx, 1, pad, 1, None, g2)
+    else:
+        Kmod.conv_dgrad_s2(dy, dense, dx, pad, None, g2)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = w.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    yr = F.conv2d(xr, wr, None, stride, pad, 1, G)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    errs = {"y": _rel_err(y, yr.permute(0, 2, 3, 1)), "dw": _rel_err(dw, wr.grad.permute(0, 2, 3, 1)),
+            "dx": _rel_err(dx, xr.grad.permute(0, 2, 3, 1))}
+    assert all(v < tol for v in errs.values()), errs
+    return errs
+
+
+def check_se(N=10, H=7, W=7, C=96, r=4, act="silu"):
+    """Fused squeeze-excite (SeFn's kernels): pool -> fc/act/fc/sigmoid -> scale, forward and backward, vs fp32 torch."""
+    Kmod = _K()
+    from .ops.native import ACT
+    x, dout = _bf16(N, H, W, C, seed=71), _bf16(N, H, W, C, seed=72)
+    w1, w2 = _bf16(r, C, scale=C ** -0.5, seed=73), _bf16(C, r, scale=r ** -0.5, seed=74)
+    b1, b2 = torch.randn(r, device="cuda") * 0.1, torch.randn(C, device="cuda") * 0.1
+    pooled = torch.empty((N, C), dtype=torch.bfloat16, device="cuda")
+    Kmod.gap_fwd(x, pooled)
+    pre1 = torch.empty((N, r), device="cuda")
+    gate = torch.empty((N, C), dtype=torch.bfloat16, device="cuda")
+    Kmod.se_gate_fwd(pooled, w1, b1, w2, b2, pre1, gate, ACT[act])
+    out = torch.empty_like(x)
+    Kmod.channel_scale_fwd(x, gate, out)
+    dx = torch.empty_like(x)
+    dgate = torch.zeros(N, C, device="cuda")
+    Kmod.channel_scale_bwd(dout, x, gate, dx, dgate)
+    ds = torch.empty(N, C, device="cuda")
+    scratch = torch.empty(N * C + 2 * N * r, device="cuda")
+    dw1, dw2 = torch.zeros(r, C, device="cuda"), torch.zeros(C, r, device="cuda")
+    db1, db2 = torch.zeros(r, device="cuda"), torch.zeros(C, device="cuda")
+    Kmod.se_gate_bwd(dgate, gate, pooled, pre1, w1, w2, dw1, db1, dw2, db2, ds, scratch, ACT[act])
+    Kmod.channel_add_bcast(dx, ds, 1.0 / (H * W))
+    torch.cuda.synchronize()
+    xr = x.float().clone().requires_grad_(True)
+    w1r, w2r = w1.float().clone().requires_grad_(True), w2.float().clone().requires_grad_(True)
+    b1r, b2r = b1.clone().requires_grad_(True), b2.clone().requires_grad_(True)
+    sp = xr.mean((1, 2))
+    hid = sp @ w1r.t() + b1r
+    hid = F.silu(hid) if act == "silu" else F.relu(hid)
+    g = torch.sigmoid(hid @ w2r.t() + b2r)
+    o = xr * g[:, None, None, :]
+    o.backward(dout.float())
+    errs = {"out": _rel_err(out, o), "dx": _rel_err(dx, xr.grad), "dw1": _rel_err(dw1, w1r.grad), "dw2": _rel_err(dw2, w2r.grad),
+            "db1": _rel_err(db1, b1r.grad), "db2": _rel_err(db2, b2r.grad)}
+    assert all(v < 3e-2 for v in errs.values()), errs
+    return errs
+
+
+def check_colsum(rows=1000, C=1000 // 8 * 8):
+    Kmod = _K()
+    d = _bf16(rows, C, seed=81)
+    out = torch.ones(C, device="cuda")
+    Kmod.colsum_add(d, out)
+    torch.cuda.synchronize()
+    err = _rel_err(out, 1.0 + d.float().sum(0))
+    assert err < 1e-4, err
+    return {"rel_err": err}
 
 
 def check_channel_scale(N=4, H=7, W=7, C=112):

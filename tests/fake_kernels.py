@@ -108,6 +108,77 @@ class FakeKernels:
             g = g + addend.float().reshape(g.shape)
         _raw(dx).copy_(g.to(BF16).reshape(dx.shape))
 
+    def conv_dgrad_s2(self, dy, w, dx, pad, addend=None, groups=1):
+        self._count("conv_dgrad_s2" + ("+addend" if addend is not None else ""))
+        N, H, W, C = dx.shape
+        P, Q = dy.shape[1], dy.shape[2]
+        R, S = w.shape[1], w.shape[2]
+        oph, opw = H - ((P - 1) * 2 - 2 * pad + R), W - ((Q - 1) * 2 - 2 * pad + S)
+        g = F.conv_transpose2d(_nchw(dy), w.permute(0, 3, 1, 2).float(), None, 2, pad, (oph, opw), groups, 1)
+        g = g.permute(0, 2, 3, 1)
+        if addend is not None:
+            g = g + addend.float().reshape(g.shape)
+        _raw(dx).copy_(g.to(BF16).reshape(dx.shape))
+
+    def strided_add_inplace(self, dx, compact, stride):
+        self._count("strided_add_inplace")
+        P, Q = compact.shape[1], compact.shape[2]
+        v = _raw(dx)[:, ::stride, ::stride, :][:, :P, :Q]
+        v.copy_((v.float() + compact.float()).to(BF16))
+
+    def colsum_add(self, d, out):
+        self._count("colsum_add")
+        _raw(out)[: d.shape[1]] += d.float().sum(0)
+
+    def blockdiag_pack(self, thin, dense):
+        self._count("blockdiag_pack")
+        K, R, S, cg = thin.shape
+        d = torch.zeros(K, R, S, 64, dtype=BF16)
+        for k in range(K):
+            g = (k % 64) // cg
+            d[k, :, :, g * cg:(g + 1) * cg] = thin[k]
+        _raw(dense).copy_(d.reshape(dense.shape))
+
+    def blockdiag_unpack_add(self, dense, thin):
+        self._count("blockdiag_unpack_add")
+        K, R, S, cg = thin.shape
+        d = dense.reshape(K, R, S, 64)
+        t = _raw(thin)
+        for k in range(K):
+            g = (k % 64) // cg
+            t[k] += d[k, :, :, g * cg:(g + 1) * cg]
+
+    def se_gate_fwd(self, sp, w1, b1, w2, b2, pre1, gate, act):
+        self._count("se_gate_fwd")
+        N, C = sp.shape
+        r = w1.numel() // C
+        z1 = sp.float() @ w1.float().reshape(r, C).t() + (b1.float() if b1 is not None else 0)
+        _raw(pre1).copy_(z1.reshape(pre1.shape))
+        z2 = _act(z1, act) @ w2.float().reshape(C, r).t() + (b2.float() if b2 is not None else 0)
+        _raw(gate).copy_(torch.sigmoid(z2).to(BF16))
+
+    def se_gate_bwd(self, dgate, gate, sp, pre1, w1, w2, dw1, db1, dw2, db2, ds, scratch, act):
+        self._count("se_gate_bwd")
+        N, C = sp.shape
+        r = w1.numel() // C
+        g = gate.float()
+        dz2 = dgate.float().reshape(N, C) * g * (1 - g)
+        z1 = pre1.float().reshape(N, r)
+        h = _act(z1, act)
+        _raw(dw2).view(C, r).add_(dz2.t() @ h)
+        if db2 is not None:
+            _raw(db2).add_(dz2.sum(0))
+        dz1 = (dz2 @ w2.float().reshape(C, r)) * _act_grad(z1, act)
+        _raw(dw1).view(r, C).add_(dz1.t() @ sp.float())
+        if db1 is not None:
+            _raw(db1).add_(dz1.sum(0))
+        _raw(ds).copy_((dz1 @ w1.float().reshape(r, C)).reshape(ds.shape))
+
+    def channel_add_bcast(self, dx, ds, scale):
+        self._count("channel_add_bcast")
+        N, H, W, C = dx.shape
+        _raw(dx).copy_((dx.float() + (ds.float().view(N, 1, 1, C) * scale)).to(BF16))
+
     def conv_wgrad(self, dy, x, dw, stride, pad, dil, groups=1):
         self._count("conv_wgrad")
         K, R, S, Cg = dw.shape

@@ -105,3 +105,49 @@ def test_checkpoint_interop_native_vs_torch_optim():
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(N=3, H=7, W=7, C=64, K=192, with_addend=True), dict(N=2, H=28, W=28, C=256, K=512, R=1, pad=0),
+                                dict(N=2, H=14, W=14, C=64, K=128, R=1, pad=0, with_addend=True), dict(N=2, H=28, W=28, C=224, K=224, G=2),
+                                dict(N=2, H=12, W=12, C=64, K=64, R=5, pad=2)],
+                         ids=["3x3", "3x3_odd_addend", "1x1", "1x1_addend", "grouped", "5x5"])
+def test_stride2_dgrad_by_parity_classes(kw):
+    from distribuuuu_b200 import selftest
+    selftest.check_dgrad_s2(**kw)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(C=256, G=32, H=28, W=28, stride=2), dict(C=512, G=32, H=7, W=7)], ids=["cg4", "cg8_s2", "cg16"])
+def test_thin_group_convs_block_diagonal(kw):
+    from distribuuuu_b200 import selftest
+    selftest.check_thin_groups(**kw)
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(N=9, H=4, W=4, C=1232, r=308, act="relu"), dict(N=33, H=7, W=7, C=480, r=20)],
+                         ids=["silu_r4", "relu_r308", "silu_r20"])
+def test_fused_squeeze_excite(kw):
+    from distribuuuu_b200 import selftest
+    selftest.check_se(**kw)
+
+
+def test_bias_gradient_colsum():
+    from distribuuuu_b200 import selftest
+    selftest.check_colsum()
+
+
+@pytest.mark.parametrize("arch", ["resnet50", "resnext50_32x4d", "regnety_160", "efficientnet_b0"])
+def test_no_library_fallbacks_for_zoo_models(arch):
+    """One native training step of a config/*.yaml family must never leave the sm_100a kernels."""
+    import torch
+    from distribuuuu_b200 import models
+    from distribuuuu_b200.parallel.native_engine import NativeEngine
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    net = models.build_model(arch, num_classes=16).to(dev)
+    eng = NativeEngine(net, dev)
+    opt = eng.make_optimizer(lr=0.01, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    eng.train()
+    x = torch.randn(4, 3, 64, 64, device=dev)
+    y = torch.randint(0, 16, (4,), device=dev)
+    loss, _, _ = eng.train_step(x, y, opt, 5)
+    assert torch.isfinite(loss).item()
+    assert eng.ops.fallbacks == {}, eng.ops.fallbacks

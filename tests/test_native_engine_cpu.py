@@ -98,9 +98,10 @@ def test_training_steps_match_the_torch_path(cpu_engine, arch, size):
 @pytest.mark.parametrize("arch,size,batch", [("efficientnet_b0", 128, 16), ("densenet121", 64, 8), ("regnety_160", 64, 4),
                                              ("resnext50_32x4d", 64, 8), ("botnet50", 224, 2)])
 def test_other_model_families_step_like_the_torch_path(cpu_engine, arch, size, batch):
-    """Depthwise + SE + SiLU (EfficientNet), pre-activation BN + concat + avg-pool (DenseNet), wide grouped convs +
-    SE (RegNetY), thin groups on the ATen fallback with gradients folded into the flat buffers (ResNeXt), the
-    relative-position attention core on bf16 ATen ops between native projections (BoTNet, fixed 224x224 input)."""
+    """Depthwise + fused SE + SiLU (EfficientNet), pre-activation BN + concat + avg-pool (DenseNet), wide grouped
+    convs + fused SE (RegNetY), thin groups as 64-channel block-diagonal groups (ResNeXt), relative-position
+    attention between native projections (BoTNet, fixed 224x224 input).  No call may leave the kernel module for an
+    ATen / library op (``NativeOps.fallbacks`` stays empty)."""
     eng, ref, fake = cpu_engine(arch, num_classes=16)
     # same batch / resolution / tolerance as the GPU parity checks (tools/gpu_selftest.py): small BN sample counts
     # make these nets sensitive to bf16 rounding, so the bound is on the loss trajectory, not per tensor
@@ -108,6 +109,13 @@ def test_other_model_families_step_like_the_torch_path(cpu_engine, arch, size, b
     for la, lb in losses:
         assert abs(la - lb) / max(abs(lb), 1e-3) < 0.15, losses
     assert float(eng.flat_grad.abs().max()) == 0.0
+    assert eng.ops.fallbacks == {}, eng.ops.fallbacks
+    if arch in ("efficientnet_b0", "regnety_160"):
+        assert fake.calls.get("se_gate_fwd", 0) > 0 and fake.calls.get("se_gate_bwd", 0) == fake.calls["se_gate_fwd"]
+    if arch == "resnext50_32x4d":
+        assert fake.calls.get("blockdiag_pack", 0) > 0 and fake.calls.get("blockdiag_unpack_add", 0) > 0
+    if arch not in ("densenet121", "efficientnet_b0"):   # strided dense/grouped convs: parity-class dgrad, no zero insertion
+        assert fake.calls.get("conv_dgrad_s2", 0) + fake.calls.get("conv_dgrad_s2+addend", 0) + fake.calls.get("strided_add_inplace", 0) > 0
 
 
 def test_activation_checkpointing_recomputes_on_the_native_path(cpu_engine):

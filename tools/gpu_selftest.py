@@ -34,6 +34,19 @@ def registry():
         "grouped_regnety": lambda: st.check_grouped_conv(C=224, K=224, G=2),
         "grouped_regnetx_s2": lambda: st.check_grouped_conv(C=512, K=512, G=4, stride=2, H=28, W=28),
         "grouped_232": lambda: st.check_grouped_conv(C=696, K=696, G=3, H=14, W=14),
+        "dgrad_s2_3x3": lambda: st.check_dgrad_s2(),
+        "dgrad_s2_3x3_odd_addend": lambda: st.check_dgrad_s2(N=3, H=7, W=7, C=64, K=192, with_addend=True),
+        "dgrad_s2_1x1": lambda: st.check_dgrad_s2(N=2, H=28, W=28, C=256, K=512, R=1, pad=0),
+        "dgrad_s2_1x1_addend": lambda: st.check_dgrad_s2(N=2, H=14, W=14, C=64, K=128, R=1, pad=0, with_addend=True),
+        "dgrad_s2_grouped": lambda: st.check_dgrad_s2(N=2, H=28, W=28, C=224, K=224, G=2),
+        "dgrad_s2_5x5": lambda: st.check_dgrad_s2(N=2, H=12, W=12, C=64, K=64, R=5, pad=2),
+        "thin_groups_cg4": lambda: st.check_thin_groups(),
+        "thin_groups_cg8_s2": lambda: st.check_thin_groups(C=256, G=32, H=28, W=28, stride=2),
+        "thin_groups_cg16": lambda: st.check_thin_groups(C=512, G=32, H=7, W=7),
+        "se_silu_r4": lambda: st.check_se(),
+        "se_relu_r308": lambda: st.check_se(N=9, H=4, W=4, C=1232, r=308, act="relu"),
+        "se_silu_r20": lambda: st.check_se(N=33, H=7, W=7, C=480, r=20),
+        "colsum": st.check_colsum,
         "depthwise_5x5_s2": lambda: st.check_depthwise(k=5, stride=2),
         "depthwise_3x3_s1": lambda: st.check_depthwise(k=3, stride=1, C=32, H=16, W=16),
         "engine_resnet18": lambda: st.check_engine_vs_torch("resnet18", batch=16, size=64),
