@@ -160,11 +160,17 @@ int pick_bn(int n) { return n > 128 ? 256 : (n > 64 ? 128 : 64); }
 // CTA's whole weight slab (k_iters x BN x 128 B) fits in shared memory next to >= 2 A stages, keeping it resident
 // removes that L2->SM traffic (the dominant term for the K <= 256 pointwise layers).  Pick whichever moves fewer
 // bytes per 128-row tile: resident = A * ceil(N/bn);  streaming = (A + B) * ceil(N/bn).
-struct TilePlan { int bn; int resident; int res_stages; };
+// CTA pairs (tcgen05 cta_group::2, conv_gemm.cu): on for every eligible layer unless B200_CONV_CG=1 (A/B measurements).
+bool cta_pairs_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200_CONV_CG"); v = (e && atoi(e) == 1) ? 0 : 1; }
+  return v == 1;
+}
+struct TilePlan { int bn; int resident; int res_stages; int cg; };
 TilePlan plan_tiles(int n_cols, int k_iters, long long m_tiles, int groups, int sms) {
   constexpr int kRing = 160 * 1024, kA = 16384;
   const int bn0 = pick_bn(n_cols);
-  TilePlan best{bn0, 0, 0};
+  TilePlan best{bn0, 0, 0, 1};
   if (groups != 1) return best;
   auto nblk = [&](int bn) { return (n_cols + bn - 1) / bn; };
   // Measured (profiles/conv_shapes_*): shrinking BN to make the slab fit, or running with fewer than 4 A stages,
@@ -174,8 +180,10 @@ TilePlan plan_tiles(int n_cols, int k_iters, long long m_tiles, int groups, int 
     const int bn = bn0;
     const long long slab = (long long)k_iters * bn * 128;
     const int stages = slab <= kRing ? (int)((kRing - slab) / kA) : 0;
-    if (stages >= 4 && nblk(bn) <= sms && m_tiles * nblk(bn) >= 2LL * sms) best = TilePlan{bn, 1, std::min(stages, 12)};
+    if (stages >= 4 && nblk(bn) <= sms && m_tiles * nblk(bn) >= 2LL * sms) best = TilePlan{bn, 1, std::min(stages, 12), 1};
   }
+  // streaming layers with a wide N tile: a CTA pair shares the weight tile (each CTA stages half of it)
+  if (!best.resident && best.bn >= 128 && m_tiles >= 2 && cta_pairs_enabled()) best.cg = 2;
   return best;
 }
 
@@ -213,10 +221,16 @@ ConvGeom geom(const at::Tensor& x, const at::Tensor& w, int stride, int pad, int
 // x [N,H,W,C], w [K,R,S,C], out [N,P,Q,K] (all bf16, contiguous).  stats: fp32 [2*K] accumulated, bias fp32 [K].
 void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const c10::optional<at::Tensor>& stats,
                 const c10::optional<at::Tensor>& bias, int64_t stride, int64_t pad, int64_t dil, int64_t groups) {
-  check_bf16_contig(x, "x"); check_bf16_contig(w, "w"); check_bf16_contig(out, "out");
+  check_bf16_contig(x, "x"); check_bf16_contig(w, "w");
   c10::cuda::CUDAGuard guard(x.device());
   const ConvGeom g = geom(x, w, stride, pad, dil, groups);
-  TORCH_CHECK(out.numel() == (int64_t)g.N * g.P * g.Q * g.K, "bad output shape");
+  // out: [N,P,Q,K] bf16, channels contiguous, uniform pixel pitch >= K (a channel slice of a wider NHWC buffer is fine:
+  // the TMA-store epilogue takes the pitch from its tensor map -- concat-free DenseNet blocks)
+  TORCH_CHECK(out.is_cuda() && out.scalar_type() == at::kBFloat16 && out.dim() == 4 && out.numel() == (int64_t)g.N * g.P * g.Q * g.K, "bad output shape");
+  const int64_t out_pitch = out.stride(2);
+  TORCH_CHECK(out.stride(3) == 1 && out_pitch >= g.K && out_pitch % 8 == 0 && out.stride(1) == g.Q * out_pitch &&
+              out.stride(0) == (int64_t)g.P * g.Q * out_pitch, "output must be NHWC with a uniform pixel pitch (multiple of 8)");
+  TORCH_CHECK(groups == 1 || out_pitch == g.K, "grouped convolutions need a dense output");
   const int G = groups, cin_g = g.C / G, cout_g = g.K / G;
   TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8 (", cin_g, ", ", cout_g, ")");
   const int M = g.N * g.P * g.Q;
@@ -228,15 +242,17 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   p.kind = KIND_FPROP; p.epi = EPI_BF16;
   p.M = M; p.N = cout_g;
   p.groups = G; p.a_cg = cin_g; p.out_cg = cout_g;
-  p.m_blocks = (M + 127) / 128; p.n_blocks = (cout_g + bn - 1) / bn;
+  const int cg = plan.cg;
+  p.cta_group = cg;
+  p.m_blocks = (M + 128 * cg - 1) / (128 * cg); p.n_blocks = (cout_g + bn - 1) / bn;
   p.taps = g.R * g.S; p.S = g.S; p.kb_per_tap = (cin_g + 63) / 64; p.dil = dil;
   p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
   p.b_im2col = 0; p.b_nbox = 1; p.b_kstep16 = kKMajorStep16; p.b_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
   p.b_flip_taps = 0;
-  p.idesc = idesc_bf16(128, bn, 0, 0);
+  p.idesc = idesc_bf16(128 * cg, bn, 0, 0);
   p.im_P = g.P; p.im_Q = g.Q; p.im_stride = stride; p.im_low_w = -pad; p.im_low_h = -pad;
   p.k_blocks_total = 0; p.splits = 1;
-  p.out = out.data_ptr(); p.ldo = g.K; p.tap_stride = 0;
+  p.out = out.data_ptr(); p.ldo = out_pitch; p.tap_stride = 0;
   p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;
   p.bias = bias.has_value() ? bias->data_ptr<float>() : nullptr;
   if (bias.has_value()) p.epi = EPI_BF16_BIAS;
@@ -248,9 +264,9 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
                        : im2col_map_4d(x.data_ptr(), g.N, g.H, g.W, g.C, -pad, -pad, pad - (g.S - 1) * dil,
                                        pad - (g.R - 1) * dil, stride, 64, 128);
   CUtensorMap mb = tiled_map_4d(w.data_ptr(), cin_g, p.taps, cout_g, G, cin_g, (uint64_t)p.taps * cin_g,
-                                (uint64_t)p.taps * cin_g * cout_g, 64, 1, bn, 1);
-  CUtensorMap mo = tiled_map_3d(out.data_ptr(), cout_g, M, G, g.K, cout_g, 64, 32, 1);
-  int grid = std::min(p.total_items, num_sms());
+                                (uint64_t)p.taps * cin_g * cout_g, 64, 1, bn / cg, 1);   // pair: each CTA loads half the N tile
+  CUtensorMap mo = tiled_map_3d(out.data_ptr(), cout_g, M, G, out_pitch, cout_g, 64, 32, 1);
+  int grid = cg == 2 ? 2 * std::min(p.total_items, num_sms() / 2) : std::min(p.total_items, num_sms());
   if (p.b_resident) grid = (grid / p.n_blocks) * p.n_blocks;   // every CTA keeps ONE n-block for its whole life
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &mo, &p, bn, grid, cur_stream()));
 }
@@ -286,13 +302,15 @@ void dgrad_launch(const at::Tensor& dy, const at::Tensor& w, at::Tensor& out, co
   p.kind = KIND_DGRAD; p.epi = EPI_BF16;
   p.M = M; p.N = cin_g;
   p.groups = G; p.a_cg = cout_g; p.out_cg = cin_g;
-  p.m_blocks = (M + 127) / 128; p.n_blocks = (cin_g + bn - 1) / bn;
+  const int cg = plan.cg;
+  p.cta_group = cg;
+  p.m_blocks = (M + 128 * cg - 1) / (128 * cg); p.n_blocks = (cin_g + bn - 1) / bn;
   p.taps = taps_v; p.S = gm.Sv; p.kb_per_tap = (cout_g + 63) / 64; p.dil = gm.dil;
   p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
-  p.b_im2col = 0; p.b_nbox = bn / 64; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
+  p.b_im2col = 0; p.b_nbox = bn / 64 / cg; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
   p.b_flip_taps = gm.lut ? 0 : 1;
   if (gm.lut) { p.tap_lut_on = 1; for (int t = 0; t < taps_v; ++t) p.tap_lut[t] = gm.lut[t]; }
-  p.idesc = idesc_bf16(128, bn, 0, 1);
+  p.idesc = idesc_bf16(128 * cg, bn, 0, 1);
   p.im_P = gm.Ho; p.im_Q = gm.Wo; p.im_stride = 1; p.im_low_w = gm.low_w; p.im_low_h = gm.low_h;
   p.splits = 1;
   p.out = out.data_ptr(); p.ldo = C;
@@ -314,7 +332,7 @@ void dgrad_launch(const at::Tensor& dy, const at::Tensor& w, at::Tensor& out, co
     p.epi = EPI_BF16_ADD;
     md = tiled_map_3d(addend->data_ptr(), cin_g, M, G, C, cin_g, 64, 32, 1);
   }
-  int grid = std::min(p.total_items, num_sms());
+  int grid = cg == 2 ? 2 * std::min(p.total_items, num_sms() / 2) : std::min(p.total_items, num_sms());
   if (p.b_resident) grid = (grid / p.n_blocks) * p.n_blocks;
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &mo, &md, &p, bn, grid, cur_stream()));
 }
@@ -396,23 +414,26 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   for (int cand = 4; cand >= 1; --cand) if (vboxes % cand == 0) { vpi = cand; break; }
   if (vpi == 1 && vboxes > 4) vpi = 4;            // no nice divisor: groups of 4 with a short tail group
   const int bn = vpi > 2 ? 256 : (vpi == 2 ? 128 : 64);
+  // CTA pairs: two 128-row blocks of Cout share the item's X boxes (each CTA stages half of them)
+  const int cg = (cta_pairs_enabled() && cout_g >= 256 && (vpi == 2 || vpi == 4) && vboxes % vpi == 0) ? 2 : 1;
   ConvGemmParams p{};
   p.kind = KIND_WGRAD; p.epi = EPI_F32_RED;
+  p.cta_group = cg;
   p.M = cout_g; p.N = cin_g;
   p.groups = G; p.a_cg = cin_g; p.out_cg = cout_g;
-  p.m_blocks = (cout_g + 127) / 128; p.n_blocks = (vboxes + vpi - 1) / vpi;
+  p.m_blocks = (cout_g + 128 * cg - 1) / (128 * cg); p.n_blocks = (vboxes + vpi - 1) / vpi;
   p.vb_per_item = vpi; p.cin_boxes = cin_boxes; p.vboxes_total = vboxes;
   p.taps = R * S; p.S = S; p.kb_per_tap = 0; p.dil = dil;
   p.a_im2col = 0; p.a_nbox = 2; p.a_kstep16 = kMnMajorStep16; p.a_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
   p.b_im2col = pointwise ? 0 : 1; p.b_nbox = vpi; p.b_kstep16 = kMnMajorStep16; p.b_desc_hi = desc_hi_sw128(kMnMajorLbo, kMnMajorSbo);
   p.b_flip_taps = 0;
-  p.idesc = idesc_bf16(128, 64 * vpi, 1, 1);
+  p.idesc = idesc_bf16(128 * cg, 64 * vpi, 1, 1);
   p.im_P = P; p.im_Q = Q; p.im_stride = stride; p.im_low_w = -pad; p.im_low_h = -pad;
   p.k_blocks_total = (int)((pixels + 63) / 64);
   const int base_items = p.m_blocks * p.n_blocks * G;
   // split-K so that the item count is just UNDER a whole number of waves (an extra partial wave costs a full
   // item time): aim at 2 waves, fall back to no split for shapes that already have many items
-  const int sms = num_sms();
+  const int sms = num_sms() / cg;     // schedulable units: SMs, or SM pairs
   int splits = (2 * sms) / base_items;
   if (splits < 1) splits = 1;
   splits = std::max(1, std::min(splits, std::max(1, p.k_blocks_total / 8)));
@@ -423,7 +444,7 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   CUtensorMap mb = pointwise ? tiled_map_3d(x.data_ptr(), C, 1, pixels, C, C, 64, 1, 64)
                              : im2col_map_4d(x.data_ptr(), N, H, W, C, -pad, -pad, pad - (S - 1) * dil,
                                              pad - (R - 1) * dil, stride, 64, 64);
-  const int grid = std::min(p.total_items, num_sms());
+  const int grid = cg == 2 ? 2 * std::min(p.total_items, num_sms() / 2) : std::min(p.total_items, num_sms());
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &ma, &ma, &p, bn, grid, cur_stream()));
 }
 
@@ -533,12 +554,11 @@ void bn_backward(const at::Tensor& y, const at::Tensor& dout, const c10::optiona
   // phase: 3 = reduce + apply (normal); 1 / 2 = only that pass (tools/bench_bn.py times them separately)
   c10::cuda::CUDAGuard guard(y.device());
   TORCH_CHECK(y.dim() == 2 && y.stride(1) == 1 && dout.stride(1) == 1 && dy.stride(1) == 1, "bn_backward expects [rows, C] views");
-  TORCH_CHECK(dy.stride(0) == y.stride(0), "dy must share y's row pitch");
   BnBwdParams p{};
   p.y = bptr(y); p.ldy = y.stride(0);
   p.dout = bptr(dout); p.ldd = dout.stride(0);
   p.residual = residual.has_value() ? bptr(*residual) : nullptr; p.ldr = residual.has_value() ? residual->stride(0) : 0;
-  p.dy = bptr_mut(dy);
+  p.dy = bptr_mut(dy); p.lddy = dy.stride(0);
   p.dresidual = dresidual.has_value() ? bptr_mut(*dresidual) : nullptr;
   if (dresidual.has_value()) { TORCH_CHECK(!residual.has_value() || dresidual->stride(0) == residual->stride(0), "dresidual pitch"); p.ldr = dresidual->stride(0); }
   p.rows = y.size(0); p.C = y.size(1);

@@ -23,11 +23,15 @@ constexpr int kEpiWarps = 8;                 // two per TMEM lane quarter: laten
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kNumThreads = 64 + kEpiThreads;
 
-template <int BN>
+// CG = CTAs per MMA (tcgen05 cta_group): with CG == 2 a CTA pair (cluster of 2, same TPC) works on a 256 x BN tile --
+// each CTA stages its own 128 A rows but only HALF of the B tile, which the pair's single MMA reads from both shared
+// memories.  L2->SM bytes per k-block drop from 16 + BN/8 KB to 16 + BN/16 KB per SM, and that ingest rate (~40
+// B/clk/SM measured in round 1, see profiles/) is what bounds every compute-heavy layer.
+template <int BN, int CG>
 struct Cfg {
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (BN / CG) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (BN == 256) ? 3 : (BN == 128 ? 5 : 6);
+  static constexpr int kStages = (CG == 2) ? (BN == 256 ? 5 : 6) : ((BN == 256) ? 3 : (BN == 128 ? 5 : 6));
   static constexpr int kTmemCols = 2 * BN;  // two accumulator stages; 128/256/512 are all legal allocations
   static constexpr int kStagingBytes = kEpiWarps * 2 /*double buffer*/ * 4096;  // 32 rows x 128 B each
   static constexpr int kMaxStages = 12;     // resident-weights mode re-partitions the ring into A-only stages
@@ -53,14 +57,15 @@ struct WorkItem { int m0, n0, nb, tap, it_begin, it_end, vb0, nbox, g; };
 
 // out of line on purpose: three warp roles call it once per work item; inlining triples ~150 instructions of
 // integer division in an instruction-cache-bound kernel
-static __device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn) {
+// m_span = rows covered by one item (BM per CTA of the pair), m_off = this CTA's offset inside it
+static __device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn, int m_span, int m_off) {
   WorkItem w;
   if (p.kind != KIND_WGRAD) {
     int nb = item % p.n_blocks;
     int rest = item / p.n_blocks;
     int mb = rest % p.m_blocks;
     w.g = rest / p.m_blocks;                       // conv group (0 when groups == 1)
-    w.m0 = mb * BM; w.n0 = nb * bn; w.nb = w.g * p.n_blocks + nb; w.tap = 0; w.vb0 = 0; w.nbox = 0;
+    w.m0 = mb * m_span + m_off; w.n0 = nb * bn; w.nb = w.g * p.n_blocks + nb; w.tap = 0; w.vb0 = 0; w.nbox = 0;
     w.it_begin = 0; w.it_end = p.taps * p.kb_per_tap;
   } else {
     // wgrad: an item owns `nbox` consecutive virtual B boxes (tap, 64-channel slice of Cin) -> N = 64*nbox columns
@@ -68,7 +73,7 @@ static __device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int
     int group = rest % p.n_blocks; rest /= p.n_blocks;
     int mb = rest % p.m_blocks;
     w.g = rest / p.m_blocks;
-    w.m0 = mb * BM; w.n0 = 0; w.nb = group; w.tap = 0;
+    w.m0 = mb * m_span + m_off; w.n0 = 0; w.nb = group; w.tap = 0;
     w.vb0 = group * p.vb_per_item;
     w.nbox = min(p.vb_per_item, p.vboxes_total - w.vb0);
     w.it_begin = (int)(((long long)p.k_blocks_total * split) / p.splits);
@@ -77,12 +82,12 @@ static __device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int
   return w;
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 __global__ void __launch_bounds__(kNumThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                  const __grid_constant__ CUtensorMap map_out, const __grid_constant__ CUtensorMap map_add,
                  const __grid_constant__ ConvGemmParams p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, CG>;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment is required by the 128B swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -106,6 +111,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // CTA pair bookkeeping: both CTAs walk the same item sequence; rank 0 (the leader) issues the MMAs
+  const uint32_t cta_rank = (CG == 2) ? cluster_ctarank() : 0u;
+  const bool leader = (cta_rank == 0);
+  const int item0 = (CG == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int item_stride = (CG == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int m_span = BM * CG, m_off = (int)cta_rank * BM;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_a);
@@ -113,16 +124,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (EPI != EPI_F32_RED) tma_prefetch_desc(&map_out);
     for (int i = 0; i < C::kMaxStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
     mbar_init(smem_u32(bres_bar), 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiThreads); }
+    // tmem_empty of the leader collects the epilogue threads of BOTH CTAs (the peer's arrive remotely)
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiThreads * CG); }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(smem_u32(&add_bar[i]), 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(smem_u32(tmem_ptr), C::kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) { tmem_alloc_2cta(smem_u32(tmem_ptr), C::kTmemCols); tmem_relinquish_2cta(); }
+    else { tmem_alloc(smem_u32(tmem_ptr), C::kTmemCols); tmem_relinquish(); }
   }
   tc_fence_before();
-  __syncthreads();
+  __syncwarp();                      // (lane 0 of warp 0 initialised the barriers in a divergent branch)
+  if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -131,8 +145,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       if (resident && (int)blockIdx.x < p.total_items) {
-        // every item of this CTA has the same n-block (grid is a multiple of n_blocks, groups == 1)
-        const WorkItem w0 = decode_item(p, blockIdx.x, BN);
+        // every item of this CTA has the same n-block (grid is a multiple of n_blocks, groups == 1); CG == 1 only
+        const WorkItem w0 = decode_item(p, blockIdx.x, BN, BM, 0);
         const uint32_t bb = smem_u32(bres_bar);
         mbar_expect_tx(bb, (uint32_t)(k_iters_fd * C::kBBytes));
         for (int it = 0; it < k_iters_fd; ++it) {
@@ -152,8 +166,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       // pace.  Divisions now happen once per work item; the reduction-pixel coordinate advances by BK per stage.
       const int step_p = (p.b_im2col && p.kind == KIND_WGRAD) ? BK / p.im_Q : 0;   // BK pixels = step_p rows + step_q
       const int step_q = (p.b_im2col && p.kind == KIND_WGRAD) ? BK - step_p * p.im_Q : 0;
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const WorkItem w = decode_item(p, item, BN);
+      // CG == 2: TMA completions of both CTAs are counted by the LEADER's full barrier (same offset, peer bit cleared)
+      const int n_half = (CG == 2) ? (int)cta_rank * (BN / 2) : 0;   // this CTA's half of the B tile (columns of the output)
+      for (int item = item0; item < p.total_items; item += item_stride) {
+        const WorkItem w = decode_item(p, item, BN, m_span, m_off);
         if (p.kind != KIND_WGRAD) {
           PixelCoord pa{0, 0, 0};
           if (p.a_im2col) pa = decode_pixel(p, w.m0);
@@ -161,12 +177,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           int tap = 0, kb = 0, r = 0, sx = 0;               // it_begin == 0 for fprop / dgrad
           for (int it = w.it_begin; it < w.it_end; ++it) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            const uint32_t bar = smem_u32(&full_bar[stage]);
+            const uint32_t bar_local = smem_u32(&full_bar[stage]);
+            const uint32_t bar = (CG == 2) ? (bar_local & kPeerBitMask) : bar_local;
             const uint32_t dst_a = smem_u32(smem_a + stage * kABytes);
             const uint32_t dst_b = smem_u32(smem_b + stage * C::kBBytes);
-            mbar_expect_tx(bar, resident ? (uint32_t)kABytes : (uint32_t)C::kStageBytes);
+            if (CG == 1) mbar_expect_tx(bar, resident ? (uint32_t)kABytes : (uint32_t)C::kStageBytes);
+            else if (leader) mbar_expect_tx(bar_local, 2u * (uint32_t)C::kStageBytes);
             const int ca = ca0 + kb * BK;                    // group slice + K block
-            if (p.a_im2col)
+            if (CG == 2) {
+              if (p.a_im2col)
+                tma_load_im2col_4d_2cta(dst_a, &map_a, bar, ca, pa.w, pa.h, pa.n, (uint16_t)(sx * p.dil), (uint16_t)(r * p.dil));
+              else
+                tma_load_3d_2cta(dst_a, &map_a, bar, ca, 0, w.m0);
+            } else if (p.a_im2col)
               tma_load_im2col_4d(dst_a, &map_a, bar, ca, pa.w, pa.h, pa.n, (uint16_t)(sx * p.dil), (uint16_t)(r * p.dil));
             else
               tma_load_3d(dst_a, &map_a, bar, ca, 0, w.m0);
@@ -174,6 +197,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
             // weights are mapped as (Cin/g, taps, Cout/g, groups): anything past a group's extent is zero-filled
             if (resident) {
               // B slab already in shared memory
+            } else if (CG == 2) {                                             // this CTA's half of the weight tile
+              if (p.kind == KIND_FPROP) {
+                tma_load_4d_2cta(dst_b, &map_b, bar, kb * BK, btap, w.n0 + n_half, w.g);
+              } else {
+                for (int j = 0; j < p.b_nbox; ++j)
+                  tma_load_4d_2cta(dst_b + j * kBoxBytes, &map_b, bar, w.n0 + n_half + 64 * j, btap, kb * BK, w.g);
+              }
             } else if (p.kind == KIND_FPROP) {
               tma_load_4d(dst_b, &map_b, bar, kb * BK, btap, w.n0, w.g);      // K-major weights [N][tap][K]
             } else {
@@ -205,26 +235,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
           for (int it = w.it_begin; it < w.it_end; ++it) {
             mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
-            const uint32_t bar = smem_u32(&full_bar[stage]);
+            const uint32_t bar_local = smem_u32(&full_bar[stage]);
+            const uint32_t bar = (CG == 2) ? (bar_local & kPeerBitMask) : bar_local;
             const uint32_t dst_a = smem_u32(smem_a + stage * kABytes);
             const uint32_t dst_b = smem_u32(smem_b + stage * C::kBBytes);
-            mbar_expect_tx(bar, (uint32_t)(kABytes + w.nbox * kBoxBytes));
+            // CG == 2: each CTA stages its own dY^T tile (different Cout rows) and HALF of the item's X boxes
+            const int nb_mine = (CG == 2) ? (w.nbox >> 1) : w.nbox;
+            const int jb0 = (CG == 2) ? (int)cta_rank * nb_mine : 0;
+            if (CG == 1) mbar_expect_tx(bar, (uint32_t)(kABytes + w.nbox * kBoxBytes));
+            else if (leader) mbar_expect_tx(bar_local, 2u * (uint32_t)(kABytes + nb_mine * kBoxBytes));
             const int k0 = it * BK;  // first reduction pixel of this block
-            for (int j = 0; j < p.a_nbox; ++j)
-              tma_load_3d(dst_a + j * kBoxBytes, &map_a, bar, a_c0 + 64 * j, 0, k0);
+            for (int j = 0; j < p.a_nbox; ++j) {
+              if (CG == 2) tma_load_3d_2cta(dst_a + j * kBoxBytes, &map_a, bar, a_c0 + 64 * j, 0, k0);
+              else tma_load_3d(dst_a + j * kBoxBytes, &map_a, bar, a_c0 + 64 * j, 0, k0);
+            }
             if (p.b_im2col) {
               const int cw = q * p.im_stride + p.im_low_w, chh = ph * p.im_stride + p.im_low_h;
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j < w.nbox)
-                  tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, box_c[j], cw, chh, n, (uint16_t)box_ow[j], (uint16_t)box_oh[j]);
+              for (int j = 0; j < 4; ++j) {
+                if (j >= jb0 && j < jb0 + nb_mine) {
+                  if (CG == 2) tma_load_im2col_4d_2cta(dst_b + (j - jb0) * kBoxBytes, &map_b, bar, box_c[j], cw, chh, n, (uint16_t)box_ow[j], (uint16_t)box_oh[j]);
+                  else tma_load_im2col_4d(dst_b + j * kBoxBytes, &map_b, bar, box_c[j], cw, chh, n, (uint16_t)box_ow[j], (uint16_t)box_oh[j]);
+                }
+              }
               q += step_q; ph += step_p;
               if (q >= p.im_Q) { q -= p.im_Q; ++ph; }
               while (ph >= p.im_P) { ph -= p.im_P; ++n; }
             } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j)
-                if (j < w.nbox) tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, box_c[j], 0, k0);
+              for (int j = 0; j < 4; ++j) {
+                if (j >= jb0 && j < jb0 + nb_mine) {
+                  if (CG == 2) tma_load_3d_2cta(dst_b + (j - jb0) * kBoxBytes, &map_b, bar, box_c[j], 0, k0);
+                  else tma_load_3d(dst_b + j * kBoxBytes, &map_b, bar, box_c[j], 0, k0);
+                }
+              }
             }
             if (++stage == n_stages) { stage = 0; phase ^= 1; }
           }
@@ -233,12 +277,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    if (lane == 0 && (CG == 1 || leader)) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       if (resident && (int)blockIdx.x < p.total_items) { mbar_wait(smem_u32(bres_bar), 0); tc_fence_after(); }
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const WorkItem w = decode_item(p, item, BN);
+      for (int item = item0; item < p.total_items; item += item_stride) {
+        const WorkItem w = decode_item(p, item, BN, m_span, m_off);
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);   // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
@@ -250,13 +294,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           const uint8_t* b_tile = resident ? (smem_b + (it - w.it_begin) * C::kBBytes) : (smem_b + stage * C::kBBytes);
           const uint64_t b_desc = p.b_desc_hi | (uint64_t)((smem_u32(b_tile) >> 4) & 0x3fff);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_d, a_desc + (uint64_t)(k * p.a_kstep16), b_desc + (uint64_t)(k * p.b_kstep16), idesc,
-                      (it > w.it_begin || k > 0) ? 1u : 0u);
-          umma_commit(smem_u32(&empty_bar[stage]));               // frees the smem slot when the MMAs retire
+          for (int k = 0; k < BK / 16; ++k) {
+            if (CG == 2)
+              umma_bf16_2cta(tmem_d, a_desc + (uint64_t)(k * p.a_kstep16), b_desc + (uint64_t)(k * p.b_kstep16), idesc,
+                             (it > w.it_begin || k > 0) ? 1u : 0u);
+            else
+              umma_bf16(tmem_d, a_desc + (uint64_t)(k * p.a_kstep16), b_desc + (uint64_t)(k * p.b_kstep16), idesc,
+                        (it > w.it_begin || k > 0) ? 1u : 0u);
+          }
+          // frees the smem slot (in both CTAs of a pair) when the MMAs retire
+          if (CG == 2) umma_commit_2cta(smem_u32(&empty_bar[stage])); else umma_commit(smem_u32(&empty_bar[stage]));
           if (++stage == n_stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(smem_u32(&tmem_full[acc]));                   // accumulator complete -> epilogue
+        // accumulator complete -> epilogue warps (of both CTAs)
+        if (CG == 2) umma_commit_2cta(smem_u32(&tmem_full[acc])); else umma_commit(smem_u32(&tmem_full[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -358,8 +409,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         st_sum[ci][0] += a0; st_sum[ci][1] += a1; st_sq[ci][0] += q0; st_sq[ci][1] += q1;
       };
 
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const WorkItem w = decode_item(p, item, BN);
+      for (int item = item0; item < p.total_items; item += item_stride) {
+        const WorkItem w = decode_item(p, item, BN, m_span, m_off);
         if (want_stats && w.nb != st_nb) { flush_stats(st_nb); st_nb = w.nb; }
         mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
         tc_fence_after();
@@ -416,7 +467,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&tmem_empty[acc]));
+        if (CG == 2) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & kPeerBitMask); else mbar_arrive(smem_u32(&tmem_empty[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (want_stats) flush_stats(st_nb);
@@ -424,8 +475,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
       __syncwarp();
     } else {
       // EPI_F32_RED: split-K partial sums into fp32 dW[M][taps][N]
-      for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const WorkItem w = decode_item(p, item, BN);
+      for (int item = item0; item < p.total_items; item += item_stride) {
+        const WorkItem w = decode_item(p, item, BN, m_span, m_off);
         mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
         tc_fence_after();
         const int row = w.m0 + row_in_tile;
@@ -460,30 +511,43 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         tc_fence_before();
-        mbar_arrive(smem_u32(&tmem_empty[acc]));
+        if (CG == 2) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & kPeerBitMask); else mbar_arrive(smem_u32(&tmem_empty[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   }
 
+  __syncwarp();                      // the single-lane producer / MMA loops rejoin their warps before the aligned barrier
   tc_fence_before();
-  __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+  if (CG == 2) cluster_sync_all();   // nobody leaves (or frees TMEM) while the peer can still signal this CTA's barriers
+  else __syncthreads();
+  if (warp == 1) {
+    if (CG == 2) tmem_dealloc_2cta(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
+  }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, int CG>
 static cudaError_t launch_one(const CUtensorMap& ma, const CUtensorMap& mb, const CUtensorMap& mo, const CUtensorMap& md,
                               const ConvGemmParams& p, int grid, cudaStream_t stream) {
-  using C = Cfg<BN>;
-  auto kern = conv_gemm_kernel<BN, EPI>;
+  using C = Cfg<BN, CG>;
+  auto kern = conv_gemm_kernel<BN, EPI, CG>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return e;
     configured = true;
   }
-  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ma, mb, mo, md, p);
-  return cudaGetLastError();
+  if (CG == 1) {
+    kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(ma, mb, mo, md, p);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kNumThreads); cfg.dynamicSmemBytes = C::kSmemBytes; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, ma, mb, mo, md, p);
 }
 
 }  // namespace b200
@@ -493,15 +557,27 @@ extern "C" int b200_conv_gemm_launch(const CUtensorMap* map_a, const CUtensorMap
                                      cudaStream_t stream) {
   using namespace b200;
   cudaError_t e = cudaErrorInvalidValue;
-#define B200_DISPATCH_BN(EPI_)                                                                          \
-  do {                                                                                                 \
-    if (bn == 64) e = launch_one<64, EPI_>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);       \
-    else if (bn == 128) e = launch_one<128, EPI_>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream); \
-    else if (bn == 256) e = launch_one<256, EPI_>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream); \
+  const int cg = p->cta_group == 2 ? 2 : 1;
+#define B200_DISPATCH_BN(EPI_)                                                                             \
+  do {                                                                                                    \
+    if (cg == 1) {                                                                                        \
+      if (bn == 64) e = launch_one<64, EPI_, 1>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);     \
+      else if (bn == 128) e = launch_one<128, EPI_, 1>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream); \
+      else if (bn == 256) e = launch_one<256, EPI_, 1>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream); \
+    } else {                                                                                              \
+      if (bn == 128) e = launch_one<128, EPI_, 2>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);   \
+      else if (bn == 256) e = launch_one<256, EPI_, 2>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream); \
+    }                                                                                                     \
   } while (0)
   switch (p->epi) {
     case EPI_BF16: B200_DISPATCH_BN(EPI_BF16); break;
-    case EPI_BF16_BIAS: B200_DISPATCH_BN(EPI_BF16_BIAS); break;
+    case EPI_BF16_BIAS:
+      if (cg == 1) {
+        if (bn == 64) e = launch_one<64, EPI_BF16_BIAS, 1>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
+        else if (bn == 128) e = launch_one<128, EPI_BF16_BIAS, 1>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
+        else if (bn == 256) e = launch_one<256, EPI_BF16_BIAS, 1>(*map_a, *map_b, *map_out, *map_add, *p, grid, stream);
+      }
+      break;
     case EPI_BF16_ADD: B200_DISPATCH_BN(EPI_BF16_ADD); break;
     case EPI_F32_RED: B200_DISPATCH_BN(EPI_F32_RED); break;
     default: break;

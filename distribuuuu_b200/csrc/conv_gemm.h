@@ -40,6 +40,7 @@ struct ConvGemmParams {
   const float* bias;    // optional [N]
   long long addend;     // non-zero: add the bf16 tile described by map_add before storing (same geometry as out)
   int total_items;
+  int cta_group;        // 1, or 2 = CTA pairs (256-row items, B operand split across the pair); see Cfg in conv_gemm.cu
 };
 
 // map_out: 2-D tiled map over the bf16 output [M][N] (box 64 cols x 32 rows, 128B swizzle) for the TMA-store

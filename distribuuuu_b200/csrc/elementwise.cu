@@ -546,7 +546,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_apply_kernel(BnBwdParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) o[i] = fmaf(d[i], scale[i], fmaf(y[i], ca[i], cb[i]));
       if (p.dresidual) store8(p.dresidual + r * p.ldr + c0, d);
-      store8(p.dy + r * p.ldy + c0, o);
+      store8(p.dy + r * p.lddy + c0, o);
       if (MODE == BWD_MASK) mq[j] = (k_issue < p.rows) ? (uint32_t)__ldg(mrow + (p.rows - 1 - k_issue) * mpitch) : 0u;
       k_issue += rstride;
       st = (st + 1 == D) ? 0 : st + 1;

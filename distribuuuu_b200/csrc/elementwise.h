@@ -49,7 +49,7 @@ struct BnBwdParams {
   const __nv_bfloat16* y; long long ldy;
   const __nv_bfloat16* dout; long long ldd;
   const __nv_bfloat16* residual; long long ldr;  // forward residual (needed to recompute act'(z)); optional
-  __nv_bfloat16* dy;                              // gradient wrt the conv output (pitch ldy)
+  __nv_bfloat16* dy; long long lddy;              // gradient wrt the conv output (own pitch: y may be a channel slice)
   __nv_bfloat16* dresidual;                       // optional gradient wrt the residual input (pitch ldr)
   long long rows; int C;
   float* sums;               // local [2][C]: sum(dz), sum(dz*xhat)

@@ -5,9 +5,9 @@ Parity: reference ``distribuuuu/models/densenet.py`` (dense layer 23-117 incl. t
 trunk 169-263, legacy-key remap 266-282, constructors 300-365).  Key names match
 torchvision (``features.denseblockK.denselayerJ.norm1`` ...).
 
-B200 note: the feature concat (reference densenet.py:68,148 ``torch.cat`` per layer) goes
-through ``Fn.concat_channels`` so the native engine can hand out channel slices of one
-pre-allocated NHWC buffer instead of copying.
+B200 note: a dense block owns one pre-allocated NHWC buffer (``Fn.dense_block_buffer``); every layer's 3x3 conv
+TMA-stores its new features into the next channel slice and ``Fn.concat_channels`` of adjacent slices is a view, so
+the per-layer ``torch.cat`` of the reference (densenet.py:68,148) moves no bytes on the native path.
 """
 from __future__ import annotations
 
@@ -58,13 +58,13 @@ class _DenseLayer(nn.Module):
         with runtime.native_scope(engine):
             return self._bottleneck(*features)
 
-    def forward(self, features):
+    def forward(self, features, out_buffer=None):
         feats = [features] if torch.is_tensor(features) else list(features)
         if self.memory_efficient and any(f.requires_grad for f in feats):
             mid = cp.checkpoint(functools.partial(self._bottleneck_on, runtime.active_engine()), *feats, use_reentrant=False)
         else:
             mid = self._bottleneck(*feats)
-        new = Fn.conv2d(Fn.bn_act(mid, self.norm2, "relu"), self.conv2)
+        new = Fn.conv2d(Fn.bn_act(mid, self.norm2, "relu"), self.conv2, out_buffer=out_buffer)
         return Fn.dropout(new, self.drop_rate, self.training)
 
 
@@ -74,11 +74,13 @@ class _DenseBlock(nn.ModuleDict):
         for i in range(num_layers):
             self[f"denselayer{i + 1}"] = _DenseLayer(cin + i * growth_rate, growth_rate, bn_size,
                                                      drop_rate, memory_efficient)
+        self.total_channels = cin + num_layers * growth_rate
 
     def forward(self, x):
+        x, buf = Fn.dense_block_buffer(x, self.total_channels)
         feats = [x]
         for layer in self.values():
-            feats.append(layer(feats))
+            feats.append(layer(feats, buf))
         return Fn.concat_channels(feats)
 
 

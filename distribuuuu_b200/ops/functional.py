@@ -31,17 +31,19 @@ def _act(x, act):
 
 
 def conv_bn_act(x, conv: nn.Conv2d, bn: nn.Module | None, act: str | None = None, residual=None, residual_sink=None,
-                input_grad_to=None):
+                input_grad_to=None, out_buffer=None):
     """``act(bn(conv(x)) + residual)``; ``bn``/``act``/``residual`` optional.
 
     ``residual_sink``: the conv module (of the same block) that consumes the *same tensor* as ``residual``; a hint
     that lets the native engine fold the residual-branch gradient into that conv's dgrad epilogue.
     ``input_grad_to``: a conv module applied EARLIER in this forward to the *same tensor* ``x`` (a projection
     shortcut); this conv's input gradient is then handed to that conv's dgrad instead of being summed by a separate
-    kernel.  Both are hints: ignored on the torch path and whenever the tensors do not actually coincide."""
+    kernel.  Both are hints: ignored on the torch path and whenever the tensors do not actually coincide.
+    ``out_buffer``: handle from ``dense_block_buffer``; a plain conv then stores its output straight into the block's
+    feature buffer (no later concatenation copy)."""
     eng = runtime.active_engine()
     if eng is not None:
-        return eng.ops.conv_bn_act(x, conv, bn, act, residual, residual_sink, input_grad_to)
+        return eng.ops.conv_bn_act(x, conv, bn, act, residual, residual_sink, input_grad_to, out_buffer)
     y = conv(x)
     if bn is not None:
         y = bn(y)
@@ -58,8 +60,19 @@ def bn_act(x, bn: nn.Module, act: str | None = None):
     return _act(bn(x), act)
 
 
-def conv2d(x, conv: nn.Conv2d, act: str | None = None):
-    return conv_bn_act(x, conv, None, act)
+def conv2d(x, conv: nn.Conv2d, act: str | None = None, out_buffer=None):
+    return conv_bn_act(x, conv, None, act, out_buffer=out_buffer)
+
+
+def dense_block_buffer(x, total_channels: int):
+    """DenseNet blocks: returns ``(x, handle)``.  With the native engine, ``x`` becomes a view into one pre-allocated
+    NHWC buffer of ``total_channels`` channels and ``handle`` lets every layer's conv write its new features right
+    behind the previous ones, so ``concat_channels`` of the block's features is a view (reference densenet.py:68,148
+    copies them with ``torch.cat`` in every layer).  On the torch path: ``(x, None)``."""
+    eng = runtime.active_engine()
+    if eng is not None:
+        return eng.ops.dense_block_buffer(x, total_channels)
+    return x, None
 
 
 def linear(x, fc: nn.Linear):

@@ -32,6 +32,91 @@ def _nchw_view(x_nhwc: torch.Tensor) -> torch.Tensor:
     return x_nhwc.permute(0, 3, 1, 2)
 
 
+def _rows_view(x: torch.Tensor):
+    """``([rows, C] view with a row pitch, (N, H, W, C))`` of a logical-NCHW activation WITHOUT copying when it is NHWC
+    with a uniform pixel pitch -- contiguous tensors and channel slices of a wider NHWC buffer (DenseNet blocks)."""
+    v = x.permute(0, 2, 3, 1)
+    N, H, W, C = v.shape
+    pitch = v.stride(2)
+    if v.stride(3) == 1 and pitch >= C and v.stride(1) == W * pitch and v.stride(0) == H * W * pitch:
+        return torch.as_strided(v, (N * H * W, C), (pitch, 1), v.storage_offset()), (N, H, W, C)
+    v = v.contiguous()
+    return v.view(-1, C), (N, H, W, C)
+
+
+class _DenseBuffer:
+    """One pre-allocated NHWC buffer per dense block: the block input is placed in its first channels and every layer's
+    3x3 convolution TMA-stores its ``growth_rate`` new channels right behind -- the concatenated input of layer l is
+    the first c_l channels of the buffer, a view (reference densenet.py:68,148 materialises it with torch.cat)."""
+
+    def __init__(self, buf: torch.Tensor, used: int):
+        self.buf, self.used = buf, used
+
+    def take(self, channels: int):
+        """Channel slice [used, used + channels) as a logical-NCHW view, or None when the buffer is full."""
+        if self.used + channels > self.buf.shape[3]:
+            return None
+        v = self.buf[:, :, :, self.used:self.used + channels]
+        self.used += channels
+        return v
+
+
+class BlockInputFn(torch.autograd.Function):
+    """Places the block input into the first channels of the block buffer; gradients pass straight through."""
+
+    @staticmethod
+    def forward(ctx, x, buf):
+        xh = x.permute(0, 2, 3, 1)
+        C = xh.shape[3]
+        buf[:, :, :, :C].copy_(xh)
+        return _nchw_view(buf[:, :, :, :C])
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+def _adjacent_channel_slices(tensors) -> bool:
+    """True when the tensors are consecutive channel slices of ONE NHWC buffer (same pixel pitch, back to back)."""
+    base = None
+    for t in tensors:
+        if t.dim() != 4 or t.dtype != torch.bfloat16:
+            return False
+        v = t.permute(0, 2, 3, 1)
+        key = (t.untyped_storage().data_ptr(), v.stride(0), v.stride(1), v.stride(2), v.shape[0], v.shape[1], v.shape[2])
+        if v.stride(3) != 1 and v.shape[3] != 1:
+            return False
+        if base is None:
+            base, nxt = key, t.storage_offset() + v.shape[3]
+            continue
+        if key != base or t.storage_offset() != nxt:
+            return False
+        nxt += v.shape[3]
+    return base is not None
+
+
+class ConcatViewFn(torch.autograd.Function):
+    """Channel concatenation of adjacent slices of one buffer: the result is a view, no bytes move.  Backward hands each
+    input its channel range of the incoming gradient (views again; autograd sums the contributions of the later layers)."""
+
+    @staticmethod
+    def forward(ctx, *tensors):
+        t0 = tensors[0]
+        v0 = t0.permute(0, 2, 3, 1)
+        N, H, W, _ = v0.shape
+        ctx.splits = [t.shape[1] for t in tensors]
+        C = sum(ctx.splits)
+        return torch.as_strided(t0.detach(), (N, C, H, W), (v0.stride(0), 1, v0.stride(1), v0.stride(2)), t0.storage_offset())
+
+    @staticmethod
+    def backward(ctx, g):
+        out, off = [], 0
+        for c in ctx.splits:
+            out.append(g.narrow(1, off, c))
+            off += c
+        return tuple(out)
+
+
 class _GradSink:
     """Mailbox between a BnActFn (producer of a residual-branch gradient) and the ConvFn that consumes the same
     block input: the gradient is added inside that conv's dgrad epilogue instead of by a separate add kernel."""
@@ -84,7 +169,7 @@ class ConvFn(torch.autograd.Function):
     """Implicit-GEMM convolution (fprop / dgrad / wgrad on tcgen05), optional BN-statistics epilogue."""
 
     @staticmethod
-    def forward(ctx, x, eng, conv, stats, anchor, hand_to=None):
+    def forward(ctx, x, eng, conv, stats, anchor, hand_to=None, out=None):
         K = eng.K
         xh = _nhwc(x)
         w, groups = _conv_weight(eng, conv)
@@ -93,7 +178,9 @@ class ConvFn(torch.autograd.Function):
         s, p, d = conv.stride[0], conv.padding[0], conv.dilation[0]
         P = (H + 2 * p - d * (R - 1) - 1) // s + 1
         Q = (W + 2 * p - d * (S - 1) - 1) // s + 1
-        y = torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
+        # `out`: a channel slice of a wider NHWC buffer the epilogue stores into directly (dense blocks)
+        y = out if (out is not None and tuple(out.shape) == (N, P, Q, Kc) and groups == 1) else \
+            torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
         K.conv_fprop(xh, w, y, stats, None, s, p, d, groups)
         ctx.eng, ctx.conv = eng, conv
         ctx.save_for_backward(xh)
@@ -140,7 +227,7 @@ class ConvFn(torch.autograd.Function):
                 dx = _nchw_view(dxh)
         # only now: the bucket's fused update overwrites the bf16 weights the dgrad above still reads
         eng.mark_ready(conv.weight)
-        return dx, None, None, None, None, None
+        return dx, None, None, None, None, None, None
 
 
 def _strided_dgrad(K, dyh, w, x_shape, s, p, d, groups=1, addend=None):
@@ -264,11 +351,9 @@ class BnActFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, residual, eng, bn, act, stats_slot, training, anchor, sink=None):
         K = eng.K
-        yh = _nhwc(y)
-        N, H, W, C = yh.shape
-        y2 = yh.view(-1, C)
+        y2, (N, H, W, C) = _rows_view(y)
         res2 = _nhwc(residual).view(-1, C) if residual is not None else None
-        out = torch.empty_like(yh)
+        out = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=y.device)
         save = torch.empty((2, C), dtype=torch.float32, device=y.device)
         peer = eng.peer_state if (training and eng.sync_bn) else None
         count = float(y2.shape[0] * (eng.world if peer is not None else 1))
@@ -609,7 +694,7 @@ class NativeOps:
         return F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
 
     # ---- functional surface ----------------------------------------------------------------------
-    def conv_bn_act(self, x, conv, bn, act, residual, residual_sink=None, input_grad_to=None):
+    def conv_bn_act(self, x, conv, bn, act, residual, residual_sink=None, input_grad_to=None, out_buffer=None):
         eng = self.eng
         training = bn is not None and bn.training
         slot = eng.fwd_slot(bn) if (training and conv.out_channels % 8 == 0) else None
@@ -618,7 +703,9 @@ class NativeOps:
             y = StemConvFn.apply(x, eng, conv, stats, eng.anchor)
         elif self._native_conv_ok(conv, x):
             hand_to = eng.last_sink.get(input_grad_to) if (input_grad_to is not None and torch.is_grad_enabled()) else None
-            y = ConvFn.apply(x, eng, conv, stats, eng.anchor, hand_to)
+            dest = out_buffer.take(conv.out_channels) if (out_buffer is not None and bn is None and act is None
+                                                          and residual is None) else None
+            y = ConvFn.apply(x, eng, conv, stats, eng.anchor, hand_to, dest)
         elif self._depthwise_ok(conv, x):
             y = DwConvFn.apply(x, eng, conv, stats, eng.anchor)
         else:
@@ -653,8 +740,8 @@ class NativeOps:
         training = bn.training
         slot = eng.fwd_slot(bn) if training else None
         if slot is not None:
-            xh = _nhwc(x)
-            eng.K.bn_stats(xh.view(-1, xh.shape[-1]), slot.tensor)
+            x2, _ = _rows_view(x)
+            eng.K.bn_stats(x2, slot.tensor)
         return BnActFn.apply(x, None, eng, bn, act, slot, training, eng.anchor)
 
     def linear(self, x, fc):
@@ -704,10 +791,22 @@ class NativeOps:
         gate = torch.sigmoid(self._se_fc(h, fc2))                     # [N, C]
         return ChannelScaleFn.apply(x, gate, self.eng)
 
+    def dense_block_buffer(self, x, total_channels):
+        """(block input as a view into a fresh [N,H,W,total_channels] buffer, handle the block's convs store into)."""
+        x = self._as_act(x)
+        N, C, H, W = x.shape
+        if C % 8 != 0 or total_channels % 8 != 0:
+            return x, None
+        buf = torch.empty((N, H, W, total_channels), dtype=torch.bfloat16, device=x.device)
+        return BlockInputFn.apply(x, buf), _DenseBuffer(buf, C)
+
     def concat_channels(self, tensors):
         tensors = [self._as_act(t) for t in tensors]
         if len(tensors) == 1:
             return tensors[0]
+        if _adjacent_channel_slices(tensors):
+            return ConcatViewFn.apply(*tensors)
+        self._fell_back("concat")
         return torch.cat(tensors, dim=1).contiguous(memory_format=torch.channels_last)
 
     def relpos_attention(self, q, k, v, rel_h, rel_w, height, width, scale):
