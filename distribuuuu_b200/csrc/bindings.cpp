@@ -234,7 +234,8 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   const int G = groups, cin_g = g.C / G, cout_g = g.K / G;
   TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8 (", cin_g, ", ", cout_g, ")");
   const int M = g.N * g.P * g.Q;
-  const TilePlan plan = plan_tiles(cout_g, g.R * g.S * ((cin_g + 63) / 64), (M + 127) / 128, G, num_sms());
+  TilePlan plan = plan_tiles(cout_g, g.R * g.S * ((cin_g + 63) / 64), (M + 127) / 128, G, num_sms());
+  if (bias.has_value()) plan.cg = 1;    // the bias epilogue (classifier) is only instantiated for single-CTA tiles
   const int bn = plan.bn;
   const bool pointwise = (g.R == 1 && g.S == 1 && stride == 1 && pad == 0);
   ConvGemmParams p{};

@@ -403,6 +403,9 @@ def check_se(N=10, H=7, W=7, C=96, r=4, act="silu"):
     w1r, w2r = w1.float().clone().requires_grad_(True), w2.float().clone().requires_grad_(True)
     b1r, b2r = b1.clone().requires_grad_(True), b2.clone().requires_grad_(True)
     sp = xr.mean((1, 2))
+    # the kernels feed the MLP the bf16-rounded pooled vector; use the same values (straight-through) so that ReLU
+    # units whose pre-activation is ~0 take the same side in both paths
+    sp = sp + (pooled.float() - sp).detach()
     hid = sp @ w1r.t() + b1r
     hid = F.silu(hid) if act == "silu" else F.relu(hid)
     g = torch.sigmoid(hid @ w2r.t() + b2r)
