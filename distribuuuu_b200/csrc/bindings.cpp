@@ -16,6 +16,7 @@
 #include "dwconv.h"
 #include "elementwise.h"
 #include "extras.h"
+#include "attention.h"
 
 namespace {
 
@@ -395,10 +396,14 @@ void conv_dgrad_s2(const at::Tensor& dy, const at::Tensor& w, at::Tensor& dx, in
 // dy [N,P,Q,K], x [N,H,W,C] -> dw fp32 [K,R,S,C] (accumulated with red.add; caller zeroes).
 void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64_t stride, int64_t pad, int64_t dil,
                 int64_t groups) {
-  check_bf16_contig(dy, "dy"); check_bf16_contig(x, "x");
+  check_bf16_contig(dy, "dy");
   TORCH_CHECK(dw.is_cuda() && dw.scalar_type() == at::kFloat && dw.is_contiguous(), "dw must be contiguous fp32");
   c10::cuda::CUDAGuard guard(dy.device());
   const int N = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
+  // x: NHWC bf16; a pointwise layer may read a channel slice of a wider buffer (uniform pixel pitch)
+  const int64_t x_pitch = x.stride(2);
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.stride(3) == 1 && x_pitch >= C && x_pitch % 8 == 0 &&
+              x.stride(1) == W * x_pitch && x.stride(0) == (int64_t)H * W * x_pitch, "x must be NHWC bf16 with a uniform pixel pitch");
   const int K = dw.size(0), R = dw.size(1), S = dw.size(2);
   const int P = dy.size(1), Q = dy.size(2);
   const int G = groups, cin_g = C / G, cout_g = K / G;
@@ -406,6 +411,7 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8");
   const long long pixels = (long long)N * P * Q;
   const bool pointwise = (R == 1 && S == 1 && stride == 1 && pad == 0);
+  TORCH_CHECK(pointwise || x_pitch == C, "only 1x1 weight gradients accept a channel-sliced input");
   // B operand = "virtual boxes": (tap, 64-channel slice of Cin).  One work item accumulates up to 4 of them
   // (N = 64..256 TMEM columns) against a single load of the dY^T tile, so dY is re-read taps*Cin/(64*vpi) times
   // instead of taps*Cin/64 times.
@@ -442,7 +448,7 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   p.out = dw.data_ptr(); p.ldo = (long long)p.taps * cin_g; p.tap_stride = cin_g;
   p.total_items = base_items * splits;
   CUtensorMap ma = tiled_map_3d(dy.data_ptr(), K, 1, pixels, K, K, 64, 1, 64);
-  CUtensorMap mb = pointwise ? tiled_map_3d(x.data_ptr(), C, 1, pixels, C, C, 64, 1, 64)
+  CUtensorMap mb = pointwise ? tiled_map_3d(x.data_ptr(), C, 1, pixels, x_pitch, x_pitch, 64, 1, 64)
                              : im2col_map_4d(x.data_ptr(), N, H, W, C, -pad, -pad, pad - (S - 1) * dil,
                                              pad - (R - 1) * dil, stride, 64, 64);
   const int grid = cg == 2 ? 2 * std::min(p.total_items, num_sms() / 2) : std::min(p.total_items, num_sms());
@@ -725,6 +731,68 @@ void channel_add_bcast(at::Tensor& dx, const at::Tensor& ds, double scale) {
   B200_CUDA_OK(b200_channel_add_bcast(dx.data_ptr(), ds.data_ptr<float>(), dx.size(0), dx.size(1) * dx.size(2), dx.size(3), (float)scale, cur_stream()));
 }
 
+// ---------------------------------------------------------------------------------------------- attention (BoTNet MHSA)
+// qk [B,14,14,2*heads*128], v / out [B,14,14,heads*128] (NHWC bf16, contiguous); rel_w / rel_h [27,128] bf16
+struct AttnMaps { CUtensorMap qk128, qk64, v128, v64, relw, relh; };
+AttnMaps attn_maps(const at::Tensor& qk, const at::Tensor& v, const at::Tensor& relw, const at::Tensor& relh, int heads) {
+  check_bf16_contig(qk, "qk"); check_bf16_contig(v, "v"); check_bf16_contig(relw, "rel_w"); check_bf16_contig(relh, "rel_h");
+  const int B = qk.size(0);
+  TORCH_CHECK(qk.dim() == 4 && qk.size(1) * qk.size(2) == 196 && qk.size(3) == 2 * heads * 128 && v.size(3) == heads * 128 && v.size(0) == B,
+              "fused MHSA handles 14x14 maps with 128-wide heads");
+  TORCH_CHECK(relw.size(0) == 27 && relw.size(1) == 128 && relh.size(0) == 27 && relh.size(1) == 128, "relative tables must be [27,128]");
+  const uint64_t C2 = 2 * heads * 128, Cv = heads * 128;
+  AttnMaps m;
+  m.qk128 = tiled_map_3d(qk.data_ptr(), C2, 196, B, C2, 196 * C2, 64, 128, 1);
+  m.qk64 = tiled_map_3d(qk.data_ptr(), C2, 196, B, C2, 196 * C2, 64, 64, 1);
+  m.v128 = tiled_map_3d(v.data_ptr(), Cv, 196, B, Cv, 196 * Cv, 64, 128, 1);
+  m.v64 = tiled_map_3d(v.data_ptr(), Cv, 196, B, Cv, 196 * Cv, 64, 64, 1);
+  m.relw = tiled_map_3d(relw.data_ptr(), 128, 27, 1, 128, 27 * 128, 64, 32, 1);
+  m.relh = tiled_map_3d(relh.data_ptr(), 128, 27, 1, 128, 27 * 128, 64, 32, 1);
+  return m;
+}
+void attn_fwd(const at::Tensor& qk, const at::Tensor& v, const at::Tensor& relw, const at::Tensor& relh, at::Tensor& out,
+              at::Tensor& p_save, int64_t heads, double scale) {
+  c10::cuda::CUDAGuard guard(qk.device());
+  AttnMaps m = attn_maps(qk, v, relw, relh, heads);
+  check_bf16_contig(out, "out"); check_bf16_contig(p_save, "p_save");
+  const int B = qk.size(0);
+  TORCH_CHECK(out.numel() == v.numel() && p_save.numel() == (int64_t)B * heads * 196 * 208, "attn_fwd output shapes");
+  const uint64_t Cv = heads * 128;
+  CUtensorMap out32 = tiled_map_3d(out.data_ptr(), Cv, 196, B, Cv, 196 * Cv, 64, 32, 1);
+  AttnParams p{};
+  p.B = B; p.heads = heads; p.scale = (float)scale; p.p_save = p_save.data_ptr();
+  B200_CUDA_OK(b200_attn_fwd(&m.qk128, &m.v64, &m.relw, &m.relh, &out32, &p, cur_stream()));
+}
+void attn_bwd(const at::Tensor& dout, const at::Tensor& qk, const at::Tensor& v, const at::Tensor& relw, const at::Tensor& relh,
+              const at::Tensor& p_save, at::Tensor& ds_save, at::Tensor& dsrel, at::Tensor& dqk, at::Tensor& dv, int64_t heads, double scale) {
+  c10::cuda::CUDAGuard guard(qk.device());
+  AttnMaps m = attn_maps(qk, v, relw, relh, heads);
+  check_bf16_contig(dout, "dout"); check_bf16_contig(p_save, "p_save"); check_bf16_contig(ds_save, "ds_save");
+  check_bf16_contig(dsrel, "dsrel"); check_bf16_contig(dqk, "dqk"); check_bf16_contig(dv, "dv");
+  const int B = qk.size(0);
+  const uint64_t C2 = 2 * heads * 128, Cv = heads * 128, BH = (uint64_t)B * heads;
+  TORCH_CHECK(dout.numel() == v.numel() && dqk.numel() == qk.numel() && dv.numel() == v.numel() &&
+              p_save.numel() == (int64_t)BH * 196 * 208 && ds_save.numel() == (int64_t)BH * 196 * 256 &&
+              dsrel.numel() == (int64_t)B * 196 * heads * 64, "attn_bwd shapes");
+  CUtensorMap dout128 = tiled_map_3d(dout.data_ptr(), Cv, 196, B, Cv, 196 * Cv, 64, 128, 1);
+  CUtensorMap dout64 = tiled_map_3d(dout.data_ptr(), Cv, 196, B, Cv, 196 * Cv, 64, 64, 1);
+  CUtensorMap dqk32 = tiled_map_3d(dqk.data_ptr(), C2, 196, B, C2, 196 * C2, 64, 32, 1);
+  CUtensorMap dv32 = tiled_map_3d(dv.data_ptr(), Cv, 196, B, Cv, 196 * Cv, 64, 32, 1);
+  CUtensorMap psave64 = tiled_map_3d(p_save.data_ptr(), 208, 196, BH, 208, 196 * 208, 64, 64, 1);
+  CUtensorMap dssave64 = tiled_map_3d(ds_save.data_ptr(), 256, 196, BH, 256, 196 * 256, 64, 64, 1);
+  AttnParams p{};
+  p.B = B; p.heads = heads; p.scale = (float)scale;
+  p.p_save = p_save.data_ptr(); p.ds_save = ds_save.data_ptr(); p.dsrel = dsrel.data_ptr();
+  B200_CUDA_OK(b200_attn_bwd_dq(&dout128, &m.v128, &m.qk64, &m.relw, &m.relh, &dqk32, &p, cur_stream()));
+  B200_CUDA_OK(b200_attn_bwd_dkv(&psave64, &dssave64, &dout64, &m.qk64, &dv32, &dqk32, &p, cur_stream()));
+}
+void rel_grad_reduce(const at::Tensor& dw, at::Tensor& grad_w, at::Tensor& grad_h, int64_t heads) {
+  c10::cuda::CUDAGuard guard(dw.device());
+  TORCH_CHECK(dw.scalar_type() == at::kFloat && dw.is_contiguous() && dw.numel() == heads * 64 * 128 && grad_w.numel() == 27 * 128 &&
+              grad_h.numel() == 27 * 128 && grad_w.scalar_type() == at::kFloat && grad_h.scalar_type() == at::kFloat, "rel_grad_reduce shapes");
+  B200_CUDA_OK(b200_rel_grad_reduce(dw.data_ptr<float>(), grad_w.data_ptr<float>(), grad_h.data_ptr<float>(), heads, cur_stream()));
+}
+
 // ---------------------------------------------------------------------------------------------- optimizer / comm
 SgdHyper hyper(double lr, double momentum, double dampening, double wd, bool nesterov, bool first) {
   SgdHyper h; h.lr = lr; h.momentum = momentum; h.dampening = dampening; h.weight_decay = wd; h.nesterov = nesterov; h.first_step = first;
@@ -797,6 +865,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
         py::arg("groups") = 1);
   m.def("conv_dgrad_s2", &conv_dgrad_s2, "stride-2 data gradient by parity classes (no zero insertion)", py::arg("dy"), py::arg("w"),
         py::arg("dx"), py::arg("pad"), py::arg("addend") = py::none(), py::arg("groups") = 1);
+  m.def("attn_fwd", &attn_fwd, "fused relative-position MHSA forward (tcgen05)");
+  m.def("attn_bwd", &attn_bwd, "fused relative-position MHSA backward: dQ, dK, dV and the relative-logit gradients");
+  m.def("rel_grad_reduce", &rel_grad_reduce);
   m.def("colsum_add", &colsum_add);
   m.def("strided_add_inplace", &strided_add_inplace);
   m.def("blockdiag_pack", &blockdiag_pack);

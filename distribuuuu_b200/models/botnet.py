@@ -10,8 +10,8 @@ assembly ``botnet50`` 275-290.  The module tree reproduces the reference's
 Differences by design: the relative-position logits are computed from index tables
 instead of the pad/reshape trick with hard-coded ``.cuda()`` (reference 33,36), so the
 model runs on any device; ``num_classes`` is honoured (the reference hard-codes 1000,
-botnet.py:288); attention runs as one fused kernel on the native path
-(``Fn.relpos_attention``).
+botnet.py:288); on the native path the attention core (QK^T + relative logits + softmax + PV, forward and backward)
+runs as fused tcgen05 kernels on the NHWC projections (``Fn.relpos_mhsa`` -> ``csrc/attention.cu``).
 """
 from __future__ import annotations
 
@@ -61,16 +61,15 @@ class MHSA(nn.Module):
         nh = self.heads
         qk = Fn.conv2d(x, self.to_qk)
         v = Fn.conv2d(x, self.to_v)
+        if self.rel:   # fused on the native path (one tcgen05 kernel on the NHWC projections)
+            return Fn.relpos_mhsa(qk, v, self.pos_emb.rel_height, self.pos_emb.rel_width, nh, self.dim_qk, self.dim_v, self.scale)
         q, k = qk[:, : nh * self.dim_qk], qk[:, nh * self.dim_qk:]
 
         def split(t, d):  # [B,(h d),H,W] -> [B,h,HW,d]
             return t.reshape(B, nh, d, H * W).transpose(2, 3)
 
         q, k, v = split(q, self.dim_qk), split(k, self.dim_qk), split(v, self.dim_v)
-        if self.rel:
-            out = Fn.relpos_attention(q, k, v, self.pos_emb.rel_height, self.pos_emb.rel_width, H, W, self.scale)
-        else:
-            out = Fn.abspos_attention(q, k, v, self.pos_emb.height, self.pos_emb.width, self.scale)
+        out = Fn.abspos_attention(q, k, v, self.pos_emb.height, self.pos_emb.width, self.scale)
         return out.transpose(2, 3).reshape(B, nh * self.dim_v, H, W)
 
 

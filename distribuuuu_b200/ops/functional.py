@@ -153,6 +153,28 @@ def relpos_attention(q, k, v, rel_h, rel_w, height: int, width: int, scale: floa
     return torch.matmul(torch.softmax(logits, dim=-1), v)
 
 
+def relpos_mhsa(qk, v, rel_h, rel_w, heads: int, dim_qk: int, dim_v: int, scale: float):
+    """BoTNet's MHSA core on the raw projections: ``qk`` [B, 2*heads*dim_qk, H, W] (q heads first, then k heads),
+    ``v`` [B, heads*dim_v, H, W] -> [B, heads*dim_v, H, W].  Same math as splitting into heads and calling
+    ``relpos_attention`` (reference botnet.py:193-215); the native engine runs it as ONE fused tcgen05 kernel on the
+    NHWC projections (no head split / transpose copies) when the map is 14x14 with 128-wide heads."""
+    eng = runtime.active_engine()
+    if eng is not None:
+        return eng.ops.relpos_mhsa(qk, v, rel_h, rel_w, heads, dim_qk, dim_v, scale)
+    return _relpos_mhsa_composite(qk, v, rel_h, rel_w, heads, dim_qk, dim_v, scale)
+
+
+def _relpos_mhsa_composite(qk, v, rel_h, rel_w, heads, dim_qk, dim_v, scale):
+    B, _, H, W = qk.shape
+    q, k = qk[:, : heads * dim_qk], qk[:, heads * dim_qk:]
+
+    def split(t, d):  # [B,(h d),H,W] -> [B,h,HW,d]
+        return t.reshape(B, heads, d, H * W).transpose(2, 3)
+
+    out = relpos_attention(split(q, dim_qk), split(k, dim_qk), split(v, dim_v), rel_h, rel_w, H, W, scale)
+    return out.transpose(2, 3).reshape(B, heads * dim_v, H, W)
+
+
 def abspos_attention(q, k, v, emb_h, emb_w, scale: float):
     """Attention with absolute position logits q.(emb_h[x]+emb_w[y]) (reference botnet.py:60-74)."""
     q = q * scale

@@ -608,6 +608,47 @@ class SeFn(torch.autograd.Function):
         return _nchw_view(dx), None, None, None, None, None
 
 
+class MhsaFn(torch.autograd.Function):
+    """BoTNet MHSA core (14x14 tokens, 128-wide heads) on the fused tcgen05 kernels of ``csrc/attention.cu``:
+    forward = QK^T + relative-position logits + softmax + PV in one kernel on the NHWC projections; backward = two
+    kernels (dQ with the softmax backward; dK / dV) plus the relative-table gradients as one grouped wgrad GEMM over all
+    samples and heads.  Softmax probabilities are kept in bf16 for the backward pass (83 MB per layer at batch 256)."""
+
+    @staticmethod
+    def forward(ctx, qk, v, eng, rel_h, rel_w, heads, scale, anchor):
+        K = eng.K
+        qkh, vh = _nhwc(qk), _nhwc(v)
+        B = qkh.shape[0]
+        out = torch.empty_like(vh)
+        p_save = torch.empty((B * heads, 196, 208), dtype=torch.bfloat16, device=qk.device)
+        K.attn_fwd(qkh, vh, eng.w16_view(rel_w), eng.w16_view(rel_h), out, p_save, heads, scale)
+        ctx.eng, ctx.rel, ctx.heads, ctx.scale = eng, (rel_h, rel_w), heads, scale
+        ctx.save_for_backward(qkh, vh, p_save)
+        return _nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng, heads = ctx.eng, ctx.heads
+        K = eng.K
+        rel_h, rel_w = ctx.rel
+        qkh, vh, p_save = ctx.saved_tensors
+        B = qkh.shape[0]
+        dev = qkh.device
+        douth = _nhwc(dout)
+        dqk, dv = torch.empty_like(qkh), torch.empty_like(vh)
+        ds_save = torch.empty((B * heads, 196, 256), dtype=torch.bfloat16, device=dev)
+        dsrel = torch.empty((B, qkh.shape[1], qkh.shape[2], heads * 64), dtype=torch.bfloat16, device=dev)
+        K.attn_bwd(douth, qkh, vh, eng.w16_view(rel_w), eng.w16_view(rel_h), p_save, ds_save, dsrel, dqk, dv, heads, ctx.scale)
+        # d(rel tables)[m, :] = sum over samples, heads, queries of dS_rel[., m] * q[., :]: a grouped (per head) 1x1 wgrad
+        dw = eng.scratch("mhsa_rel_dw", (heads * 64, 1, 1, 128), torch.float32)
+        dw.zero_()
+        K.conv_wgrad(dsrel, qkh[..., : heads * 128], dw, 1, 0, 1, heads)
+        K.rel_grad_reduce(dw, eng.grad_flat_view(rel_w), eng.grad_flat_view(rel_h), heads)
+        eng.mark_ready(rel_w)
+        eng.mark_ready(rel_h)
+        return _nchw_view(dqk), _nchw_view(dv), None, None, None, None, None, None
+
+
 class CeTopkFn(torch.autograd.Function):
     """softmax-CE + top-1/top-k counts + dlogits in one kernel (reference trainer.py:43,50 + utils.py:265-277)."""
 
@@ -809,7 +850,19 @@ class NativeOps:
         self._fell_back("concat")
         return torch.cat(tensors, dim=1).contiguous(memory_format=torch.channels_last)
 
+    def relpos_mhsa(self, qk, v, rel_h, rel_w, heads, dim_qk, dim_v, scale):
+        B, _, H, W = qk.shape
+        if (qk.dtype == torch.bfloat16 and v.dtype == torch.bfloat16 and H * W == 196 and H == 14 and dim_qk == 128
+                and dim_v == 128 and tuple(rel_h.shape) == (27, 128) and tuple(rel_w.shape) == (27, 128)):
+            return MhsaFn.apply(qk, v, self.eng, rel_h, rel_w, heads, float(scale), self.eng.anchor)
+        self._fell_back("mhsa")
+        from . import functional as Fn
+        from . import runtime
+        with runtime.native_scope(None):  # other map sizes / head widths: composite torch ops on the bf16 tensors
+            return Fn._relpos_mhsa_composite(qk, v, self.eng.w16_leaf(rel_h), self.eng.w16_leaf(rel_w), heads, dim_qk, dim_v, scale)
+
     def relpos_attention(self, q, k, v, rel_h, rel_w, height, width, scale):
+        self._fell_back("relpos_attention")
         from . import functional as Fn
         from . import runtime
         with runtime.native_scope(None):  # composite torch ops on bf16; positional tables via leaf views

@@ -417,6 +417,43 @@ def check_se(N=10, H=7, W=7, C=96, r=4, act="silu"):
     return errs
 
 
+def check_mhsa(B=3, heads=4, scale=128 ** -0.5):
+    """Fused relative-position MHSA (csrc/attention.cu) forward + backward (dQ, dK, dV, d rel tables) against the fp32
+    composite of ops.functional (reference botnet.py:193-215)."""
+    Kmod = _K()
+    from .ops import functional as Fn
+    d = 128
+    qk = _bf16(B, 14, 14, 2 * heads * d, seed=91)
+    v = _bf16(B, 14, 14, heads * d, seed=92)
+    relw = _bf16(27, d, scale=d ** -0.5, seed=93)
+    relh = _bf16(27, d, scale=d ** -0.5, seed=94)
+    dout = _bf16(B, 14, 14, heads * d, seed=95)
+    out = torch.full_like(v, float("nan"))
+    p_save = torch.empty((B * heads, 196, 208), dtype=torch.bfloat16, device="cuda")
+    Kmod.attn_fwd(qk, v, relw, relh, out, p_save, heads, scale)
+    dqk, dv = torch.full_like(qk, float("nan")), torch.full_like(v, float("nan"))
+    ds_save = torch.empty((B * heads, 196, 256), dtype=torch.bfloat16, device="cuda")
+    dsrel = torch.empty((B, 14, 14, heads * 64), dtype=torch.bfloat16, device="cuda")
+    Kmod.attn_bwd(dout, qk, v, relw, relh, p_save, ds_save, dsrel, dqk, dv, heads, scale)
+    dw = torch.zeros((heads * 64, 1, 1, d), device="cuda")
+    Kmod.conv_wgrad(dsrel, qk[..., : heads * d], dw, 1, 0, 1, heads)
+    gw, gh = torch.zeros(27, d, device="cuda"), torch.zeros(27, d, device="cuda")
+    Kmod.rel_grad_reduce(dw, gw, gh, heads)
+    torch.cuda.synchronize()
+    qkr = qk.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    vr = v.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    rwr, rhr = relw.float().clone().requires_grad_(True), relh.float().clone().requires_grad_(True)
+    o = Fn._relpos_mhsa_composite(qkr, vr, rhr, rwr, heads, d, d, scale)
+    o.backward(dout.float().permute(0, 3, 1, 2))
+    nh = lambda t: t.permute(0, 2, 3, 1)
+    errs = {"out": _rel_err(out, nh(o)), "dq": _rel_err(dqk[..., : heads * d], nh(qkr.grad)[..., : heads * d]),
+            "dk": _rel_err(dqk[..., heads * d:], nh(qkr.grad)[..., heads * d:]), "dv": _rel_err(dv, nh(vr.grad)),
+            "drel_w": _rel_err(gw, rwr.grad), "drel_h": _rel_err(gh, rhr.grad),
+            "p_rowsum": float((p_save.float().sum(-1) - 1).abs().max())}
+    assert all(v_ < 3e-2 for v_ in errs.values()), errs
+    return errs
+
+
 def check_colsum(rows=1000, C=1000 // 8 * 8):
     Kmod = _K()
     d = _bf16(rows, C, seed=81)

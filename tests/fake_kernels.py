@@ -120,6 +120,64 @@ class FakeKernels:
             g = g + addend.float().reshape(g.shape)
         _raw(dx).copy_(g.to(BF16).reshape(dx.shape))
 
+    def attn_fwd(self, qk, v, relw, relh, out, p_save, heads, scale):
+        self._count("attn_fwd")
+        B = qk.shape[0]
+        d = 128
+        x = qk.float().reshape(B, 196, 2 * heads, d)
+        q, k = x[:, :, :heads].permute(0, 2, 1, 3), x[:, :, heads:].permute(0, 2, 1, 3)      # [B,h,196,d]
+        vv = v.float().reshape(B, 196, heads, d).permute(0, 2, 1, 3)
+        idx = torch.arange(14)
+        tw = relw.float()[(idx[None, :] - idx[:, None]) + 13]      # [xi, xj, d]
+        th = relh.float()[(idx[None, :] - idx[:, None]) + 13]      # [yi, yj, d]
+        q5 = q.reshape(B, heads, 14, 14, d)
+        lw = torch.einsum("bnyxd,xjd->bnyxj", q5, tw)
+        lh = torch.einsum("bnyxd,yid->bnyxi", q5, th)
+        pos = (lh[..., :, None] + lw[..., None, :]).reshape(B, heads, 196, 196)
+        logits = scale * (q @ k.transpose(-1, -2) + pos)
+        pr = torch.softmax(logits, dim=-1).to(BF16)
+        ps = _raw(p_save).view(B, heads, 196, 208)
+        ps.zero_()
+        ps[..., :196] = pr
+        o = (pr.float() @ vv).permute(0, 2, 1, 3).reshape(out.shape)
+        _raw(out).copy_(o.to(BF16))
+
+    def attn_bwd(self, dout, qk, v, relw, relh, p_save, ds_save, dsrel, dqk, dv, heads, scale):
+        self._count("attn_bwd")
+        B = qk.shape[0]
+        d = 128
+        x = qk.float().reshape(B, 196, 2 * heads, d)
+        q, k = x[:, :, :heads].permute(0, 2, 1, 3), x[:, :, heads:].permute(0, 2, 1, 3)
+        vv = v.float().reshape(B, 196, heads, d).permute(0, 2, 1, 3)
+        do = dout.float().reshape(B, 196, heads, d).permute(0, 2, 1, 3)
+        pr = p_save.float().view(B, heads, 196, 208)[..., :196]
+        dp = do @ vv.transpose(-1, -2)
+        ds = (scale * pr * (dp - (pr * dp).sum(-1, keepdim=True))).to(BF16).float()
+        dvv = pr.transpose(-1, -2) @ do
+        ds5 = ds.reshape(B, heads, 14, 14, 14, 14)                 # [b,h,yi,xi,yj,xj]
+        gw = ds5.sum(4)                                            # [b,h,yi,xi,xj]
+        gh = ds5.sum(5)                                            # [b,h,yi,xi,yj]
+        rel = torch.zeros(B, heads, 14, 14, 64)
+        idx = torch.arange(14)
+        for xi in range(14):
+            rel[:, :, :, xi, idx - xi + 13] = gw[:, :, :, xi, :]
+        for yi in range(14):
+            rel[:, :, yi, :, 32 + idx - yi + 13] = gh[:, :, yi, :, :]
+        rel = rel.to(BF16)
+        _raw(dsrel).copy_(rel.permute(0, 2, 3, 1, 4).reshape(dsrel.shape))
+        relf = rel.float().reshape(B, heads, 196, 64)
+        dq = ds @ k + relf[..., :27] @ relw.float() + relf[..., 32:59] @ relh.float()
+        dk = ds.transpose(-1, -2) @ q
+        dx = torch.cat([dq.permute(0, 2, 1, 3), dk.permute(0, 2, 1, 3)], dim=2).reshape(dqk.shape)
+        _raw(dqk).copy_(dx.to(BF16))
+        _raw(dv).copy_(dvv.permute(0, 2, 1, 3).reshape(dv.shape).to(BF16))
+
+    def rel_grad_reduce(self, dw, grad_w, grad_h, heads):
+        self._count("rel_grad_reduce")
+        t = dw.float().reshape(heads, 64, 128).sum(0)
+        _raw(grad_w).view(27, 128).add_(t[:27])
+        _raw(grad_h).view(27, 128).add_(t[32:59])
+
     def strided_add_inplace(self, dx, compact, stride):
         self._count("strided_add_inplace")
         P, Q = compact.shape[1], compact.shape[2]

@@ -151,3 +151,26 @@ def test_no_library_fallbacks_for_zoo_models(arch):
     loss, _, _ = eng.train_step(x, y, opt, 5)
     assert torch.isfinite(loss).item()
     assert eng.ops.fallbacks == {}, eng.ops.fallbacks
+
+
+@pytest.mark.parametrize("B", [1, 3])
+def test_fused_relpos_mhsa(B):
+    from distribuuuu_b200 import selftest
+    selftest.check_mhsa(B=B)
+
+
+def test_botnet50_step_has_no_library_fallbacks():
+    import torch
+    from distribuuuu_b200 import models
+    from distribuuuu_b200.parallel.native_engine import NativeEngine
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    net = models.build_model("botnet50", num_classes=16).to(dev)
+    eng = NativeEngine(net, dev)
+    opt = eng.make_optimizer(lr=0.01, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    eng.train()
+    x = torch.randn(2, 3, 224, 224, device=dev)
+    y = torch.randint(0, 16, (2,), device=dev)
+    loss, _, _ = eng.train_step(x, y, opt, 5)
+    assert torch.isfinite(loss).item()
+    assert eng.ops.fallbacks == {}, eng.ops.fallbacks

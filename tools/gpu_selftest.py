@@ -47,6 +47,8 @@ def registry():
         "se_relu_r308": lambda: st.check_se(N=9, H=4, W=4, C=1232, r=308, act="relu"),
         "se_silu_r20": lambda: st.check_se(N=33, H=7, W=7, C=480, r=20),
         "colsum": st.check_colsum,
+        "mhsa": st.check_mhsa,
+        "mhsa_b1": lambda: st.check_mhsa(B=1),
         "depthwise_5x5_s2": lambda: st.check_depthwise(k=5, stride=2),
         "depthwise_3x3_s1": lambda: st.check_depthwise(k=3, stride=1, C=32, H=16, W=16),
         "engine_resnet18": lambda: st.check_engine_vs_torch("resnet18", batch=16, size=64),
