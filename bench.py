@@ -29,7 +29,8 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=256, help="per-GPU batch (BASELINE config: 256)")
+    ap.add_argument("--batch", type=int, default=0, help="per-GPU batch; 0 = 256 for resnet50 (BASELINE config), else the arch's "
+                    "config/<arch>.yaml TRAIN.BATCH_SIZE")
     ap.add_argument("--arch", default="resnet50")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--ref-variant", default="stock", choices=["stock", "amp"],
@@ -133,6 +134,26 @@ def _timed(dev, fn, steps):
 
 BASELINE_PUBLISHED = None  # the reference publishes accuracy only -> vs_baseline is null
 
+_PRETTY = {"resnet50": "ResNet-50", "regnety_160": "RegNetY-160", "regnetx_160": "RegNetX-160", "regnety_320": "RegNetY-320",
+           "efficientnet_b0": "EfficientNet-B0", "botnet50": "BoTNet-50", "resnet18": "ResNet-18"}
+
+
+def _metric_name(arch):
+    return f"{_PRETTY.get(arch, arch)} training images/sec (whole job, device-timed, max over ranks)"
+
+
+def _resolve_batch(args):
+    if args.batch > 0:
+        return args.batch
+    if args.arch == "resnet50":
+        return 256
+    path = os.path.join(ROOT, "config", f"{args.arch}.yaml")
+    try:
+        import yaml
+        return int(yaml.safe_load(open(path))["TRAIN"]["BATCH_SIZE"])
+    except Exception:
+        return 64
+
 
 # --------------------------------------------------------------------------------------------- our arm
 class _LaunchCounter:
@@ -169,7 +190,7 @@ def run_ours(args):
     eng.K = counter
     opt = eng.make_optimizer(lr=0.2, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
     eng.train()
-    B = args.batch
+    B = args.batch = _resolve_batch(args)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     # a few distinct device-resident batches; each is 154 MB fp32 (> 126 MB L2), so inputs never sit in L2
     nbuf = 2
@@ -268,7 +289,7 @@ def run_ours(args):
         else:
             e2e = measure_e2e(args.e2e_input)
     if rank == 0:
-        out = {"metric": "ResNet-50 training images/sec (whole job, device-timed, max over ranks)", "impl": "ours",
+        out = {"metric": _metric_name(args.arch), "impl": "ours",
                "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": sec * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": BASELINE_PUBLISHED, "dtype": "bf16", "data": "synthetic (random-init weights)",
@@ -276,7 +297,8 @@ def run_ours(args):
                           "parallelism": f"dp{world}", "syncbn": bool(sync_bn and world > 1), "comm": eng.comm_mode,
                           "optimizer": "nesterov-sgd fused into the gradient all-reduce",
                           "l2": "inputs larger than L2 (154 MB fp32 per batch, alternating buffers)"},
-               "clocks": clocks, "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1)}
+               "clocks": clocks, "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1),
+               "library_fallbacks": dict(eng.ops.fallbacks)}
         if e2e is not None:
             out["e2e"] = e2e
         if e2e_alt is not None:
@@ -345,6 +367,7 @@ def run_reference(args):
     except Exception as exc:
         _emit({"impl": "reference", "unavailable": f"import failed: {type(exc).__name__}: {exc}"})
         return
+    args.batch = _resolve_batch(args)
     rcfg.MODEL.ARCH, rcfg.MODEL.SYNCBN, rcfg.MODEL.DUMMY_INPUT = args.arch, not args.no_syncbn, True
     rcfg.TRAIN.BATCH_SIZE, rcfg.TRAIN.PRINT_FREQ = args.batch, 10 ** 9
     rcfg.OUT_DIR = "/tmp/ref_bench_out"
@@ -383,7 +406,17 @@ def run_reference(args):
         torch.cuda.empty_cache()
         return sec_, clk
 
-    sec, clocks = run_variant(args.ref_variant)
+    try:
+        sec, clocks = run_variant(args.ref_variant)
+    except Exception as exc:
+        # e.g. regnety_160 / efficientnet_b0: the reference takes them from timm (trainer.py:124-128), which cannot be
+        # installed offline -- the arm is unavailable for those configs, say so instead of substituting another model
+        if rank == 0:
+            _emit({"impl": "reference", "metric": _metric_name(args.arch), "n_gpus": world,
+                   "unavailable": f"reference cannot build/run '{args.arch}' here: {type(exc).__name__}: {str(exc)[:200]}"})
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     value = world * B * args.steps / sec
     amp = None
     if args.ref_variant == "stock":
@@ -396,7 +429,7 @@ def run_reference(args):
         except Exception as exc:  # never let the context arm break the stock number
             amp = {"unavailable": f"{type(exc).__name__}: {exc}"}
     if rank == 0:
-        out = {"metric": "ResNet-50 training images/sec (whole job, device-timed, max over ranks)", "impl": "reference",
+        out = {"metric": _metric_name(args.arch), "impl": "reference",
                "variant": args.ref_variant, "value": value, "unit": "images/sec", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": sec * 1e3 / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "fp32 (tf32 convs; reference as written)" if args.ref_variant == "stock" else "bf16 autocast",
