@@ -1,6 +1,7 @@
 #!/usr/bin/env python
 """CPU: per-kernel SASS instruction-class counts of the built extension (`cuobjdump -sass`), the evidence that the
-hot kernels really use tcgen05 / TMEM / TMA / multimem / cp.async.  Writes profiles/sass_summary.txt."""
+hot kernels really use tcgen05 / TMEM / TMA / multimem / cp.async.  Writes profiles/sass_summary.txt and, for the
+named hot kernels (FULL below), the complete SASS listing to profiles/sass/<kernel>.sass."""
 import collections
 import os
 import re
@@ -13,15 +14,26 @@ INTERESTING = re.compile(r"^(UTCHMMA|UTCQMMA|UTCBAR|UTCATOMSWS|LDTM|STTM|UTMALDG
                          r"REDG|RED\.|ATOMG|ATOMS|LDGMC|STGMC|REDGMC|MULTIMEM|LD\.E.*\.SYS|ST\.E.*\.SYS|ELECT|BAR\.|DEPBAR)")
 
 
+# kernels whose complete listing is committed (one instantiation per role)
+FULL = [r"conv_gemm_kernel<256, 0, 2>", r"conv_gemm_kernel<256, 0, 1>", r"conv_gemm_kernel<256, 1, 2>", r"conv_gemm_kernel<64, 0, 1>",
+        r"conv_gemm_kernel<256, 3, 2>", r"allreduce_sgd_kernel", r"bn_apply_kernel<1, true>", r"bn_bwd_apply_kernel<1, 1>",
+        r"bn_bwd_reduce_kernel<1, 1>", r"attn_fwd_kernel", r"attn_bwd_dq_kernel", r"attn_bwd_dkv_kernel", r"dw_fprop", r"ce_topk_kernel",
+        r"se_gate_fwd_kernel", r"stem_im2col_kernel<unsigned char>"]
+
+
 def main():
     out = subprocess.run(["cuobjdump", "-sass", SO], capture_output=True, text=True).stdout
     kernels, name = collections.OrderedDict(), None
+    raw = collections.OrderedDict()
     for line in out.splitlines():
         m = re.match(r"\s*Function : (\S+)", line)
         if m:
             name = m.group(1)
             kernels[name] = []
+            raw[name] = []
             continue
+        if name:
+            raw[name].append(line)
         m = re.match(r"\s+/\*[0-9a-f]{4,5}\*/\s+(.*?);", line)
         if m and name:
             ins = re.sub(r"^@!?U?P\d\s+", "", m.group(1).strip())
@@ -38,6 +50,20 @@ def main():
         short = re.sub(r"\(.*", "", pretty).replace("void ", "")
         lines.append(f"## {short}  ({len(ins)} instructions)")
         lines.append("   " + (", ".join(f"{k} x{v}" for k, v in sorted(c.items())) or "(no tensor / TMA / async / atomic instructions)"))
+    sass_dir = os.path.join(ROOT, "profiles", "sass")
+    os.makedirs(sass_dir, exist_ok=True)
+    written = 0
+    for (mangled, _), pretty in zip(kernels.items(), demangle):
+        short = re.sub(r"\(.*", "", pretty).replace("void ", "")
+        if any(pat in short for pat in FULL):
+            fn = re.sub(r"[^A-Za-z0-9_]+", "_", short.replace("b200::", "")).strip("_") + ".sass"
+            body = [l for l in raw[mangled] if re.match(r"\s+/\*[0-9a-f]{4,5}\*/", l)]   # instruction lines, encodings stripped
+            body = [re.sub(r"\s*/\* 0x[0-9a-f]+ \*/\s*$", "", l) for l in body]
+            with open(os.path.join(sass_dir, fn), "w") as f:
+                f.write(f"// {pretty}\n// cuobjdump -sass of distribuuuu_b200/_ext/b200_kernels.so (sm_100a), {len(body)} instructions\n")
+                f.write("\n".join(body) + "\n")
+            written += 1
+    print(f"{written} full listings -> {sass_dir}")
     dst = os.path.join(ROOT, "profiles", "sass_summary.txt")
     open(dst, "w").write("\n".join(lines) + "\n")
     print(f"{len([k for k in kernels if 'b200' in k])} kernels -> {dst}")
