@@ -44,7 +44,8 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--iters", type=int, default=7)
     ap.add_argument("--shapes", type=int, nargs="*", help="indices into SHAPES (default: all)")
-    ap.add_argument("--no-cudnn", action="store_true")
+    ap.add_argument("--no-cudnn", action="store_true", help="fprop of our kernel only")
+    ap.add_argument("--ours-only", action="store_true", help="all three directions of our kernels, no cuDNN timing (A/B runs)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "conv_shapes.json"))
     a = ap.parse_args()
     from distribuuuu_b200.ops import build
@@ -76,20 +77,25 @@ def main():
         if a.no_cudnn:
             rows.append(r)
             continue
-        r["fprop_cudnn_ms"] = timeit(lambda: F.conv2d(xc, wc, None, s, pad), a.iters, flush)
         r["wgrad_ours_ms"] = timeit(lambda: K.conv_wgrad(dy, x, dw, s, pad, 1), a.iters, flush)
-        r["wgrad_cudnn_ms"] = timeit(lambda: torch.ops.aten.convolution_backward(
-            dyc, xc, wc, None, [s, s], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False]), a.iters, flush)
         if s == 1:
             r["dgrad_ours_ms"] = timeit(lambda: K.conv_dgrad(dy, w, dx, 1, pad, 1), a.iters, flush)
-        r["dgrad_cudnn_ms"] = timeit(lambda: torch.ops.aten.convolution_backward(
-            dyc, xc, wc, None, [s, s], [pad, pad], [1, 1], False, [0, 0], 1, [True, False, False]), a.iters, flush)
+        else:   # stride 2: parity-class dgrad (compact stride-1 dgrads + one interleave pass)
+            r["dgrad_ours_ms"] = timeit(lambda: K.conv_dgrad_s2(dy, w, dx, pad), a.iters, flush)
+        if not a.ours_only:
+            r["fprop_cudnn_ms"] = timeit(lambda: F.conv2d(xc, wc, None, s, pad), a.iters, flush)
+            r["wgrad_cudnn_ms"] = timeit(lambda: torch.ops.aten.convolution_backward(
+                dyc, xc, wc, None, [s, s], [pad, pad], [1, 1], False, [0, 0], 1, [False, True, False]), a.iters, flush)
+            r["dgrad_cudnn_ms"] = timeit(lambda: torch.ops.aten.convolution_backward(
+                dyc, xc, wc, None, [s, s], [pad, pad], [1, 1], False, [0, 0], 1, [True, False, False]), a.iters, flush)
         for kind in ("fprop", "dgrad", "wgrad"):
-            if f"{kind}_ours_ms" in r:
-                r[f"{kind}_ours_tflops"] = flops / r[f"{kind}_ours_ms"] / 1e9
+            r[f"{kind}_ours_tflops"] = flops / r[f"{kind}_ours_ms"] / 1e9
+            tot["ours"] += cnt * r[f"{kind}_ours_ms"]
+            tot[kind + "_ours"] = tot.get(kind + "_ours", 0.0) + cnt * r[f"{kind}_ours_ms"]
+            if not a.ours_only:
                 r[f"{kind}_cudnn_tflops"] = flops / r[f"{kind}_cudnn_ms"] / 1e9
-                tot["ours"] += cnt * r[f"{kind}_ours_ms"]
                 tot["cudnn"] += cnt * r[f"{kind}_cudnn_ms"]
+                tot[kind + "_cudnn"] = tot.get(kind + "_cudnn", 0.0) + cnt * r[f"{kind}_cudnn_ms"]
         bytes_min = 2.0 * (x.numel() + y.numel())
         r["fprop_ours_gbs_min"] = bytes_min / r["fprop_ours_ms"] / 1e6
         rows.append(r)
