@@ -124,8 +124,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     if (EPI != EPI_F32_RED) tma_prefetch_desc(&map_out);
     for (int i = 0; i < C::kMaxStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
     mbar_init(smem_u32(bres_bar), 1);
-    // tmem_empty of the leader collects the epilogue threads of BOTH CTAs (the peer's arrive remotely)
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiThreads * CG); }
+    // tmem_empty of the leader collects one arrival per epilogue WARP of BOTH CTAs (the peer's arrive remotely; 256
+    // per-thread remote arrivals per tile cost ~4k cycles on the short-K layers, measured on 256->1024 @14^2)
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiWarps * CG); }
     for (int i = 0; i < kEpiWarps; ++i) mbar_init(smem_u32(&add_bar[i]), 1);
     fence_barrier_init();
   }
@@ -467,7 +468,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         tc_fence_before();
-        if (CG == 2) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & kPeerBitMask); else mbar_arrive(smem_u32(&tmem_empty[acc]));
+        __syncwarp();                      // every lane has drained its TMEM loads of this accumulator stage
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & kPeerBitMask); else mbar_arrive(smem_u32(&tmem_empty[acc]));
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
       if (want_stats) flush_stats(st_nb);
@@ -511,7 +515,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
           }
         }
         tc_fence_before();
-        if (CG == 2) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & kPeerBitMask); else mbar_arrive(smem_u32(&tmem_empty[acc]));
+        __syncwarp();                      // every lane has drained its TMEM loads of this accumulator stage
+        if (lane == 0) {
+          if (CG == 2) mbar_arrive_cluster(smem_u32(&tmem_empty[acc]) & kPeerBitMask); else mbar_arrive(smem_u32(&tmem_empty[acc]));
+        }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
