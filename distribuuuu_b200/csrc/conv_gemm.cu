@@ -61,10 +61,23 @@ struct WorkItem { int m0, n0, nb, tap, it_begin, it_end, vb0, nbox, g; };
 static __device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int item, int bn, int m_span, int m_off) {
   WorkItem w;
   if (p.kind != KIND_WGRAD) {
-    int nb = item % p.n_blocks;
-    int rest = item / p.n_blocks;
-    int mb = rest % p.m_blocks;
-    w.g = rest / p.m_blocks;                       // conv group (0 when groups == 1)
+    int nb, mb;
+    if (p.b_resident) {
+      // n fastest: the grid is a multiple of n_blocks, so a CTA keeps ONE n-block (its resident weight slab) for life
+      nb = item % p.n_blocks;
+      const int rest = item / p.n_blocks;
+      mb = rest % p.m_blocks;
+      w.g = rest / p.m_blocks;                     // conv group (0 when groups == 1)
+    } else {
+      // m fastest: a CTA's consecutive items share the n-block, so (a) the BN statistics it keeps in registers are
+      // flushed (atomics on 2 x BN hot addresses) a handful of times per launch instead of after every item -- with n
+      // fastest and 74 pairs (or N = 2048: 8 n-blocks on 148 CTAs) every item switched n-block, which cost 50 % on
+      // 256->1024 @14^2 -- and (b) all CTAs read the same weight tile from L2 at the same time
+      mb = item % p.m_blocks;
+      const int rest = item / p.m_blocks;
+      nb = rest % p.n_blocks;
+      w.g = rest / p.n_blocks;
+    }
     w.m0 = mb * m_span + m_off; w.n0 = nb * bn; w.nb = w.g * p.n_blocks + nb; w.tap = 0; w.vb0 = 0; w.nbox = 0;
     w.it_begin = 0; w.it_end = p.taps * p.kb_per_tap;
   } else {
