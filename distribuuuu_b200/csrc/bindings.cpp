@@ -220,8 +220,10 @@ ConvGeom geom(const at::Tensor& x, const at::Tensor& w, int stride, int pad, int
 
 // ---------------------------------------------------------------------------------------------- conv fprop
 // x [N,H,W,C], w [K,R,S,C], out [N,P,Q,K] (all bf16, contiguous).  stats: fp32 [2*K] accumulated, bias fp32 [K].
+struct PeerState;
+PeerCtx peer_ctx_for_producer(PeerState* peer);
 void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const c10::optional<at::Tensor>& stats,
-                const c10::optional<at::Tensor>& bias, int64_t stride, int64_t pad, int64_t dil, int64_t groups) {
+                const c10::optional<at::Tensor>& bias, int64_t stride, int64_t pad, int64_t dil, int64_t groups, PeerState* peer) {
   check_bf16_contig(x, "x"); check_bf16_contig(w, "w");
   c10::cuda::CUDAGuard guard(x.device());
   const ConvGeom g = geom(x, w, stride, pad, dil, groups);
@@ -261,6 +263,8 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   if (stats.has_value()) TORCH_CHECK(stats->numel() >= 2 * g.K && stats->scalar_type() == at::kFloat, "stats must be fp32 [2*K]");
   p.vb_per_item = 0; p.cin_boxes = 1; p.vboxes_total = 0;
   p.total_items = p.m_blocks * p.n_blocks * G;
+  p.peer = PeerCtx{}; p.peer.world = 1;
+  if (peer != nullptr) { TORCH_CHECK(stats.has_value(), "conv_fprop: a peer context needs the statistics epilogue"); p.peer = peer_ctx_for_producer(peer); }
   CUtensorMap ma = pointwise
                        ? tiled_map_3d(x.data_ptr(), g.C, 1, M, g.C, g.C, 64, 1, 128)
                        : im2col_map_4d(x.data_ptr(), g.N, g.H, g.W, g.C, -pad, -pad, pad - (g.S - 1) * dil,
@@ -498,7 +502,9 @@ struct PeerState {
   std::vector<int64_t> signal_pads, sym_bufs;
   int64_t ticket = 0, mc_stats = 0, reduced = 0, ready = 0, wait_ns = 0;
   uint32_t epoch = 0;
-  PeerCtx make() {
+  // make(): context of the NEXT exchange (epoch + 1); current(): the exchange a producer kernel already announced
+  PeerCtx current() { return make(false); }
+  PeerCtx make(bool advance = true) {
     PeerCtx c{};
     c.world = world; c.rank = rank; c.slot_base = slot_base;
     if (world > 1) {
@@ -507,9 +513,10 @@ struct PeerState {
         c.signal_pads[i] = reinterpret_cast<uint32_t*>(signal_pads[i]);
         c.sym_bufs[i] = reinterpret_cast<float*>(sym_bufs[i]);
       }
-      c.epoch = ++epoch;
+      c.epoch = advance ? ++epoch : epoch;
     }
     c.ticket = reinterpret_cast<int*>(ticket);
+    c.presignaled = 0;
     c.mc_stats = reinterpret_cast<float*>(mc_stats);
     c.reduced = reinterpret_cast<float*>(reduced);
     c.ready = reinterpret_cast<uint32_t*>(ready);
@@ -520,12 +527,14 @@ struct PeerState {
 };
 
 
+PeerCtx peer_ctx_for_producer(PeerState* peer) { return peer->make(); }
+
 // y/out/residual are [rows, C] views (last dim contiguous, arbitrary row pitch).
 void bn_apply(const at::Tensor& y, const c10::optional<at::Tensor>& residual, at::Tensor& out, const at::Tensor& stats,
               int64_t sym_offset, const c10::optional<at::Tensor>& gamma, const c10::optional<at::Tensor>& beta,
               c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var, at::Tensor& save_mean,
               at::Tensor& save_invstd, double count, double eps, double momentum, int64_t act, bool training,
-              PeerState* peer, c10::optional<at::Tensor> relu_mask) {
+              PeerState* peer, c10::optional<at::Tensor> relu_mask, bool presignaled) {
   c10::cuda::CUDAGuard guard(y.device());
   TORCH_CHECK(y.dim() == 2 && y.stride(1) == 1 && out.stride(1) == 1 && y.size(1) % 8 == 0, "bn_apply expects [rows, C] with C % 8 == 0");
   BnApplyParams p{};
@@ -543,7 +552,9 @@ void bn_apply(const at::Tensor& y, const c10::optional<at::Tensor>& residual, at
     TORCH_CHECK(relu_mask->scalar_type() == at::kByte && relu_mask->is_contiguous() && relu_mask->numel() == y.size(0) * (y.size(1) / 8) && act == ACT_RELU, "relu_mask: uint8 [rows, C/8], relu only");
     p.relu_mask = relu_mask->data_ptr<uint8_t>();
   }
-  if (peer && training) p.peer = peer->make(); else { p.peer = PeerCtx{}; p.peer.world = 1; }
+  // presignaled: the conv that produced `stats` already raised this exchange's flag at its tail (conv_fprop(peer=...))
+  if (peer && training) { p.peer = presignaled ? peer->current() : peer->make(); p.peer.presignaled = presignaled ? 1 : 0; }
+  else { p.peer = PeerCtx{}; p.peer.world = 1; }
   B200_CUDA_OK(b200_bn_apply(&p, cur_stream()));
 }
 
@@ -575,10 +586,18 @@ void bn_backward(const at::Tensor& y, const at::Tensor& dout, const c10::optiona
   p.dgamma = fptr_mut(dgamma); p.dbeta = fptr_mut(dbeta);
   p.count = (float)count; p.act = act;
   p.relu_mask = relu_mask.has_value() ? relu_mask->data_ptr<uint8_t>() : nullptr;
+  // SyncBN: the reduce pass announces the exchange at its tail (last CTA out), the apply pass only waits for the peers.
+  // A phase-2-only call continues the exchange its phase-1 call opened (the engine launches a weight-gradient GEMM
+  // in between, which hides the NVLink round trip and the inter-rank skew).
   p.peer = PeerCtx{}; p.peer.world = 1;
-  if (phase & 1) B200_CUDA_OK(b200_bn_bwd_reduce(&p, cur_stream()));
-  if (peer) p.peer = peer->make();
-  if (phase & 2) B200_CUDA_OK(b200_bn_bwd_apply(&p, cur_stream()));
+  if (phase & 1) {
+    if (peer) p.peer = peer->make();
+    B200_CUDA_OK(b200_bn_bwd_reduce(&p, cur_stream()));
+  }
+  if (phase & 2) {
+    if (peer) { p.peer = peer->current(); p.peer.presignaled = 1; }
+    B200_CUDA_OK(b200_bn_bwd_apply(&p, cur_stream()));
+  }
 }
 
 void maxpool_fwd(const at::Tensor& x, at::Tensor& out, c10::optional<at::Tensor> argmax, int64_t k, int64_t stride, int64_t pad) {
@@ -859,7 +878,8 @@ void rank_barrier(CommState* cs) {
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "distribuuuu_b200 sm_100a kernels";
   m.def("conv_fprop", &conv_fprop, "tcgen05 implicit-GEMM convolution forward (NHWC bf16)", py::arg("x"), py::arg("w"),
-        py::arg("out"), py::arg("stats"), py::arg("bias"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("groups") = 1);
+        py::arg("out"), py::arg("stats"), py::arg("bias"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("groups") = 1,
+        py::arg("peer") = py::none());
   m.def("conv_dgrad", &conv_dgrad, "tcgen05 implicit-GEMM data gradient (stride 1), optional fused addend",
         py::arg("dy"), py::arg("w"), py::arg("dx"), py::arg("stride"), py::arg("pad"), py::arg("dil"), py::arg("addend") = py::none(),
         py::arg("groups") = 1);
@@ -898,7 +918,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("dw_wgrad", &dw_wgrad);
   m.def("bn_apply", &bn_apply, py::arg("y"), py::arg("residual"), py::arg("out"), py::arg("stats"), py::arg("sym_offset"), py::arg("gamma"),
         py::arg("beta"), py::arg("running_mean"), py::arg("running_var"), py::arg("save_mean"), py::arg("save_invstd"), py::arg("count"),
-        py::arg("eps"), py::arg("momentum"), py::arg("act"), py::arg("training"), py::arg("peer"), py::arg("relu_mask") = py::none());
+        py::arg("eps"), py::arg("momentum"), py::arg("act"), py::arg("training"), py::arg("peer"), py::arg("relu_mask") = py::none(),
+        py::arg("presignaled") = false);
   m.def("bn_stats", &bn_stats);
   m.def("bn_backward", &bn_backward, py::arg("y"), py::arg("dout"), py::arg("residual"), py::arg("dy"), py::arg("dresidual"), py::arg("sums"),
         py::arg("sym_offset"), py::arg("gamma"), py::arg("beta"), py::arg("save_mean"), py::arg("save_invstd"), py::arg("dgamma"), py::arg("dbeta"),

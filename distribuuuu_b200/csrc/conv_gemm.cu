@@ -487,7 +487,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
-      if (want_stats) flush_stats(st_nb);
+      if (want_stats) { flush_stats(st_nb); if (p.peer.world > 1) __threadfence(); }   // ordered before the tail counter
       if (lane == 0) bulk_wait_group<0>();            // all stores complete before the CTA may exit
       __syncwarp();
     } else {
@@ -543,6 +543,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
   else __syncthreads();
   if (warp == 1) {
     if (CG == 2) tmem_dealloc_2cta(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+  // SyncBN forward: this launch produced the layer's local statistics; the last CTA out raises this rank's flag on every
+  // peer, so the flag travels during the kernel boundary instead of inside bn_apply (elementwise.cu: peer_exchange_reduce)
+  if (EPI != EPI_F32_RED && p.peer.world > 1 && threadIdx.x == 0) {
+    const int done = atomicAdd(p.peer.ticket + 2, 1);
+    if (done == (int)gridDim.x - 1) {
+      p.peer.ticket[2] = 0;
+      __threadfence_system();
+      for (int r = 0; r < p.peer.world; ++r)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer.signal_pads[r] + p.peer.slot_base + p.peer.rank), "r"(p.peer.epoch) : "memory");
+    }
   }
 }
 

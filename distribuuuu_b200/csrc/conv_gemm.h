@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "elementwise.h"   // PeerCtx
+
 enum ConvGemmKind { KIND_FPROP = 0, KIND_DGRAD = 1, KIND_WGRAD = 2 };
 // EPI_BF16: bf16 TMA-store epilogue (+ BN statistics); _BIAS / _ADD add a per-column bias / an addend tile.  They are
 // separate instantiations so the common path carries no dead bias/addend code (the epilogue is I-cache sensitive).
@@ -40,6 +42,7 @@ struct ConvGemmParams {
   const float* bias;    // optional [N]
   long long addend;     // non-zero: add the bf16 tile described by map_add before storing (same geometry as out)
   int total_items;
+  PeerCtx peer;         // SyncBN: world > 1 => the last CTA to finish tells the peers that p.stats is final (exchange #epoch)
   int cta_group;        // 1, or 2 = CTA pairs (256-row items, B operand split across the pair); see Cfg in conv_gemm.cu
 };
 

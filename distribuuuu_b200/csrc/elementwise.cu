@@ -83,6 +83,23 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
   return t;
 }
 
+// Producer side of the exchange: called by EVERY thread at the very end of the kernel that accumulates the local
+// statistics (conv epilogue atomics, bn_bwd_reduce REDs).  The last CTA to get here tells all peers "my statistics for
+// exchange #epoch are final" -- so the flag crosses NVLink during the kernel boundary (and, in backward, during the
+// weight-gradient GEMM the engine schedules between the reduce and the apply pass) instead of inside the consumer.
+__device__ void peer_signal_at_tail(const PeerCtx& pc, unsigned total_ctas) {
+  __threadfence();                    // this thread's atomics / REDs on the statistics are ordered before the counter
+  __syncthreads();
+  if (threadIdx.x == 0 && threadIdx.y == 0) {
+    const int done = atomicAdd(pc.ticket + 2, 1);
+    if (done == (int)total_ctas - 1) {
+      pc.ticket[2] = 0;
+      __threadfence_system();
+      for (int r = 0; r < pc.world; ++r) st_release_sys(pc.signal_pads[r] + pc.slot_base + pc.rank, pc.epoch);
+    }
+  }
+}
+
 // Cross-rank reduction of one layer's [2][C] statistics, once per launch instead of once per CTA:
 //   * the first CTA to take a ticket is the *designated* CTA: it tells every peer "my statistics for exchange
 //     #epoch are final" (flags on the signal pads), waits for the peers' flags, sums the statistics of all ranks
@@ -103,8 +120,10 @@ __device__ void peer_exchange_reduce(const PeerCtx& pc, long long sym_offset, in
     unsigned long long t_begin = 0;
     if (tid == 0 && pc.wait_ns) t_begin = global_timer_ns();
     if (tid < pc.world) {
-      __threadfence_system();
-      st_release_sys(pc.signal_pads[tid] + pc.slot_base + pc.rank, pc.epoch);
+      if (!pc.presignaled) {
+        __threadfence_system();
+        st_release_sys(pc.signal_pads[tid] + pc.slot_base + pc.rank, pc.epoch);
+      }
       const uint32_t* flag = pc.signal_pads[pc.rank] + pc.slot_base + tid;
       long long t0 = clock64();
       while ((int)(ld_acquire_sys(flag) - pc.epoch) < 0) {
@@ -459,6 +478,7 @@ __global__ void __launch_bounds__(256, 2) bn_bwd_reduce_kernel(BnBwdParams p) {
       red_add_v4(p.sums + (quad >= 2 ? p.C : 0) + c + (quad & 1) * 4, s0, s1, s2, s3);
     }
   }
+  if (p.peer.world > 1) peer_signal_at_tail(p.peer, gridDim.x * gridDim.y);   // SyncBN: the exchange starts here
 }
 
 // pass 2: dy = (dz - mean(dz) - xhat * mean(dz*xhat)) * gamma * invstd (means over all ranks for SyncBN);

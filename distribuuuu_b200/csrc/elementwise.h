@@ -17,7 +17,8 @@ struct PeerCtx {
   int slot_base;                    // first signal-pad slot used by this exchange stream
   uint32_t* signal_pads[kMaxPeers]; // signal pad of every rank
   float* sym_bufs[kMaxPeers];       // statistics buffer of every rank
-  int* ticket;                      // [2] local ints: arrival ticket / departure counter
+  int* ticket;                      // [3] local ints: arrival ticket / departure counter / producer-tail counter
+  int presignaled;                  // the kernel that PRODUCED the statistics already told the peers (peer_signal_at_tail)
   float* mc_stats;                  // NVLS multicast alias of the statistics buffers (nullptr: P2P loads from every peer)
   float* reduced;                   // local scratch [2][C]: the cross-rank sums published by the designated CTA
   uint32_t* ready;                  // local flag: `reduced` holds exchange #epoch

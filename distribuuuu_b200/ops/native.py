@@ -169,7 +169,7 @@ class ConvFn(torch.autograd.Function):
     """Implicit-GEMM convolution (fprop / dgrad / wgrad on tcgen05), optional BN-statistics epilogue."""
 
     @staticmethod
-    def forward(ctx, x, eng, conv, stats, anchor, hand_to=None, out=None):
+    def forward(ctx, x, eng, conv, stats, anchor, hand_to=None, out=None, peer=None):
         K = eng.K
         xh = _nhwc(x)
         w, groups = _conv_weight(eng, conv)
@@ -181,7 +181,8 @@ class ConvFn(torch.autograd.Function):
         # `out`: a channel slice of a wider NHWC buffer the epilogue stores into directly (dense blocks)
         y = out if (out is not None and tuple(out.shape) == (N, P, Q, Kc) and groups == 1) else \
             torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
-        K.conv_fprop(xh, w, y, stats, None, s, p, d, groups)
+        # peer (SyncBN): the kernel's last CTA announces this layer's statistics exchange to the other ranks
+        K.conv_fprop(xh, w, y, stats, None, s, p, d, groups, peer)
         ctx.eng, ctx.conv = eng, conv
         ctx.save_for_backward(xh)
         ctx.x_needs_grad = x.requires_grad
@@ -206,13 +207,25 @@ class ConvFn(torch.autograd.Function):
             # weights were packed in forward (unchanged since: the bucket update is gated on mark_ready below)
             Kc, _, R, S = conv.weight.shape
             w, groups = eng.scratch(f"blockdiag_w_{id(conv)}", (Kc, R, S, 64), torch.bfloat16), conv.in_channels // 64
-            dwd = eng.scratch("blockdiag_dw", (Kc, R, S, 64), torch.float32)
-            dwd.zero_()
-            K.conv_wgrad(dyh, xh, dwd, s, p, d, groups)
-            K.blockdiag_unpack_add(dwd, eng.grad_krsc(conv.weight))
         else:
             w, groups = eng.w16_krsc(conv.weight), conv.groups
-            K.conv_wgrad(dyh, xh, eng.grad_krsc(conv.weight), s, p, d, groups)
+
+        def wgrad():
+            if cg:
+                dwd = eng.scratch("blockdiag_dw", (Kc, R, S, 64), torch.float32)
+                dwd.zero_()
+                K.conv_wgrad(dyh, xh, dwd, s, p, d, groups)
+                K.blockdiag_unpack_add(dwd, eng.grad_krsc(conv.weight))
+            else:
+                K.conv_wgrad(dyh, xh, eng.grad_krsc(conv.weight), s, p, d, groups)
+            # only now: the bucket's fused update overwrites the bf16 weights the dgrad (enqueued earlier) still reads
+            eng.mark_ready(conv.weight)
+
+        # SyncBN on several GPUs: the weight gradient is launched BETWEEN the two passes of the preceding layer's BN
+        # backward (BnActFn.backward), where it hides that layer's cross-rank exchange; otherwise right here
+        defer = eng.defer_wgrad and ctx.x_needs_grad
+        if not defer:
+            wgrad()
         dx = None
         if ctx.x_needs_grad:
             addend = ctx.sink.take() if ctx.sink is not None else None
@@ -225,9 +238,9 @@ class ConvFn(torch.autograd.Function):
                 dx = None          # the sibling conv's dgrad adds it; autograd treats None as zero
             else:
                 dx = _nchw_view(dxh)
-        # only now: the bucket's fused update overwrites the bf16 weights the dgrad above still reads
-        eng.mark_ready(conv.weight)
-        return dx, None, None, None, None, None, None
+        if defer:
+            eng.defer(wgrad)
+        return dx, None, None, None, None, None, None, None
 
 
 def _strided_dgrad(K, dyh, w, x_shape, s, p, d, groups=1, addend=None):
@@ -363,10 +376,13 @@ class BnActFn(torch.autograd.Function):
         mask = None
         if training and residual is not None and act == "relu" and (y.requires_grad or residual.requires_grad):
             mask = torch.empty((y2.shape[0], C // 8), dtype=torch.uint8, device=y.device)
+        presignaled = bool(peer is not None and stats_slot is not None and stats_slot.presignaled)
         K.bn_apply(y2, res2, out.view(-1, C), stats, stats_slot.sym_offset if stats_slot is not None else 0,
                    eng.master_view(bn.weight) if bn.affine else None, eng.master_view(bn.bias) if bn.affine else None,
                    bn.running_mean, bn.running_var, save[0], save[1], count, bn.eps,
-                   bn.momentum if bn.momentum is not None else 0.1, ACT[act], training, peer, mask)
+                   bn.momentum if bn.momentum is not None else 0.1, ACT[act], training, peer, mask, presignaled)
+        if stats_slot is not None:
+            stats_slot.presignaled = False
         if training and bn.track_running_stats:
             eng.note_bn_step(bn)
         ctx.frozen = not training
@@ -398,11 +414,20 @@ class BnActFn(torch.autograd.Function):
         dres = torch.empty((N, H, W, C), dtype=torch.bfloat16, device=dout.device) if ctx.res_needs_grad else None
         slot = eng.bwd_slot(bn)
         peer = eng.peer_state if eng.sync_bn else None
-        K.bn_backward(y2, d2, res2, dy.view(-1, C), dres.view(-1, C) if dres is not None else None, slot.tensor,
-                      slot.sym_offset, eng.master_view(bn.weight) if bn.affine else None,
-                      eng.master_view(bn.bias) if bn.affine else None, save[0], save[1],
-                      eng.grad_flat_view(bn.weight) if bn.affine else None,
-                      eng.grad_flat_view(bn.bias) if bn.affine else None, ctx.count, ACT[ctx.act], peer, mask)
+        args = (y2, d2, res2, dy.view(-1, C), dres.view(-1, C) if dres is not None else None, slot.tensor,
+                slot.sym_offset, eng.master_view(bn.weight) if bn.affine else None,
+                eng.master_view(bn.bias) if bn.affine else None, save[0], save[1],
+                eng.grad_flat_view(bn.weight) if bn.affine else None,
+                eng.grad_flat_view(bn.bias) if bn.affine else None, ctx.count, ACT[ctx.act], peer, mask)
+        if peer is not None and eng.defer_wgrad:
+            # reduce pass (its last CTA opens the cross-rank exchange) -> the weight-gradient GEMM of the conv that
+            # consumed this BN's output, deferred by ConvFn.backward -> apply pass (waits for the peers' sums, which have
+            # been travelling in the meantime)
+            K.bn_backward(*args, 1)
+            eng.flush_deferred()
+            K.bn_backward(*args, 2)
+        else:
+            K.bn_backward(*args)
         if bn.affine:
             eng.mark_ready(bn.weight)
             eng.mark_ready(bn.bias)
@@ -746,7 +771,10 @@ class NativeOps:
             hand_to = eng.last_sink.get(input_grad_to) if (input_grad_to is not None and torch.is_grad_enabled()) else None
             dest = out_buffer.take(conv.out_channels) if (out_buffer is not None and bn is None and act is None
                                                           and residual is None) else None
-            y = ConvFn.apply(x, eng, conv, stats, eng.anchor, hand_to, dest)
+            peer = eng.peer_state if (slot is not None and eng.sync_bn) else None
+            y = ConvFn.apply(x, eng, conv, stats, eng.anchor, hand_to, dest, peer)
+            if peer is not None:
+                slot.presignaled = True     # consumed (and cleared) by the BnActFn right below
         elif self._depthwise_ok(conv, x):
             y = DwConvFn.apply(x, eng, conv, stats, eng.anchor)
         else:

@@ -45,6 +45,7 @@ _ONE_SHOT_BYTES = 512 * 1024
 class _Slot:
     tensor: torch.Tensor
     sym_offset: int
+    presignaled: bool = False   # the conv that filled the slot already announced the SyncBN exchange (its last CTA)
 
 
 @dataclass
@@ -488,6 +489,21 @@ class NativeEngine(nn.Module):
 
     _in_train_step = False
     debug_skip_comm = False   # measurement aid: update locally without any gradient exchange (ranks diverge!)
+    _deferred = None
+
+    @property
+    def defer_wgrad(self) -> bool:
+        """SyncBN across GPUs: weight-gradient GEMMs are launched between the two passes of the preceding BN backward."""
+        return self.sync_bn and self.world > 1
+
+    def defer(self, fn):
+        self.flush_deferred()
+        self._deferred = fn
+
+    def flush_deferred(self):
+        fn, self._deferred = self._deferred, None
+        if fn is not None:
+            fn()
 
     # ------------------------------------------------------------------------------ steps
     def forward(self, x):
@@ -512,7 +528,9 @@ class NativeEngine(nn.Module):
                 logits = self.module(inputs)
                 loss, hits1, hitsk = self.ops.cross_entropy_topk(logits, targets, topk)
             loss.backward()
+            self.flush_deferred()
         finally:
+            self._deferred = None
             self._in_train_step = False
         if self._bn_stepped:
             torch._foreach_add_(self._bn_stepped, 1)

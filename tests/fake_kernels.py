@@ -87,7 +87,7 @@ class FakeKernels:
         _raw(dst.view(rows, cols)).add_(src.view(rows, cols_pad)[:, :cols])
 
     # ---------------------------------------------------------------- convolutions (implicit GEMM on the GPU)
-    def conv_fprop(self, x, w, y, stats, bias, stride, pad, dil, groups=1):
+    def conv_fprop(self, x, w, y, stats, bias, stride, pad, dil, groups=1, peer=None):
         self._count("conv_fprop")
         out = F.conv2d(_nchw(x), w.permute(0, 3, 1, 2).float(), bias.float() if bias is not None else None,
                        stride, pad, dil, groups)
@@ -278,7 +278,7 @@ class FakeKernels:
         _raw(stats)[C:2 * C] += (f * f).sum(0)
 
     def bn_apply(self, y2, res2, out2, stats, sym_offset, gamma, beta, rm, rv, save_mean, save_invstd, count, eps,
-                 momentum, act, training, peer, relu_mask=None):
+                 momentum, act, training, peer, relu_mask=None, presignaled=False):
         self._count("bn_apply")
         assert peer is None
         C = y2.shape[1]
