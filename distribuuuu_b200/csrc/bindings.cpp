@@ -167,6 +167,11 @@ bool cta_pairs_enabled() {
   if (v < 0) { const char* e = getenv("B200_CONV_CG"); v = (e && atoi(e) == 1) ? 0 : 1; }
   return v == 1;
 }
+bool conv_m_fastest() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("B200_CONV_ORDER"); v = (e && e[0] == 'm') ? 1 : 0; }
+  return v == 1;
+}
 struct TilePlan { int bn; int resident; int res_stages; int cg; };
 TilePlan plan_tiles(int n_cols, int k_iters, long long m_tiles, int groups, int sms) {
   constexpr int kRing = 160 * 1024, kA = 16384;
@@ -248,6 +253,7 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   p.groups = G; p.a_cg = cin_g; p.out_cg = cout_g;
   const int cg = plan.cg;
   p.cta_group = cg;
+  p.m_fastest = conv_m_fastest() ? 1 : 0;
   p.m_blocks = (M + 128 * cg - 1) / (128 * cg); p.n_blocks = (cout_g + bn - 1) / bn;
   p.taps = g.R * g.S; p.S = g.S; p.kb_per_tap = (cin_g + 63) / 64; p.dil = dil;
   p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);
@@ -310,6 +316,7 @@ void dgrad_launch(const at::Tensor& dy, const at::Tensor& w, at::Tensor& out, co
   p.groups = G; p.a_cg = cout_g; p.out_cg = cin_g;
   const int cg = plan.cg;
   p.cta_group = cg;
+  p.m_fastest = conv_m_fastest() ? 1 : 0;
   p.m_blocks = (M + 128 * cg - 1) / (128 * cg); p.n_blocks = (cin_g + bn - 1) / bn;
   p.taps = taps_v; p.S = gm.Sv; p.kb_per_tap = (cout_g + 63) / 64; p.dil = gm.dil;
   p.a_im2col = pointwise ? 0 : 1; p.a_nbox = 1; p.a_kstep16 = kKMajorStep16; p.a_desc_hi = desc_hi_sw128(kKMajorLbo, kKMajorSbo);

@@ -62,17 +62,17 @@ static __device__ __noinline__ WorkItem decode_item(const ConvGemmParams& p, int
   WorkItem w;
   if (p.kind != KIND_WGRAD) {
     int nb, mb;
-    if (p.b_resident) {
-      // n fastest: the grid is a multiple of n_blocks, so a CTA keeps ONE n-block (its resident weight slab) for life
+    if (p.b_resident || !p.m_fastest) {
+      // n fastest (resident mode: the grid is a multiple of n_blocks, so a CTA keeps ONE n-block -- its resident weight
+      // slab -- for life; streaming mode: the CTAs running at the same time share A tiles and spread over n_blocks B tiles)
       nb = item % p.n_blocks;
       const int rest = item / p.n_blocks;
       mb = rest % p.m_blocks;
       w.g = rest / p.m_blocks;                     // conv group (0 when groups == 1)
     } else {
-      // m fastest: a CTA's consecutive items share the n-block, so (a) the BN statistics it keeps in registers are
-      // flushed (atomics on 2 x BN hot addresses) a handful of times per launch instead of after every item -- with n
-      // fastest and 74 pairs (or N = 2048: 8 n-blocks on 148 CTAs) every item switched n-block, which cost 50 % on
-      // 256->1024 @14^2 -- and (b) all CTAs read the same weight tile from L2 at the same time
+      // m fastest: a CTA's consecutive items share the n-block (BN statistics flushed a handful of times per launch), but
+      // every CTA then pulls the SAME weight tile from L2 at the same time -- measured slower (profiles/r2), kept as an
+      // experiment knob (B200_CONV_ORDER=m)
       mb = item % p.m_blocks;
       const int rest = item / p.m_blocks;
       nb = rest % p.n_blocks;

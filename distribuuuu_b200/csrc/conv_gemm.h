@@ -43,6 +43,7 @@ struct ConvGemmParams {
   long long addend;     // non-zero: add the bf16 tile described by map_add before storing (same geometry as out)
   int total_items;
   PeerCtx peer;         // SyncBN: world > 1 => the last CTA to finish tells the peers that p.stats is final (exchange #epoch)
+  int m_fastest;        // fprop/dgrad item order: 0 = n-block fastest, 1 = m-block fastest (ignored in resident mode)
   int cta_group;        // 1, or 2 = CTA pairs (256-row items, B operand split across the pair); see Cfg in conv_gemm.cu
 };
 

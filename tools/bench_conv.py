@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--iters", type=int, default=7)
     ap.add_argument("--shapes", type=int, nargs="*", help="indices into SHAPES (default: all)")
     ap.add_argument("--no-cudnn", action="store_true", help="fprop of our kernel only")
+    ap.add_argument("--no-stats", action="store_true", help="fprop without the BN-statistics epilogue")
     ap.add_argument("--ours-only", action="store_true", help="all three directions of our kernels, no cuDNN timing (A/B runs)")
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "conv_shapes.json"))
     a = ap.parse_args()
@@ -73,7 +74,7 @@ def main():
         flops = 2.0 * B * p * p * cout * cin * k * k
         xc, wc, dyc = x.permute(0, 3, 1, 2), w.permute(0, 3, 1, 2), dy.permute(0, 3, 1, 2)
         r = {"shape": f"{cin}->{cout} k{k} s{s} {h}->{p}", "count": cnt, "gflop": flops / 1e9}
-        r["fprop_ours_ms"] = timeit(lambda: K.conv_fprop(x, w, y, st, None, s, pad, 1), a.iters, flush)
+        r["fprop_ours_ms"] = timeit(lambda: K.conv_fprop(x, w, y, None if a.no_stats else st, None, s, pad, 1), a.iters, flush)
         if a.no_cudnn:
             rows.append(r)
             continue
