@@ -662,23 +662,59 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
 }
 
 // Global average pool [N][HW][C] -> [N][C] and its backward (broadcast / HW).
-__global__ void gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int N, int HW, int C) {
-  const int total = N * (C / VEC);
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
-    const int cv = idx % (C / VEC), n = idx / (C / VEC);
-    float acc[8];
+// CTA = (32 channel vectors) x (8 pixel lanes) of ONE sample: the pixel loop is split over threadIdx.y (4 loads in flight
+// per thread) and reduced through shared memory.  The first version had one thread walk all HW pixels of a channel
+// vector -- with the squeeze-excite layers of RegNetY / EfficientNet (C = 32..224 at 112^2..56^2, batch 64) that was a
+// few thousand threads in total and 6.8 ms of a 20 ms EfficientNet-B0 step.
+__global__ void __launch_bounds__(256) gap_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ out, int HW, int C) {
+  const int cv = blockIdx.x * 32 + threadIdx.x;
+  const int n = blockIdx.y;
+  const bool active = cv * VEC < C;
+  float acc[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-    for (int t = 0; t < HW; ++t) {
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  if (active) {
+    const __nv_bfloat16* base = x + (long long)n * HW * C + cv * VEC;
+    int t = threadIdx.y;
+    for (; t + 24 < HW; t += 32) {
+      uint4 r0 = ldg_stream(base + (long long)t * C), r1 = ldg_stream(base + (long long)(t + 8) * C);
+      uint4 r2 = ldg_stream(base + (long long)(t + 16) * C), r3 = ldg_stream(base + (long long)(t + 24) * C);
       float v[8];
-      load8(x + ((long long)n * HW + t) * C + cv * VEC, v);
+      unpack8f(r0, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      unpack8f(r1, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      unpack8f(r2, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      unpack8f(r3, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += v[i];
     }
-    const float inv = 1.f / HW;
+    for (; t < HW; t += 8) {
+      float v[8];
+      load8(base + (long long)t * C, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= inv;
-    store8(out + (long long)n * C + cv * VEC, acc);
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+  __shared__ float sm[8][32][9];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[threadIdx.y][threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.y == 0 && active) {
+    const float inv = 1.f / HW;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s_ = 0.f;
+#pragma unroll
+      for (int y = 0; y < 8; ++y) s_ += sm[y][threadIdx.x][i];
+      o[i] = s_ * inv;
+    }
+    store8(out + (long long)n * C + cv * VEC, o);
   }
 }
 // I = index type: 32-bit whenever the element count allows it (64-bit divisions cost ~100 instructions each)
@@ -768,28 +804,43 @@ __global__ void channel_scale_fwd_kernel(const __nv_bfloat16* __restrict__ x, co
     store8(out + o, v);
   }
 }
-__global__ void channel_scale_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
+__global__ void __launch_bounds__(256) channel_scale_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ x,
                                          const __nv_bfloat16* __restrict__ gate, __nv_bfloat16* __restrict__ dx,
                                          float* __restrict__ dgate, int HW, int C) {
   const int cv = blockIdx.x * blockDim.x + threadIdx.x;
   const int c0 = cv * VEC;
-  if (c0 >= C) return;
+  const bool active = c0 < C;
   const int n = blockIdx.z;
   float g[8], acc[8];
-  load8(gate + (long long)n * C + c0, g);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-  for (int t = blockIdx.y * blockDim.y + threadIdx.y; t < HW; t += gridDim.y * blockDim.y) {
-    const long long o = ((long long)n * HW + t) * C + c0;
-    float d[8], v[8];
-    load8(dout + o, d);
-    load8(x + o, v);
+  for (int i = 0; i < 8; ++i) { acc[i] = 0.f; g[i] = 0.f; }
+  if (active) {
+    load8(gate + (long long)n * C + c0, g);
+    for (int t = blockIdx.y * blockDim.y + threadIdx.y; t < HW; t += gridDim.y * blockDim.y) {
+      const long long o = ((long long)n * HW + t) * C + c0;
+      float d[8], v[8];
+      load8(dout + o, d);
+      load8(x + o, v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { acc[i] = fmaf(d[i], v[i], acc[i]); d[i] *= g[i]; }
-    store8(dx + o, d);
+      for (int i = 0; i < 8; ++i) { acc[i] = fmaf(d[i], v[i], acc[i]); d[i] *= g[i]; }
+      store8(dx + o, d);
+    }
   }
+  // reduce over threadIdx.y in shared memory, then ONE atomic per channel and CTA (the per-thread atomics of the first
+  // version -- 16 M per launch on RegNetY-160's stage 3 -- were the whole cost of this kernel)
+  __shared__ float sm[256 * 9];
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) atomicAdd(dgate + (long long)n * C + c0 + i, acc[i]);
+  for (int i = 0; i < 8; ++i) sm[tid * 9 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.y == 0 && active) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float s_ = 0.f;
+      for (int y = 0; y < (int)blockDim.y; ++y) s_ += sm[(y * blockDim.x + threadIdx.x) * 9 + i];
+      atomicAdd(dgate + (long long)n * C + c0 + i, s_);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1046,7 +1097,7 @@ extern "C" int b200_maxpool_bwd(const void* dout, const void* argmax, void* dx, 
   return (int)cudaGetLastError();
 }
 extern "C" int b200_gap_fwd(const void* x, void* out, int N, int HW, int C, cudaStream_t s) {
-  gap_fwd_kernel<<<ew_grid((long long)N * (C / VEC), 128), 128, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, N, HW, C);
+  gap_fwd_kernel<<<dim3((C / VEC + 31) / 32, N), dim3(32, 8), 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)out, HW, C);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_gap_bwd(const void* dout, void* dx, int N, int HW, int C, cudaStream_t s) {
@@ -1072,8 +1123,9 @@ static inline void scale_dims(int HW, int C, int N, dim3& grid, dim3& block) {
   int bx = 1;
   while (bx < 32 && bx < cvs) bx <<= 1;
   const int by = 256 / bx;
-  int gy = (HW + by - 1) / by;
+  int gy = (HW + 4 * by - 1) / (4 * by);   // >= 4 pixel iterations per thread
   if (gy > 32) gy = 32;
+  if (gy < 1) gy = 1;
   grid = dim3((cvs + bx - 1) / bx, gy, N);
   block = dim3(bx, by);
 }

@@ -154,198 +154,206 @@ __global__ void blockdiag_unpack_add_kernel(const float* __restrict__ dense, flo
 
 // ------------------------------------------------------------------------------------------------ squeeze-excite MLP
 // gate[n][c] = sigmoid(b2[c] + sum_j w2[c][j] * act(b1[j] + sum_c' w1[j][c'] * s[n][c']))   (s = pooled input, bf16)
-// One CTA handles kSeS samples so the (L2-resident) weights are streamed once per kSeS samples.
-// pre1 [N][r] fp32 (pre-activation of the hidden layer) is kept for the backward pass.
+// The MLP is a pair of skinny GEMMs ([N x C] x [C x r], r = 4 .. 350).  Every kernel below puts the WIDE dimension on the
+// grid -- hidden units (fc1) or channels (fc2) in x, groups of kSeS samples in y -- so that even a batch of 64 fills the
+// machine; the first version (one CTA per 4 samples doing everything) ran on 16 CTAs and was 40 % of a RegNetY-160 step.
 constexpr int kSeS = 4;
-__global__ void __launch_bounds__(256) se_gate_fwd_kernel(const __nv_bfloat16* __restrict__ s, const __nv_bfloat16* __restrict__ w1,
-                                                          const float* __restrict__ b1, const __nv_bfloat16* __restrict__ w2,
-                                                          const float* __restrict__ b2, float* __restrict__ pre1,
-                                                          __nv_bfloat16* __restrict__ gate, int N, int C, int r, int act) {
-  extern __shared__ float sm[];
-  float* s_in = sm;                 // [kSeS][C]
-  float* s_h = sm + kSeS * C;       // [kSeS][r]
-  const int n0 = blockIdx.x * kSeS;
-  const int ns = min(kSeS, N - n0);
-  for (int i = threadIdx.x; i < kSeS * C; i += blockDim.x) {
-    const int q = i / C, c = i - q * C;
-    s_in[i] = q < ns ? __bfloat162float(s[(long long)(n0 + q) * C + c]) : 0.f;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int j = warp; j < r; j += nwarps) {            // hidden unit j: warp-wide dot products over C
-    float acc[kSeS];
+
+// fc1: pre1[n][j] = b1[j] + sum_c w1[j][c] * s[n][c].   grid (ceil(r/8), ceil(N/kSeS)), 8 warps, warp = hidden unit j
+__global__ void __launch_bounds__(256) se_fc1_kernel(const __nv_bfloat16* __restrict__ s, const __nv_bfloat16* __restrict__ w1,
+                                                     const float* __restrict__ b1, float* __restrict__ pre1, int N, int C, int r) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  const int n0 = blockIdx.y * kSeS;
+  if (j >= r) return;
+  float acc[kSeS];
 #pragma unroll
-    for (int q = 0; q < kSeS; ++q) acc[q] = 0.f;
-    const __nv_bfloat16* wr = w1 + (long long)j * C;
-    for (int c = lane; c < C; c += 32) {
-      const float w = __bfloat162float(wr[c]);
+  for (int q = 0; q < kSeS; ++q) acc[q] = 0.f;
+  const __nv_bfloat16* wr = w1 + (long long)j * C;
+  for (int c = lane * 8; c < C; c += 256) {          // C % 8 == 0: 16-byte vectors
+    float w[8];
+    ld8(wr + c, w);
 #pragma unroll
-      for (int q = 0; q < kSeS; ++q) acc[q] = fmaf(w, s_in[q * C + c], acc[q]);
-    }
+    for (int q = 0; q < kSeS; ++q) {
+      if (n0 + q < N) {
+        float x[8];
+        ld8(s + (long long)(n0 + q) * C + c, x);
 #pragma unroll
-    for (int q = 0; q < kSeS; ++q) acc[q] = warp_sum(acc[q]);
-    if (lane == 0) {
-      const float bb = b1 ? b1[j] : 0.f;
-#pragma unroll
-      for (int q = 0; q < kSeS; ++q) {
-        const float z = acc[q] + bb;
-        if (q < ns) pre1[(long long)(n0 + q) * r + j] = z;
-        s_h[q * r + j] = act_f(z, act);
+        for (int e = 0; e < 8; ++e) acc[q] = fmaf(w[e], x[e], acc[q]);
       }
     }
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {  // output channel c: sequential dot over the (small) hidden width
-    float acc[kSeS];
-    const float bb = b2 ? b2[c] : 0.f;
 #pragma unroll
-    for (int q = 0; q < kSeS; ++q) acc[q] = bb;
-    const __nv_bfloat16* wr = w2 + (long long)c * r;
-    for (int j = 0; j < r; ++j) {
-      const float w = __bfloat162float(wr[j]);
+  for (int q = 0; q < kSeS; ++q) acc[q] = warp_sum(acc[q]);
+  if (lane == 0) {
+    const float bb = b1 ? b1[j] : 0.f;
 #pragma unroll
-      for (int q = 0; q < kSeS; ++q) acc[q] = fmaf(w, s_h[q * r + j], acc[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < kSeS; ++q)
-      if (q < ns) gate[(long long)(n0 + q) * C + c] = __float2bfloat16(1.f / (1.f + __expf(-acc[q])));
+    for (int q = 0; q < kSeS; ++q) if (n0 + q < N) pre1[(long long)(n0 + q) * r + j] = acc[q] + bb;
   }
 }
 
-// Backward of the MLP, data part (one CTA per kSeS samples, no weight-gradient atomics):
-//   dz2 [N][C] = dgate * gate * (1 - gate);  h [N][r] = act(pre1);  dz1 [N][r] = (dz2 . w2) * act'(pre1);
-//   ds [N][C] = dz1 . w1   (gradient wrt the pooled input).   dz2 / h / dz1 are written out for the weight part.
-__global__ void __launch_bounds__(256) se_gate_bwd_data_kernel(const float* __restrict__ dgate, const __nv_bfloat16* __restrict__ gate,
-                                                               const float* __restrict__ pre1, const __nv_bfloat16* __restrict__ w1,
-                                                               const __nv_bfloat16* __restrict__ w2, float* __restrict__ dz2_out,
-                                                               float* __restrict__ h_out, float* __restrict__ dz1_out,
-                                                               float* __restrict__ ds, int N, int C, int r, int act) {
-  extern __shared__ float sm[];
-  float* s_dz2 = sm;                     // [kSeS][C]
-  float* s_dh = sm + kSeS * C;           // [kSeS][r]  (accumulated with shared atomics, then turned into dz1 in place)
-  const int n0 = blockIdx.x * kSeS;
-  const int ns = min(kSeS, N - n0);
-  for (int i = threadIdx.x; i < kSeS * C; i += blockDim.x) {
-    const int q = i / C, c = i - q * C;
-    float dz = 0.f;
-    if (q < ns) {
-      const long long o = (long long)(n0 + q) * C + c;
-      const float g = __bfloat162float(gate[o]);
-      dz = dgate[o] * g * (1.f - g);
-      dz2_out[o] = dz;
-    }
-    s_dz2[i] = dz;
-  }
-  for (int i = threadIdx.x; i < kSeS * r; i += blockDim.x) s_dh[i] = 0.f;
-  __syncthreads();
-  // dh[q][j] = sum_c dz2[q][c] * w2[c][j]: thread = (hidden unit j, slice of c); consecutive threads read consecutive j
-  int jt = 1;
-  while (jt < r && jt < 256) jt <<= 1;
-  const int ct = 256 / jt;
-  const int jl = threadIdx.x % jt, cs = threadIdx.x / jt;
-  for (int j = jl; j < r; j += jt) {
-    float acc[kSeS];
-#pragma unroll
-    for (int q = 0; q < kSeS; ++q) acc[q] = 0.f;
-    for (int c = cs; c < C; c += ct) {
-      const float w = __bfloat162float(w2[(long long)c * r + j]);
-#pragma unroll
-      for (int q = 0; q < kSeS; ++q) acc[q] = fmaf(w, s_dz2[q * C + c], acc[q]);
-    }
-#pragma unroll
-    for (int q = 0; q < kSeS; ++q) atomicAdd(&s_dh[q * r + j], acc[q]);
-  }
-  __syncthreads();
+// fc2 + sigmoid: gate[n][c].   grid (ceil(C/256), ceil(N/kSeS)), thread = channel c, hidden activations in smem
+__global__ void __launch_bounds__(256) se_fc2_kernel(const float* __restrict__ pre1, const __nv_bfloat16* __restrict__ w2,
+                                                     const float* __restrict__ b2, __nv_bfloat16* __restrict__ gate, int N, int C, int r,
+                                                     int act) {
+  extern __shared__ float sm[];            // [kSeS][r]
+  const int n0 = blockIdx.y * kSeS;
   for (int i = threadIdx.x; i < kSeS * r; i += blockDim.x) {
     const int q = i / r, j = i - q * r;
-    float d = 0.f;
-    if (q < ns) {
-      const long long o = (long long)(n0 + q) * r + j;
-      const float z = pre1[o];
-      d = s_dh[i] * act_df(z, act);
-      h_out[o] = act_f(z, act);
-      dz1_out[o] = d;
-    }
-    s_dh[i] = d;
+    sm[i] = (n0 + q < N) ? act_f(pre1[(long long)(n0 + q) * r + j], act) : 0.f;
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {   // ds[q][c] = sum_j dz1[q][j] * w1[j][c]  (coalesced over c)
-    float dsv[kSeS];
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float acc[kSeS];
+  const float bb = b2 ? b2[c] : 0.f;
 #pragma unroll
-    for (int q = 0; q < kSeS; ++q) dsv[q] = 0.f;
-    for (int j = 0; j < r; ++j) {
-      const float w = __bfloat162float(w1[(long long)j * C + c]);
+  for (int q = 0; q < kSeS; ++q) acc[q] = bb;
+  const __nv_bfloat16* wr = w2 + (long long)c * r;
+  for (int j = 0; j < r; ++j) {
+    const float w = __bfloat162float(wr[j]);
 #pragma unroll
-      for (int q = 0; q < kSeS; ++q) dsv[q] = fmaf(s_dh[q * r + j], w, dsv[q]);
+    for (int q = 0; q < kSeS; ++q) acc[q] = fmaf(w, sm[q * r + j], acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < kSeS; ++q)
+    if (n0 + q < N) gate[(long long)(n0 + q) * C + c] = __float2bfloat16(1.f / (1.f + __expf(-acc[q])));
+}
+
+// backward 1: dz1[n][j] = (sum_c dz2[n][c] * w2[c][j]) * act'(pre1[n][j]),  h[n][j] = act(pre1[n][j]),
+//             with dz2 = dgate * gate * (1 - gate) recomputed on the fly.   grid (ceil(r/8), ceil(N/kSeS)), warp = hidden unit
+__global__ void __launch_bounds__(256) se_bwd_hidden_kernel(const float* __restrict__ dgate, const __nv_bfloat16* __restrict__ gate,
+                                                            const float* __restrict__ pre1, const __nv_bfloat16* __restrict__ w2,
+                                                            float* __restrict__ h_out, float* __restrict__ dz1_out, int N, int C, int r,
+                                                            int act) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 8 + warp;
+  const int n0 = blockIdx.y * kSeS;
+  if (j >= r) return;
+  float acc[kSeS];
+#pragma unroll
+  for (int q = 0; q < kSeS; ++q) acc[q] = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    const float w = __bfloat162float(w2[(long long)c * r + j]);
+#pragma unroll
+    for (int q = 0; q < kSeS; ++q) {
+      if (n0 + q < N) {
+        const long long o = (long long)(n0 + q) * C + c;
+        const float g = __bfloat162float(gate[o]);
+        acc[q] = fmaf(w, dgate[o] * g * (1.f - g), acc[q]);
+      }
     }
+  }
 #pragma unroll
-    for (int q = 0; q < kSeS; ++q)
-      if (q < ns) ds[(long long)(n0 + q) * C + c] = dsv[q];
+  for (int q = 0; q < kSeS; ++q) acc[q] = warp_sum(acc[q]);
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < kSeS; ++q) {
+      if (n0 + q < N) {
+        const long long o = (long long)(n0 + q) * r + j;
+        const float z = pre1[o];
+        h_out[o] = act_f(z, act);
+        dz1_out[o] = acc[q] * act_df(z, act);
+      }
+    }
   }
 }
 
-// Backward of the MLP, weight part: every (c, j) pair is owned by exactly one thread, which loops over the batch
-// (no atomics):  dw2[c][j] += sum_n dz2[n][c] h[n][j];  dw1[j][c] += sum_n dz1[n][j] s[n][c];  db2, db1 likewise.
-// CTA = 32 channels x 8 hidden-unit lanes; a thread owns hidden units jl, jl + 8, ... (<= kSeJ per pass).
+// backward 2: ds[n][c] = sum_j dz1[n][j] * w1[j][c]  (gradient wrt the pooled input) and dz2[n][c] written out for the
+// weight-gradient kernel.   grid (ceil(C/256), ceil(N/kSeS)), thread = channel
+__global__ void __launch_bounds__(256) se_bwd_input_kernel(const float* __restrict__ dgate, const __nv_bfloat16* __restrict__ gate,
+                                                           const float* __restrict__ dz1, const __nv_bfloat16* __restrict__ w1,
+                                                           float* __restrict__ dz2_out, float* __restrict__ ds, int N, int C, int r) {
+  extern __shared__ float sm[];            // [kSeS][r]
+  const int n0 = blockIdx.y * kSeS;
+  for (int i = threadIdx.x; i < kSeS * r; i += blockDim.x) {
+    const int q = i / r, j = i - q * r;
+    sm[i] = (n0 + q < N) ? dz1[(long long)(n0 + q) * r + j] : 0.f;
+  }
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float acc[kSeS];
+#pragma unroll
+  for (int q = 0; q < kSeS; ++q) acc[q] = 0.f;
+  for (int j = 0; j < r; ++j) {
+    const float w = __bfloat162float(w1[(long long)j * C + c]);
+#pragma unroll
+    for (int q = 0; q < kSeS; ++q) acc[q] = fmaf(sm[q * r + j], w, acc[q]);
+  }
+#pragma unroll
+  for (int q = 0; q < kSeS; ++q) {
+    if (n0 + q < N) {
+      const long long o = (long long)(n0 + q) * C + c;
+      const float g = __bfloat162float(gate[o]);
+      dz2_out[o] = dgate[o] * g * (1.f - g);
+      ds[o] = acc[q];
+    }
+  }
+}
+
+// backward 3, weight part: every (c, j) pair is owned by exactly one thread, which loops over the batch (no atomics):
+//   dw2[c][j] += sum_n dz2[n][c] h[n][j];  dw1[j][c] += sum_n dz1[n][j] s[n][c];  db2, db1 likewise.
+// CTA = 32 channels x 8 hidden-unit lanes; blockIdx.y = pass over the hidden width (8 * kSeJ = 128 units per pass).
 constexpr int kSeJ = 16, kSeNB = 8;
 __global__ void __launch_bounds__(256) se_gate_bwd_weights_kernel(const float* __restrict__ dz2, const float* __restrict__ h,
                                                                   const float* __restrict__ dz1, const __nv_bfloat16* __restrict__ s,
                                                                   float* __restrict__ dw1, float* __restrict__ db1,
                                                                   float* __restrict__ dw2, float* __restrict__ db2, int N, int C, int r) {
   extern __shared__ float sm[];
-  float* s_h = sm;                       // [kSeNB][r]
-  float* s_d1 = sm + kSeNB * r;          // [kSeNB][r]
+  const int j0 = blockIdx.y * 8 * kSeJ;
+  const int jw = min(8 * kSeJ, r - j0);  // hidden units of this pass
+  float* s_h = sm;                       // [kSeNB][jw]
+  float* s_d1 = sm + kSeNB * jw;         // [kSeNB][jw]
   const int cl = threadIdx.x & 31, jl = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + cl;
   const bool c_ok = c < C;
-  for (int j0 = 0; j0 < r; j0 += 8 * kSeJ) {            // passes over the hidden width (one pass for r <= 128)
-    float a2[kSeJ], a1[kSeJ], sb2 = 0.f;
+  float a2[kSeJ], a1[kSeJ], sb2 = 0.f;
 #pragma unroll
-    for (int t = 0; t < kSeJ; ++t) { a2[t] = 0.f; a1[t] = 0.f; }
-    for (int nb = 0; nb < N; nb += kSeNB) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < kSeNB * r; i += blockDim.x) {
-        const int q = i / r, j = i - q * r;
-        const bool ok = nb + q < N;
-        s_h[i] = ok ? h[(long long)(nb + q) * r + j] : 0.f;
-        s_d1[i] = ok ? dz1[(long long)(nb + q) * r + j] : 0.f;
-      }
-      __syncthreads();
-#pragma unroll
-      for (int q = 0; q < kSeNB; ++q) {
-        float z2 = 0.f, sv = 0.f;
-        if (c_ok && nb + q < N) {
-          z2 = dz2[(long long)(nb + q) * C + c];
-          sv = __bfloat162float(s[(long long)(nb + q) * C + c]);
-        }
-        sb2 += z2;
-#pragma unroll
-        for (int t = 0; t < kSeJ; ++t) {
-          const int j = j0 + jl + 8 * t;
-          if (j < r) {
-            a2[t] = fmaf(z2, s_h[q * r + j], a2[t]);
-            a1[t] = fmaf(s_d1[q * r + j], sv, a1[t]);
-          }
-        }
-      }
+  for (int t = 0; t < kSeJ; ++t) { a2[t] = 0.f; a1[t] = 0.f; }
+  for (int nb = 0; nb < N; nb += kSeNB) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSeNB * jw; i += blockDim.x) {
+      const int q = i / jw, j = i - q * jw;
+      const bool ok = nb + q < N;
+      s_h[i] = ok ? h[(long long)(nb + q) * r + j0 + j] : 0.f;
+      s_d1[i] = ok ? dz1[(long long)(nb + q) * r + j0 + j] : 0.f;
     }
-    if (c_ok) {
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < kSeNB; ++q) {
+      float z2 = 0.f, sv = 0.f;
+      if (c_ok && nb + q < N) {
+        z2 = dz2[(long long)(nb + q) * C + c];
+        sv = __bfloat162float(s[(long long)(nb + q) * C + c]);
+      }
+      sb2 += z2;
 #pragma unroll
       for (int t = 0; t < kSeJ; ++t) {
-        const int j = j0 + jl + 8 * t;
-        if (j < r) {
-          dw2[(long long)c * r + j] += a2[t];
-          dw1[(long long)j * C + c] += a1[t];
+        const int j = jl + 8 * t;
+        if (j < jw) {
+          a2[t] = fmaf(z2, s_h[q * jw + j], a2[t]);
+          a1[t] = fmaf(s_d1[q * jw + j], sv, a1[t]);
         }
       }
-      if (j0 == 0 && jl == 0 && db2) db2[c] += sb2;
     }
   }
-  if (blockIdx.x == 0 && db1) {                          // db1[j] = sum_n dz1[n][j]
-    for (int j = threadIdx.x; j < r; j += blockDim.x) {
+  if (c_ok) {
+#pragma unroll
+    for (int t = 0; t < kSeJ; ++t) {
+      const int j = jl + 8 * t;
+      if (j < jw) {
+        dw2[(long long)c * r + j0 + j] += a2[t];
+        dw1[(long long)(j0 + j) * C + c] += a1[t];
+      }
+    }
+    if (blockIdx.y == 0 && jl == 0 && db2) db2[c] += sb2;
+  }
+  if (blockIdx.x == 0 && db1) {                          // db1[j] = sum_n dz1[n][j] for the units of this pass
+    for (int j = threadIdx.x; j < jw; j += blockDim.x) {
       float a = 0.f;
-      for (int n = 0; n < N; ++n) a += dz1[(long long)n * r + j];
-      db1[j] += a;
+      for (int n = 0; n < N; ++n) a += dz1[(long long)n * r + j0 + j];
+      db1[j0 + j] += a;
     }
   }
 }
@@ -408,15 +416,12 @@ extern "C" int b200_blockdiag_unpack_add(const float* dense, float* thin, int K,
 }
 extern "C" int b200_se_gate_fwd(const void* sp, const void* w1, const float* b1, const void* w2, const float* b2, float* pre1, void* gate,
                                 int N, int C, int r, int act, cudaStream_t s) {
-  const size_t smem = (size_t)kSeS * (C + r) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(se_gate_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
-  se_gate_fwd_kernel<<<(N + kSeS - 1) / kSeS, 256, smem, s>>>((const __nv_bfloat16*)sp, (const __nv_bfloat16*)w1, b1, (const __nv_bfloat16*)w2,
-                                                             b2, pre1, (__nv_bfloat16*)gate, N, C, r, act);
+  const int gy = (N + kSeS - 1) / kSeS;
+  se_fc1_kernel<<<dim3((r + 7) / 8, gy), 256, 0, s>>>((const __nv_bfloat16*)sp, (const __nv_bfloat16*)w1, b1, pre1, N, C, r);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  se_fc2_kernel<<<dim3((C + 255) / 256, gy), 256, (size_t)kSeS * r * sizeof(float), s>>>(pre1, (const __nv_bfloat16*)w2, b2, (__nv_bfloat16*)gate,
+                                                                                        N, C, r, act);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_se_gate_bwd(const float* dgate, const void* gate, const void* sp, const float* pre1, const void* w1, const void* w2,
@@ -426,25 +431,17 @@ extern "C" int b200_se_gate_bwd(const float* dgate, const void* gate, const void
   float* dz2 = scratch;
   float* h = scratch + (size_t)N * C;
   float* dz1 = h + (size_t)N * r;
-  const size_t smem = (size_t)kSeS * (C + r) * sizeof(float);
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    cudaError_t e = cudaFuncSetAttribute(se_gate_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    configured = smem;
-  }
-  se_gate_bwd_data_kernel<<<(N + kSeS - 1) / kSeS, 256, smem, s>>>(dgate, (const __nv_bfloat16*)gate, pre1, (const __nv_bfloat16*)w1,
-                                                                  (const __nv_bfloat16*)w2, dz2, h, dz1, ds, N, C, r, act);
+  const int gy = (N + kSeS - 1) / kSeS;
+  se_bwd_hidden_kernel<<<dim3((r + 7) / 8, gy), 256, 0, s>>>(dgate, (const __nv_bfloat16*)gate, pre1, (const __nv_bfloat16*)w2, h, dz1, N, C, r, act);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return (int)e;
-  const size_t smem2 = (size_t)2 * kSeNB * r * sizeof(float);
-  static size_t configured2 = 0;
-  if (smem2 > 48 * 1024 && smem2 > configured2) {
-    e = cudaFuncSetAttribute(se_gate_bwd_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
-    if (e != cudaSuccess) return (int)e;
-    configured2 = smem2;
-  }
-  se_gate_bwd_weights_kernel<<<(C + 31) / 32, 256, smem2, s>>>(dz2, h, dz1, (const __nv_bfloat16*)sp, dw1, db1, dw2, db2, N, C, r);
+  se_bwd_input_kernel<<<dim3((C + 255) / 256, gy), 256, (size_t)kSeS * r * sizeof(float), s>>>(dgate, (const __nv_bfloat16*)gate, dz1,
+                                                                                              (const __nv_bfloat16*)w1, dz2, ds, N, C, r);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return (int)e;
+  const int jw = std::min(r, 8 * kSeJ);
+  se_gate_bwd_weights_kernel<<<dim3((C + 31) / 32, (r + 8 * kSeJ - 1) / (8 * kSeJ)), 256, (size_t)2 * kSeNB * jw * sizeof(float), s>>>(
+      dz2, h, dz1, (const __nv_bfloat16*)sp, dw1, db1, dw2, db2, N, C, r);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_channel_add_bcast(void* dx, const float* ds, int N, int HW, int C, float scale, cudaStream_t s) {
