@@ -43,6 +43,8 @@ def parse_args():
                          "kernel (B200.INPUT_UINT8, the framework's real-data path); fp32 = host-normalised images (what the "
                          "reference's loader yields); both = uint8 is reported as e2e, fp32 as e2e_fp32_input")
     ap.add_argument("--exposed", action="store_true", help="(kept for compatibility) the multi-GPU attribution runs -- step without gradient exchange, step without SyncBN -- are now always done when N > 1")
+    ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
+                    help="CUDA-graph replay of the training step (B200.CUDA_GRAPH): auto = on for single-GPU runs")
     ap.add_argument("--attr-steps", type=int, default=10, help="steps of each multi-GPU attribution run (N > 1)")
     return ap.parse_args()
 
@@ -185,7 +187,9 @@ def run_ours(args):
     torch.manual_seed(1)
     net = models.build_model(args.arch, num_classes=1000).to(dev)
     sync_bn = (not args.no_syncbn)
-    eng = NativeEngine(net, dev, precision="bf16", comm=args.comm, bucket_cap_mb=cfg.B200.BUCKET_MB, sync_bn=sync_bn)
+    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    eng = NativeEngine(net, dev, precision="bf16", comm=args.comm, bucket_cap_mb=cfg.B200.BUCKET_MB, sync_bn=sync_bn,
+                       cuda_graph=use_graph)
     counter = _LaunchCounter(eng.K)
     eng.K = counter
     opt = eng.make_optimizer(lr=0.2, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
@@ -200,16 +204,19 @@ def run_ours(args):
     def step(i):
         eng.train_step(xs[i % nbuf], ys[i % nbuf], opt, 5)
 
-    for i in range(args.warmup):
+    # with graph replay the capture happens on step 4 (three eager steps first): keep it inside the untimed warm-up
+    for i in range(max(args.warmup, 6) if use_graph else args.warmup):
         step(i)
     torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)
     sampler.start()
     counter.count = 0
+    replays0 = eng.graph_replays
     if getattr(eng, "syncbn_wait_ns", None) is not None:
         eng.syncbn_wait_ns.zero_()
     sec = _timed(dev, step, args.steps)
-    launches = counter.count
+    # kernels launched by Python calls + kernels launched by graph replays (counted once, at capture)
+    launches = counter.count + (eng.graph_replays - replays0) * eng.graph_launches_per_step
     clocks = sampler.stop()
     value = world * B * args.steps / sec
 
@@ -296,6 +303,7 @@ def run_ours(args):
                "config": {"model": args.arch, "global_batch": world * B, "per_gpu_batch": B, "image": "3x224x224",
                           "parallelism": f"dp{world}", "syncbn": bool(sync_bn and world > 1), "comm": eng.comm_mode,
                           "optimizer": "nesterov-sgd fused into the gradient all-reduce",
+                          "cuda_graph": bool(eng.graph_replays > 0),
                           "l2": "inputs larger than L2 (154 MB fp32 per batch, alternating buffers)"},
                "clocks": clocks, "gpu_launches": launches, "gpu_launches_per_step": launches / max(args.steps, 1),
                "library_fallbacks": dict(eng.ops.fallbacks)}

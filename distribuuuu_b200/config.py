@@ -261,6 +261,11 @@ _C.B200.PROFILE = False
 # stop an epoch after this many iterations (0 = full epoch); used by tests/smoke
 _C.B200.MAX_ITERS = 0
 # failure detection (utils/health.py): process-group timeout, step watchdog, per-rank heartbeat files
+# capture the native engine's whole training step (forward + backward + fused update, ~330 launches for ResNet-50)
+# in a CUDA graph after a few eager steps and replay it; removes the per-step Python / launch overhead that bounds
+# the small-batch configs (batch 32-64 per GPU).  Single-GPU runs only for now: multi-GPU steps carry host-side
+# exchange epochs in their kernel arguments.
+_C.B200.CUDA_GRAPH = False
 _C.B200.DIST_TIMEOUT_MIN = 30
 _C.B200.WATCHDOG_S = 0          # 0 = off; else seconds without a finished iteration before stacks are dumped
 _C.B200.WATCHDOG_ABORT = False  # exit(3) when the watchdog fires so the launcher restarts the job (AUTO_RESUME)

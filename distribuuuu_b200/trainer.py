@@ -79,7 +79,7 @@ def build_engine(net: nn.Module, device: torch.device):
     if _select_engine(device) == "native":
         from .parallel.native_engine import NativeEngine
         return NativeEngine(net, device, precision=cfg.B200.PRECISION, comm=cfg.B200.COMM,
-                            bucket_cap_mb=cfg.B200.BUCKET_MB, sync_bn=cfg.MODEL.SYNCBN)
+                            bucket_cap_mb=cfg.B200.BUCKET_MB, sync_bn=cfg.MODEL.SYNCBN, cuda_graph=cfg.B200.CUDA_GRAPH)
     return TorchEngine(net, bucket_cap_mb=cfg.B200.BUCKET_MB)
 
 
