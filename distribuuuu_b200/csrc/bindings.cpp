@@ -189,7 +189,9 @@ TilePlan plan_tiles(int n_cols, int k_iters, long long m_tiles, int groups, int 
     if (stages >= 4 && nblk(bn) <= sms && m_tiles * nblk(bn) >= 2LL * sms) best = TilePlan{bn, 1, std::min(stages, 12), 1};
   }
   // streaming layers with a wide N tile: a CTA pair shares the weight tile (each CTA stages half of it)
-  if (!best.resident && best.bn >= 128 && m_tiles >= 2 && cta_pairs_enabled()) best.cg = 2;
+  // (measured, profiles/r2/conv_ablation: pays from 8 k-blocks per tile on -- 1024->512 @14^2 0.069 -> 0.062 ms, 3x3 layers
+  // 5-15 % -- and loses on the short-K wide-N layers such as 256->1024, which stay single-CTA)
+  if (!best.resident && best.bn >= 128 && m_tiles >= 2 && k_iters >= 8 && cta_pairs_enabled()) best.cg = 2;
   return best;
 }
 
