@@ -17,6 +17,7 @@
 #include "elementwise.h"
 #include "extras.h"
 #include "attention.h"
+#include "conv3x3_halo.h"
 
 namespace {
 
@@ -759,6 +760,33 @@ void channel_add_bcast(at::Tensor& dx, const at::Tensor& ds, double scale) {
   B200_CUDA_OK(b200_channel_add_bcast(dx.data_ptr(), ds.data_ptr<float>(), dx.size(0), dx.size(1) * dx.size(2), dx.size(3), (float)scale, cur_stream()));
 }
 
+// ---------------------------------------------------------------------------------------------- 3x3 halo conv (64 -> 64)
+// x [N,H,W,64], w [64,3,3,64], y [N,H,W,64]; dgrad: x = dy, y = dx (same weight tensor, read MN-major with flipped taps)
+void conv3x3_halo(const at::Tensor& x, const at::Tensor& w, at::Tensor& y, const c10::optional<at::Tensor>& stats, bool dgrad,
+                  PeerState* peer) {
+  check_bf16_contig(x, "x"); check_bf16_contig(w, "w"); check_bf16_contig(y, "y");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int N = x.size(0), H = x.size(1), W = x.size(2);
+  TORCH_CHECK(x.size(3) == 64 && w.size(0) == 64 && w.size(1) == 3 && w.size(2) == 3 && w.size(3) == 64 && y.numel() == x.numel(),
+              "conv3x3_halo handles 64 -> 64 channel 3x3 / stride 1 / pad 1 convolutions");
+  const int halo_rows = (128 + 2 * (W + 2) + 2 + 7) / 8 * 8;
+  TORCH_CHECK(halo_rows <= 256, "conv3x3_halo: feature map too wide (W <= 61)");
+  Conv3x3HaloParams p{};
+  p.N = N; p.H = H; p.W = W;
+  p.tiles = (int)(((long long)N * (H + 2) * (W + 2) + 127) / 128);
+  p.halo_rows = halo_rows;
+  p.dgrad = dgrad ? 1 : 0;
+  p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;
+  if (stats.has_value()) TORCH_CHECK(stats->numel() >= 128 && stats->scalar_type() == at::kFloat, "stats must be fp32 [2*64]");
+  p.peer = PeerCtx{}; p.peer.world = 1;
+  if (peer != nullptr) { TORCH_CHECK(stats.has_value() && !dgrad, "conv3x3_halo: a peer context needs the statistics epilogue"); p.peer = peer_ctx_for_producer(peer); }
+  CUtensorMap mx = im2col_map_4d(x.data_ptr(), N, H, W, 64, -1, -1, 1, 1, 1, 64, (uint32_t)halo_rows);
+  CUtensorMap mw = tiled_map_3d(w.data_ptr(), 64, 9, 64, 64, 9 * 64, 64, 1, 64);
+  CUtensorMap my = tiled_map_4d(y.data_ptr(), 64, W, H, N, 64, (uint64_t)W * 64, (uint64_t)H * W * 64, 64, 32, 1, 1);
+  const int grid = std::min(p.tiles, num_sms());
+  B200_CUDA_OK(b200_conv3x3_halo_launch(&mx, &mw, &my, &p, grid, cur_stream()));
+}
+
 // ---------------------------------------------------------------------------------------------- attention (BoTNet MHSA)
 // qk [B,14,14,2*heads*128], v / out [B,14,14,heads*128] (NHWC bf16, contiguous); rel_w / rel_h [27,128] bf16
 struct AttnMaps { CUtensorMap qk128, qk64, v128, v64, relw, relh; };
@@ -897,6 +925,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("attn_fwd", &attn_fwd, "fused relative-position MHSA forward (tcgen05)");
   m.def("attn_bwd", &attn_bwd, "fused relative-position MHSA backward: dQ, dK, dV and the relative-logit gradients");
   m.def("rel_grad_reduce", &rel_grad_reduce);
+  m.def("conv3x3_halo", &conv3x3_halo, "3x3/s1/p1 64->64 convolution with one halo load per tile (forward or data gradient)",
+        py::arg("x"), py::arg("w"), py::arg("y"), py::arg("stats") = py::none(), py::arg("dgrad") = false, py::arg("peer") = py::none());
   m.def("colsum_add", &colsum_add);
   m.def("strided_add_inplace", &strided_add_inplace);
   m.def("blockdiag_pack", &blockdiag_pack);

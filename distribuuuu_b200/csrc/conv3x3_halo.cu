@@ -1,0 +1,240 @@
+// 3x3 / stride 1 / pad 1 convolution with ONE activation load per tile (halo reuse), for the layers whose whole weight
+// tensor fits in shared memory (Cin = Cout = 64: ResNet-18/34/50 layer1) -- forward and data gradient.
+//
+// Why a second kernel: conv_gemm.cu feeds every filter tap with its own im2col TMA load, i.e. it pulls the activation
+// tile nine times from L2.  The B200's L2 -> SM fabric delivers ~7.5 TB/s in total (measured: profiles/r2), and the
+// 64 -> 64 @ 56^2 layer moves 9 x 16 KB per 128-pixel tile over it for only 1152 tensor-core cycles of work: it ran at
+// 163 us where the tensor cores need 27 us and HBM 31 us.  Here a tile is 128 consecutive positions of the PADDED raster
+// (rows of W + 2, images of H + 2 rows): the input of tap (r, s) for position p is padded position p + r (W + 2) + s, so
+// ONE im2col TMA load of 128 + 2 (W + 2) + 2 rows (zero fill supplies the padding) serves all nine taps, each as an
+// MMA whose A descriptor simply starts r (W + 2) + s rows further down.  tools/probes/umma_shift_probe.cu established
+// that tcgen05.mma accepts an A tile starting at any 128-byte row of a 128B-swizzled buffer (the swizzle is a function
+// of the absolute shared-memory address).  The 2 (W + 2) / (H + 2) garbage positions per row / image cost 7 % extra MMA
+// work at 56^2; the epilogue clips them (TMA stores are issued per image-row segment; BN statistics mask them).
+//
+// Replaces the cuDNN call of reference resnet.py:36-54 for this layer; VERDICT r1 "next round" item 1(c).
+#include "common.cuh"
+#include "conv3x3_halo.h"
+
+namespace b200 {
+
+namespace halo {
+constexpr int BM = 128, BN = 64, BK = 64;
+constexpr int kTapBytes = BN * BK * 2;          // 8 KB: one tap's [64 x 64] weight tile
+constexpr int kWBytes = 9 * kTapBytes;          // 72 KB resident weights
+constexpr int kStageBytes = 32 * 1024;          // halo stage (<= 256 rows of 128 B)
+constexpr int kStages = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;
+constexpr int kThreads = 64 + kEpiThreads;
+constexpr int kStagingBytes = 4 * 2 * 4096;     // one 32-row x 64-col chunk per lane quarter, double buffered
+// + 4 KB: a row-segment store reads a full 32-row box starting at its first row (the excess is clipped, but read)
+constexpr int kSmem = kWBytes + kStages * kStageBytes + kStagingBytes + 4096 + 1024 + 256;
+}  // namespace halo
+using namespace halo;
+
+__global__ void __launch_bounds__(kThreads, 1)
+conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_y, const __grid_constant__ Conv3x3HaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;
+  uint8_t* s_a = smem + kWBytes;
+  uint8_t* s_out = s_a + kStages * kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kStagingBytes + 4096);
+  uint64_t* full_bar = bars;                 // [kStages]
+  uint64_t* empty_bar = bars + kStages;      // [kStages]
+  uint64_t* tmem_full = bars + 2 * kStages;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;      // [2]
+  uint64_t* w_bar = tmem_empty + 2;          // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int Wp = p.W + 2, Hp = p.H + 2;
+  const int img = Hp * Wp;                                  // padded positions per image
+  const int halo_rows = p.halo_rows;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_y);
+    for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiWarps); }
+    mbar_init(smem_u32(w_bar), 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) { tmem_alloc(smem_u32(tmem_ptr), 2 * BN); tmem_relinquish(); }
+  tc_fence_before();
+  __syncwarp();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // =============================== TMA producer: resident weights once, then one halo tile per item
+    if (lane == 0) {
+      const uint32_t wb = smem_u32(w_bar);
+      mbar_expect_tx(wb, (uint32_t)kWBytes);
+      for (int t = 0; t < 9; ++t) tma_load_3d(smem_u32(s_w + t * kTapBytes), &map_w, wb, 0, t, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.tiles; item += gridDim.x) {
+        const int p0 = item * BM;                           // first padded position of the tile
+        const int n = p0 / img, rem = p0 - n * img;
+        const int hp = rem / Wp, wp = rem - hp * Wp;
+        mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
+        const uint32_t bar = smem_u32(&full_bar[stage]);
+        mbar_expect_tx(bar, (uint32_t)(halo_rows * 128));
+        // base pixel (w, h) = padded coordinate - 1 (the bounding box starts at -1); zero fill outside the image
+        tma_load_im2col_4d(smem_u32(s_a + stage * kStageBytes), &map_x, bar, 0, wp - 1, hp - 1, n, 0, 0);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================== MMA issuer: 9 taps x 4 K-steps per tile, A descriptor shifted by r * Wp + s rows
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      mbar_wait(smem_u32(w_bar), 0);
+      tc_fence_after();
+      const uint64_t a_hi = make_smem_desc_hi_sw128(16, 1024);
+      const uint64_t b_hi = p.dgrad ? make_smem_desc_hi_sw128(8192, 1024) : make_smem_desc_hi_sw128(16, 1024);
+      const uint32_t b_step = p.dgrad ? 128u : 2u;
+      const uint32_t idesc = make_idesc_bf16(BM, BN, 0, p.dgrad ? 1u : 0u);
+      for (int item = blockIdx.x; item < p.tiles; item += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
+        mbar_wait(smem_u32(&full_bar[stage]), phase);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t a_base = smem_u32(s_a + stage * kStageBytes);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+          for (int sx = 0; sx < 3; ++sx) {
+            const int tap = r * 3 + sx;
+            const int wtap = p.dgrad ? (8 - tap) : tap;     // data gradient: flipped filter
+            const uint64_t a_desc = a_hi | (uint64_t)(((a_base + (uint32_t)(r * Wp + sx) * 128u) >> 4) & 0x3fff);
+            const uint64_t b_desc = b_hi | (uint64_t)((smem_u32(s_w + wtap * kTapBytes) >> 4) & 0x3fff);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(b_step * k), idesc, (tap | k) ? 1u : 0u);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[stage]));
+        umma_commit(smem_u32(&tmem_full[acc]));
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================== epilogue: TMEM -> bf16 -> swizzled staging -> per-row-segment TMA stores (+ statistics)
+    const int quarter = warp & 3;                 // TMEM lanes [32 q, 32 q + 32)
+    const int half = (warp - 2) >> 2;             // the two warps of a quarter split the 64 columns
+    int acc = 0; uint32_t acc_phase = 0;
+    int buf = 0;
+    float st_sum[2] = {0.f, 0.f}, st_sq[2] = {0.f, 0.f};   // lane l: columns 2l, 2l+1 over this warp's 16 rows of every chunk
+    const bool want_stats = p.stats != nullptr;
+    const uint32_t pair_bar = 1 + quarter;
+    for (int item = blockIdx.x; item < p.tiles; item += gridDim.x) {
+      mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      tc_fence_after();
+      // this lane's row: padded position -> (n, hp, wp) and validity
+      const int pos = item * BM + quarter * 32 + lane;
+      const int n = pos / img, rem = pos - n * img;
+      const int hp = rem / Wp, wp = rem - hp * Wp;
+      const bool valid = (n < p.N) && (hp < p.H) && (wp < p.W);
+      const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      uint8_t* sbuf = s_out + quarter * 8192 + buf * 4096;
+      if (half == 0 && lane == 0) bulk_wait_group_read<1>();          // the stores that last read this buffer have drained
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 pk;
+          pk.x = pack_bf16x2(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
+          pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+          pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+          pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+          *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((half * 4 + g) ^ (lane & 7)) << 4)) = pk;
+        }
+      }
+      tc_fence_before();
+      fence_proxy_async_smem();
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // whole 32 x 64 chunk staged
+      if (half == 0 && lane == 0) {
+        // the 32 rows are consecutive padded positions: one store per image-row segment; the box is 32 positions wide and
+        // the tensor map clips everything at w >= W, which removes the garbage columns and the rows of the next segment
+        int done = 0;
+        int sn = n, sh = hp, sw = wp;                                   // lane 0 == first row of the chunk
+        while (done < 32 && sn < p.N) {
+          const int seg = min(32 - done, Wp - sw);
+          if (sh < p.H && sw < p.W) tma_store_4d(&map_y, smem_u32(sbuf + done * 128), 0, sw, sh, sn);
+          done += seg;
+          sw = 0;
+          if (++sh == Hp) { sh = 0; ++sn; }
+        }
+        bulk_commit_group();
+      }
+      if (want_stats) {
+        // column sums over the VALID rows: lane l owns columns 2l, 2l+1; the two warps of the quarter take 16 rows each
+        float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll 8
+        for (int r = half * 16; r < half * 16 + 16; ++r) {
+          const uint32_t wd = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
+          const bool ok = (vmask >> r) & 1u;
+          const float f0 = ok ? __uint_as_float(wd << 16) : 0.f;
+          const float f1 = ok ? __uint_as_float(wd & 0xffff0000u) : 0.f;
+          a0 += f0; q0 = fmaf(f0, f0, q0);
+          a1 += f1; q1 = fmaf(f1, f1, q1);
+        }
+        st_sum[0] += a0; st_sum[1] += a1; st_sq[0] += q0; st_sq[1] += q1;
+      }
+      buf ^= 1;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (want_stats) {
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        atomicAdd(p.stats + 2 * lane + h2, st_sum[h2]);
+        atomicAdd(p.stats + BN + 2 * lane + h2, st_sq[h2]);
+      }
+      if (p.peer.world > 1) __threadfence();
+    }
+    if (lane == 0) bulk_wait_group<0>();
+    __syncwarp();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 2 * BN);
+  // SyncBN: the last CTA out announces this layer's statistics exchange (see conv_gemm.cu)
+  if (p.peer.world > 1 && threadIdx.x == 0) {
+    const int done = atomicAdd(p.peer.ticket + 2, 1);
+    if (done == (int)gridDim.x - 1) {
+      p.peer.ticket[2] = 0;
+      __threadfence_system();
+      for (int r = 0; r < p.peer.world; ++r)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer.signal_pads[r] + p.peer.slot_base + p.peer.rank), "r"(p.peer.epoch) : "memory");
+    }
+  }
+}
+
+}  // namespace b200
+
+extern "C" int b200_conv3x3_halo_launch(const CUtensorMap* map_x, const CUtensorMap* map_w, const CUtensorMap* map_y,
+                                        const Conv3x3HaloParams* p, int grid, cudaStream_t stream) {
+  using namespace b200;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3x3_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem);
+    if (e != cudaSuccess) return (int)e;
+    configured = true;
+  }
+  conv3x3_halo_kernel<<<grid, kThreads, kSmem, stream>>>(*map_x, *map_w, *map_y, *p);
+  return (int)cudaGetLastError();
+}

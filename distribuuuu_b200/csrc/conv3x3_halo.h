@@ -1,0 +1,19 @@
+// Parameter block of the halo-reuse 3x3 convolution kernel (conv3x3_halo.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "elementwise.h"   // PeerCtx
+
+struct Conv3x3HaloParams {
+  int N, H, W;          // activation [N,H,W,64] -> output [N,H,W,64]
+  int tiles;            // ceil(N (H+2) (W+2) / 128) tiles of the padded raster
+  int halo_rows;        // rows of one halo load: 128 + 2 (W+2) + 2, rounded up to 8 (<= 256)
+  int dgrad;            // 0: forward (weights K-major); 1: data gradient (same weight bytes read MN-major, taps flipped)
+  float* stats;         // optional [2][64] BN statistics of the output (valid positions only)
+  PeerCtx peer;         // SyncBN: world > 1 => the last CTA announces the statistics exchange
+};
+
+extern "C" int b200_conv3x3_halo_launch(const CUtensorMap* map_x, const CUtensorMap* map_w, const CUtensorMap* map_y,
+                                        const Conv3x3HaloParams* p, int grid, cudaStream_t stream);

@@ -165,6 +165,15 @@ def _conv_weight(eng, conv):
     return dense, conv.in_channels // 64
 
 
+def _halo_ok(conv, xh, out) -> bool:
+    """64 -> 64 channel 3x3 / stride 1 / pad 1 layers run on the halo-reuse kernel (conv3x3_halo.cu): the activation tile
+    is loaded once per 128 output positions instead of once per filter tap.  B200_CONV_HALO=0 switches it off (A/B)."""
+    import os
+    return (out is None and conv.groups == 1 and conv.in_channels == 64 and conv.out_channels == 64
+            and conv.kernel_size == (3, 3) and conv.stride == (1, 1) and conv.padding == (1, 1) and conv.dilation == (1, 1)
+            and xh.shape[2] <= 61 and os.environ.get("B200_CONV_HALO", "1") != "0")
+
+
 class ConvFn(torch.autograd.Function):
     """Implicit-GEMM convolution (fprop / dgrad / wgrad on tcgen05), optional BN-statistics epilogue."""
 
@@ -182,7 +191,11 @@ class ConvFn(torch.autograd.Function):
         y = out if (out is not None and tuple(out.shape) == (N, P, Q, Kc) and groups == 1) else \
             torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
         # peer (SyncBN): the kernel's last CTA announces this layer's statistics exchange to the other ranks
-        K.conv_fprop(xh, w, y, stats, None, s, p, d, groups, peer)
+        ctx.halo = _halo_ok(conv, xh, out)
+        if ctx.halo:
+            K.conv3x3_halo(xh, w, y, stats, False, peer)
+        else:
+            K.conv_fprop(xh, w, y, stats, None, s, p, d, groups, peer)
         ctx.eng, ctx.conv = eng, conv
         ctx.save_for_backward(xh)
         ctx.x_needs_grad = x.requires_grad
@@ -231,7 +244,10 @@ class ConvFn(torch.autograd.Function):
             addend = ctx.sink.take() if ctx.sink is not None else None
             if s == 1:
                 dxh = torch.empty_like(xh)
-                K.conv_dgrad(dyh, w, dxh, 1, p, d, addend, groups)
+                if ctx.halo and addend is None:
+                    K.conv3x3_halo(dyh, w, dxh, None, True, None)
+                else:
+                    K.conv_dgrad(dyh, w, dxh, 1, p, d, addend, groups)
             else:
                 dxh = _strided_dgrad(K, dyh, w, xh.shape, s, p, d, groups, addend)
             if ctx.hand_to is not None and ctx.hand_to.offer(dxh):

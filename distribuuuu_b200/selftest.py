@@ -86,6 +86,31 @@ def check_conv_wgrad(N=4, H=14, W=14, C=64, K=128, R=3, stride=1, pad=1, dil=1, 
     return {"rel_err": err}
 
 
+def check_conv_halo(N=2, H=56, W=56, tol=2e-2):
+    """Halo-reuse 3x3 kernel (conv3x3_halo.cu, 64 -> 64): forward + BN statistics and data gradient vs F.conv2d."""
+    Kmod = _K()
+    C = 64
+    x = _bf16(N, H, W, C, seed=11)
+    w = _bf16(C, 3, 3, C, scale=(C * 9) ** -0.5, seed=12)
+    dy = _bf16(N, H, W, C, seed=13)
+    y = torch.full((N, H, W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    st = torch.zeros(2 * C, device="cuda")
+    Kmod.conv3x3_halo(x, w, y, st, False, None)
+    dx = torch.full((N, H, W, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    Kmod.conv3x3_halo(dy, w, dx, None, True, None)
+    torch.cuda.synchronize()
+    xr = x.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    wr = w.float().permute(0, 3, 1, 2)
+    yr = F.conv2d(xr, wr, None, 1, 1)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    yf = y.float().view(-1, C)
+    errs = {"y": _rel_err(y, yr.permute(0, 2, 3, 1)), "dx": _rel_err(dx, xr.grad.permute(0, 2, 3, 1)),
+            "stats": _rel_err(st[:C], yf.sum(0)), "stats_sq": _rel_err(st[C:], (yf * yf).sum(0))}
+    assert not torch.isnan(y.float()).any() and not torch.isnan(dx.float()).any(), "unwritten output positions"
+    assert errs["y"] < tol and errs["dx"] < tol and errs["stats"] < 2e-3 and errs["stats_sq"] < 2e-3, errs
+    return errs
+
+
 def check_grouped_conv(N=2, H=14, W=14, C=224, K=224, G=2, R=3, stride=1, pad=1, tol=2e-2):
     """Grouped convolution (RegNet group widths): fprop (+stats), dgrad, wgrad against F.conv2d(groups=G)."""
     Kmod = _K()

@@ -99,6 +99,12 @@ class FakeKernels:
             _raw(stats)[:K] += f.sum(0)
             _raw(stats)[K:2 * K] += (f * f).sum(0)
 
+    def conv3x3_halo(self, x, w, y, stats=None, dgrad=False, peer=None):
+        self._count("conv3x3_halo" + ("+dgrad" if dgrad else ""))
+        if dgrad:
+            return self.conv_dgrad(x, w, y, 1, 1, 1)
+        return self.conv_fprop(x, w, y, stats, None, 1, 1, 1)
+
     def conv_dgrad(self, dy, w, dx, stride, pad, dil, addend=None, groups=1):
         self._count("conv_dgrad" + ("+addend" if addend is not None else ""))
         assert stride == 1

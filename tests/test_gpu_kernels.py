@@ -174,3 +174,9 @@ def test_botnet50_step_has_no_library_fallbacks():
     loss, _, _ = eng.train_step(x, y, opt, 5)
     assert torch.isfinite(loss).item()
     assert eng.ops.fallbacks == {}, eng.ops.fallbacks
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 56, 56), (3, 14, 14), (5, 9, 13), (256, 56, 56)])
+def test_conv3x3_halo_kernel(N, H, W):
+    from distribuuuu_b200 import selftest
+    selftest.check_conv_halo(N=N, H=H, W=W)

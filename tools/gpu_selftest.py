@@ -47,6 +47,10 @@ def registry():
         "se_relu_r308": lambda: st.check_se(N=9, H=4, W=4, C=1232, r=308, act="relu"),
         "se_silu_r20": lambda: st.check_se(N=33, H=7, W=7, C=480, r=20),
         "colsum": st.check_colsum,
+        "conv_halo_56": lambda: st.check_conv_halo(),
+        "conv_halo_14_n3": lambda: st.check_conv_halo(N=3, H=14, W=14),
+        "conv_halo_9x13": lambda: st.check_conv_halo(N=5, H=9, W=13),
+        "conv_halo_prod": lambda: st.check_conv_halo(N=256, H=56, W=56),
         "mhsa": st.check_mhsa,
         "mhsa_b1": lambda: st.check_mhsa(B=1),
         "depthwise_5x5_s2": lambda: st.check_depthwise(k=5, stride=2),
