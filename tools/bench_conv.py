@@ -83,6 +83,9 @@ def main():
             r["dgrad_ours_ms"] = timeit(lambda: K.conv_dgrad(dy, w, dx, 1, pad, 1), a.iters, flush)
         else:   # stride 2: parity-class dgrad (compact stride-1 dgrads + one interleave pass)
             r["dgrad_ours_ms"] = timeit(lambda: K.conv_dgrad_s2(dy, w, dx, pad), a.iters, flush)
+        if cin == 64 and cout == 64 and k == 3 and s == 1:   # halo-reuse kernel (what the engine runs for this layer)
+            r["fprop_halo_ms"] = timeit(lambda: K.conv3x3_halo(x, w, y, st, False, None), a.iters, flush)
+            r["dgrad_halo_ms"] = timeit(lambda: K.conv3x3_halo(dy, w, dx, None, True, None), a.iters, flush)
         if not a.ours_only:
             r["fprop_cudnn_ms"] = timeit(lambda: F.conv2d(xc, wc, None, s, pad), a.iters, flush)
             r["wgrad_cudnn_ms"] = timeit(lambda: torch.ops.aten.convolution_backward(
