@@ -776,6 +776,7 @@ void conv3x3_halo(const at::Tensor& x, const at::Tensor& w, at::Tensor& y, const
   p.tiles = (int)(((long long)N * (H + 2) * (W + 2) + 127) / 128);
   p.halo_rows = halo_rows;
   p.dgrad = dgrad ? 1 : 0;
+  p.y = y.data_ptr();
   p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;
   if (stats.has_value()) TORCH_CHECK(stats->numel() >= 128 && stats->scalar_type() == at::kFloat, "stats must be fp32 [2*64]");
   p.peer = PeerCtx{}; p.peer.world = 1;

@@ -10,7 +10,8 @@
 // MMA whose A descriptor simply starts r (W + 2) + s rows further down.  tools/probes/umma_shift_probe.cu established
 // that tcgen05.mma accepts an A tile starting at any 128-byte row of a 128B-swizzled buffer (the swizzle is a function
 // of the absolute shared-memory address).  The 2 (W + 2) / (H + 2) garbage positions per row / image cost 7 % extra MMA
-// work at 56^2; the epilogue clips them (TMA stores are issued per image-row segment; BN statistics mask them).
+// work at 56^2; the epilogue drops them (rows are written from the staging tile with per-row predicates -- a TMA box
+// cannot express the variable-length image-row segments of a 32-position chunk -- and the BN statistics mask them).
 //
 // Replaces the cuDNN call of reference resnet.py:36-54 for this layer; VERDICT r1 "next round" item 1(c).
 #include "common.cuh"
@@ -28,8 +29,7 @@ constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
 constexpr int kStagingBytes = 4 * 2 * 4096;     // one 32-row x 64-col chunk per lane quarter, double buffered
-// + 4 KB: a row-segment store reads a full 32-row box starting at its first row (the excess is clipped, but read)
-constexpr int kSmem = kWBytes + kStages * kStageBytes + kStagingBytes + 4096 + 1024 + 256;
+constexpr int kSmem = kWBytes + kStages * kStageBytes + kStagingBytes + 1024 + 256;
 }  // namespace halo
 using namespace halo;
 
@@ -41,7 +41,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   uint8_t* s_w = smem;
   uint8_t* s_a = smem + kWBytes;
   uint8_t* s_out = s_a + kStages * kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kStagingBytes + 4096);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kStagingBytes);
   uint64_t* full_bar = bars;                 // [kStages]
   uint64_t* empty_bar = bars + kStages;      // [kStages]
   uint64_t* tmem_full = bars + 2 * kStages;  // [2]
@@ -55,7 +55,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   const int halo_rows = p.halo_rows;
 
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_y);
+    tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w);
     for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiWarps); }
     mbar_init(smem_u32(w_bar), 1);
@@ -143,9 +143,10 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const int hp = rem / Wp, wp = rem - hp * Wp;
       const bool valid = (n < p.N) && (hp < p.H) && (wp < p.W);
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+      // element offset of this row in y ([N,H,W,64]); -1 for garbage positions
+      const long long row_off = valid ? (((long long)n * p.H + hp) * p.W + wp) * BN : -1ll;
       uint8_t* sbuf = s_out + quarter * 8192 + buf * 4096;
-      if (half == 0 && lane == 0) bulk_wait_group_read<1>();          // the stores that last read this buffer have drained
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // both warps are done with this buffer's previous tile
       {
         uint32_t v[32];
         tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 32, v);
@@ -161,21 +162,14 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
       }
       tc_fence_before();
-      fence_proxy_async_smem();
       asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // whole 32 x 64 chunk staged
-      if (half == 0 && lane == 0) {
-        // the 32 rows are consecutive padded positions: one store per image-row segment; the box is 32 positions wide and
-        // the tensor map clips everything at w >= W, which removes the garbage columns and the rows of the next segment
-        int done = 0;
-        int sn = n, sh = hp, sw = wp;                                   // lane 0 == first row of the chunk
-        while (done < 32 && sn < p.N) {
-          const int seg = min(32 - done, Wp - sw);
-          if (sh < p.H && sw < p.W) tma_store_4d(&map_y, smem_u32(sbuf + done * 128), 0, sw, sh, sn);
-          done += seg;
-          sw = 0;
-          if (++sh == Hp) { sh = 0; ++sn; }
-        }
-        bulk_commit_group();
+      // each warp writes 16 of the 32 rows: 4 rows (4 x 128 B, fully coalesced) per instruction, garbage rows predicated off
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int r = half * 16 + it * 4 + (lane >> 3), g = lane & 7;
+        const long long off = __shfl_sync(0xffffffffu, row_off, r);
+        const uint4 v = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((g ^ (r & 7)) << 4));
+        if (off >= 0) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off + g * 8) = v;
       }
       if (want_stats) {
         // column sums over the VALID rows: lane l owns columns 2l, 2l+1; the two warps of the quarter take 16 rows each
@@ -204,8 +198,6 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       }
       if (p.peer.world > 1) __threadfence();
     }
-    if (lane == 0) bulk_wait_group<0>();
-    __syncwarp();
   }
 
   __syncwarp();

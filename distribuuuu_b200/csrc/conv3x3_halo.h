@@ -11,6 +11,7 @@ struct Conv3x3HaloParams {
   int tiles;            // ceil(N (H+2) (W+2) / 128) tiles of the padded raster
   int halo_rows;        // rows of one halo load: 128 + 2 (W+2) + 2, rounded up to 8 (<= 256)
   int dgrad;            // 0: forward (weights K-major); 1: data gradient (same weight bytes read MN-major, taps flipped)
+  void* y;              // output [N,H,W,64] bf16 (rows are written with per-row predicates; map_y is unused)
   float* stats;         // optional [2][64] BN statistics of the output (valid positions only)
   PeerCtx peer;         // SyncBN: world > 1 => the last CTA announces the statistics exchange
 };
