@@ -28,7 +28,7 @@ constexpr int kStages = 3;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = kEpiWarps * 32;
 constexpr int kThreads = 64 + kEpiThreads;
-constexpr int kStagingBytes = 4 * 2 * 4096;     // one 32-row x 64-col chunk per lane quarter, double buffered
+constexpr int kStagingBytes = kEpiWarps * 4096; // one private 32-row x 64-col tile per epilogue warp
 constexpr int kSmem = kWBytes + kStages * kStageBytes + kStagingBytes + 1024 + 256;
 }  // namespace halo
 using namespace halo;
@@ -57,7 +57,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_w);
     for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&full_bar[i]), 1); mbar_init(smem_u32(&empty_bar[i]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiWarps); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiWarps / 2); }
     mbar_init(smem_u32(w_bar), 1);
     fence_barrier_init();
   }
@@ -126,16 +126,22 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     }
     __syncwarp();
   } else {
-    // =============================== epilogue: TMEM -> bf16 -> swizzled staging -> per-row-segment TMA stores (+ statistics)
+    // =============================== epilogue: TMEM -> bf16 -> swizzled staging -> predicated row stores (+ statistics)
+    // Two groups of four warps take ALTERNATE tiles (group g <-> TMEM accumulator stage g), so two tiles are in the
+    // epilogue at any time: with one tile at a time the ~2k-cycle latency chain tcgen05.ld -> pack -> st.shared -> store ->
+    // statistics set the pace (ncu: 3.9k cycles per tile for 1152 cycles of MMA).  A warp owns 32 rows x 64 columns.
     const int quarter = warp & 3;                 // TMEM lanes [32 q, 32 q + 32)
-    const int half = (warp - 2) >> 2;             // the two warps of a quarter split the 64 columns
-    int acc = 0; uint32_t acc_phase = 0;
-    int buf = 0;
-    float st_sum[2] = {0.f, 0.f}, st_sq[2] = {0.f, 0.f};   // lane l: columns 2l, 2l+1 over this warp's 16 rows of every chunk
+    const int group = (warp - 2) >> 2;            // 0 / 1
+    const int acc = group;
+    uint32_t acc_phase = 0;
+    float st_sum[2] = {0.f, 0.f}, st_sq[2] = {0.f, 0.f};   // lane l: columns 2l, 2l+1
     const bool want_stats = p.stats != nullptr;
-    const uint32_t pair_bar = 1 + quarter;
-    for (int item = blockIdx.x; item < p.tiles; item += gridDim.x) {
+    uint8_t* sbuf = s_out + (warp - 2) * 4096;    // private 32-row x 128-byte staging tile
+    int local = 0;
+    for (int item = blockIdx.x; item < p.tiles; item += gridDim.x, ++local) {
+      if ((local & 1) != group) continue;
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
+      acc_phase ^= 1;
       tc_fence_after();
       // this lane's row: padded position -> (n, hp, wp) and validity
       const int pos = item * BM + quarter * 32 + lane;
@@ -143,13 +149,11 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const int hp = rem / Wp, wp = rem - hp * Wp;
       const bool valid = (n < p.N) && (hp < p.H) && (wp < p.W);
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-      // element offset of this row in y ([N,H,W,64]); -1 for garbage positions
-      const long long row_off = valid ? (((long long)n * p.H + hp) * p.W + wp) * BN : -1ll;
-      uint8_t* sbuf = s_out + quarter * 8192 + buf * 4096;
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // both warps are done with this buffer's previous tile
-      {
+      const long long row_off = valid ? (((long long)n * p.H + hp) * p.W + wp) * BN : -1ll;   // element offset in y
+#pragma unroll
+      for (int hlf = 0; hlf < 2; ++hlf) {
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + half * 32, v);
+        tmem_ld_32x32b_x32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * BN + hlf * 32, v);
         tmem_ld_wait();
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
@@ -158,24 +162,25 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
           pk.y = pack_bf16x2(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
           pk.z = pack_bf16x2(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
           pk.w = pack_bf16x2(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-          *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((half * 4 + g) ^ (lane & 7)) << 4)) = pk;
+          *reinterpret_cast<uint4*>(sbuf + lane * 128 + (((hlf * 4 + g) ^ (lane & 7)) << 4)) = pk;
         }
       }
+      // the accumulator stage is free as soon as every lane has its values in registers / shared memory
       tc_fence_before();
-      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");     // whole 32 x 64 chunk staged
-      // each warp writes 16 of the 32 rows: 4 rows (4 x 128 B, fully coalesced) per instruction, garbage rows predicated off
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
+      // 4 rows (4 x 128 B, fully coalesced) per instruction, garbage rows predicated off
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int r = half * 16 + it * 4 + (lane >> 3), g = lane & 7;
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), g = lane & 7;
         const long long off = __shfl_sync(0xffffffffu, row_off, r);
         const uint4 v = *reinterpret_cast<const uint4*>(sbuf + r * 128 + ((g ^ (r & 7)) << 4));
         if (off >= 0) *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.y) + off + g * 8) = v;
       }
       if (want_stats) {
-        // column sums over the VALID rows: lane l owns columns 2l, 2l+1; the two warps of the quarter take 16 rows each
         float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll 8
-        for (int r = half * 16; r < half * 16 + 16; ++r) {
+        for (int r = 0; r < 32; ++r) {
           const uint32_t wd = *reinterpret_cast<const uint32_t*>(sbuf + r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + ((lane & 3) << 2));
           const bool ok = (vmask >> r) & 1u;
           const float f0 = ok ? __uint_as_float(wd << 16) : 0.f;
@@ -185,10 +190,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         }
         st_sum[0] += a0; st_sum[1] += a1; st_sq[0] += q0; st_sq[1] += q1;
       }
-      buf ^= 1;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&tmem_empty[acc]));
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      __syncwarp();                               // the staging tile is rewritten by the next tile of this warp
     }
     if (want_stats) {
 #pragma unroll
