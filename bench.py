@@ -44,7 +44,7 @@ def parse_args():
                          "reference's loader yields); both = uint8 is reported as e2e, fp32 as e2e_fp32_input")
     ap.add_argument("--exposed", action="store_true", help="(kept for compatibility) the multi-GPU attribution runs -- step without gradient exchange, step without SyncBN -- are now always done when N > 1")
     ap.add_argument("--graph", default="auto", choices=["auto", "on", "off"],
-                    help="CUDA-graph replay of the training step (B200.CUDA_GRAPH): auto = on for single-GPU runs")
+                    help="CUDA-graph replay of the training step (B200.CUDA_GRAPH): auto = on")
     ap.add_argument("--attr-steps", type=int, default=10, help="steps of each multi-GPU attribution run (N > 1)")
     return ap.parse_args()
 
@@ -187,7 +187,7 @@ def run_ours(args):
     torch.manual_seed(1)
     net = models.build_model(args.arch, num_classes=1000).to(dev)
     sync_bn = (not args.no_syncbn)
-    use_graph = args.graph == "on" or (args.graph == "auto" and world == 1)
+    use_graph = args.graph in ("on", "auto")
     eng = NativeEngine(net, dev, precision="bf16", comm=args.comm, bucket_cap_mb=cfg.B200.BUCKET_MB, sync_bn=sync_bn,
                        cuda_graph=use_graph)
     counter = _LaunchCounter(eng.K)
@@ -205,7 +205,7 @@ def run_ours(args):
         eng.train_step(xs[i % nbuf], ys[i % nbuf], opt, 5)
 
     # with graph replay the capture happens on step 4 (three eager steps first): keep it inside the untimed warm-up
-    for i in range(max(args.warmup, 6) if use_graph else args.warmup):
+    for i in range(max(args.warmup, 8) if use_graph else args.warmup):
         step(i)
     torch.cuda.synchronize(dev)
     sampler = ClockSampler(local)

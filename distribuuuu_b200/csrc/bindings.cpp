@@ -510,7 +510,7 @@ void dw_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64_t
 struct PeerState {
   int world = 1, rank = 0, slot_base = 0;
   std::vector<int64_t> signal_pads, sym_bufs;
-  int64_t ticket = 0, mc_stats = 0, reduced = 0, ready = 0, wait_ns = 0;
+  int64_t ticket = 0, mc_stats = 0, reduced = 0, ready = 0, wait_ns = 0, epoch_dev = 0;
   uint32_t epoch = 0;
   // make(): context of the NEXT exchange (epoch + 1); current(): the exchange a producer kernel already announced
   PeerCtx current() { return make(false); }
@@ -523,7 +523,9 @@ struct PeerState {
         c.signal_pads[i] = reinterpret_cast<uint32_t*>(signal_pads[i]);
         c.sym_bufs[i] = reinterpret_cast<float*>(sym_bufs[i]);
       }
-      c.epoch = advance ? ++epoch : epoch;
+      c.epoch = advance ? ++epoch : epoch;       // informational only: the kernels use the device-side counter
+      TORCH_CHECK(epoch_dev != 0, "PeerState needs the device-side exchange counter (epoch_dev)");
+      c.epoch_dev = reinterpret_cast<uint32_t*>(epoch_dev);
     }
     c.ticket = reinterpret_cast<int*>(ticket);
     c.presignaled = 0;
@@ -873,7 +875,7 @@ void cast_bf16(const at::Tensor& src, at::Tensor& dst) {
 struct CommState {
   int world = 1, rank = 0, slot_base = 0;
   std::vector<int64_t> signal_pads, stage, w16;
-  int64_t mc_stage = 0, mc_w16 = 0, local_counter = 0, local_release = 0;
+  int64_t mc_stage = 0, mc_w16 = 0, local_counter = 0, local_release = 0, epoch_dev = 0;
   uint32_t epoch = 0;
   CommCtx make() const {
     CommCtx c{};
@@ -886,6 +888,8 @@ struct CommState {
     }
     c.mc_stage = reinterpret_cast<__nv_bfloat16*>(mc_stage);
     c.mc_w16 = reinterpret_cast<__nv_bfloat16*>(mc_w16);
+    TORCH_CHECK(epoch_dev != 0, "CommState needs the device-side barrier counter (epoch_dev)");
+    c.epoch_dev = reinterpret_cast<uint32_t*>(epoch_dev);
     c.local_counter = reinterpret_cast<int*>(local_counter);
     c.local_release = reinterpret_cast<uint32_t*>(local_release);
     return c;
@@ -944,6 +948,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("sym_bufs", &PeerState::sym_bufs).def_readwrite("ticket", &PeerState::ticket)
       .def_readwrite("mc_stats", &PeerState::mc_stats).def_readwrite("reduced", &PeerState::reduced)
       .def_readwrite("ready", &PeerState::ready).def_readwrite("wait_ns", &PeerState::wait_ns)
+      .def_readwrite("epoch_dev", &PeerState::epoch_dev)
       .def_readwrite("epoch", &PeerState::epoch);
   py::class_<CommState>(m, "CommState")
       .def(py::init<>())
@@ -952,6 +957,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
       .def_readwrite("stage", &CommState::stage).def_readwrite("w16", &CommState::w16)
       .def_readwrite("mc_stage", &CommState::mc_stage).def_readwrite("mc_w16", &CommState::mc_w16)
       .def_readwrite("local_counter", &CommState::local_counter).def_readwrite("local_release", &CommState::local_release)
+      .def_readwrite("epoch_dev", &CommState::epoch_dev)
       .def_readwrite("epoch", &CommState::epoch);
   m.def("dw_fprop", &dw_fprop, "depthwise conv forward (+BN statistics)");
   m.def("dw_dgrad", &dw_dgrad);

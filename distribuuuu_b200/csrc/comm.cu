@@ -146,6 +146,8 @@ __global__ void __launch_bounds__(256, 4) allreduce_sgd_kernel(AllreduceSgdParam
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long nthreads = (long long)gridDim.x * blockDim.x;
   const float scale = 1.f / c.world;
+  // every thread reads the barrier counter before the first barrier; thread 0 of CTA 0 advances it after the second one
+  const uint32_t epoch0 = *reinterpret_cast<volatile uint32_t*>(c.epoch_dev);
 
   // phase A: fp32 grad -> scaled bf16 staging (own symmetric buffer), zero the fp32 slots
   __nv_bfloat16* my_stage = c.stage[c.rank];
@@ -158,7 +160,7 @@ __global__ void __launch_bounds__(256, 4) allreduce_sgd_kernel(AllreduceSgdParam
     F8 z = {{0, 0, 0, 0, 0, 0, 0, 0}};
     st_f8(p.grad + e, z);
   }
-  rank_barrier(c, p.epoch + 1);
+  rank_barrier(c, epoch0 + 1);
 
   // phase B
   long long b0 = 0, b1 = p.n8;  // one-shot: whole bucket on every rank
@@ -217,10 +219,15 @@ __global__ void __launch_bounds__(256, 4) allreduce_sgd_kernel(AllreduceSgdParam
       }
     }
   }
-  rank_barrier(c, p.epoch + 2);
+  rank_barrier(c, epoch0 + 2);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(c.epoch_dev) = epoch0 + 2;
 }
 
-__global__ void rank_barrier_kernel(CommCtx c, uint32_t epoch) { rank_barrier(c, epoch); }
+__global__ void rank_barrier_kernel(CommCtx c, uint32_t /*unused*/) {
+  const uint32_t epoch0 = *reinterpret_cast<volatile uint32_t*>(c.epoch_dev);
+  rank_barrier(c, epoch0 + 1);
+  if (threadIdx.x == 0) *reinterpret_cast<volatile uint32_t*>(c.epoch_dev) = epoch0 + 1;
+}
 
 }  // namespace b200
 

@@ -19,6 +19,7 @@ struct CommCtx {
   __nv_bfloat16* w16[kCommMaxPeers];       // every rank's bf16 weight buffer
   __nv_bfloat16* mc_stage;                 // NVLS multicast alias of the staging buffers (nullptr: P2P loads)
   __nv_bfloat16* mc_w16;                   // NVLS multicast alias of the weight buffers   (nullptr: P2P stores)
+  uint32_t* epoch_dev;                     // device-resident barrier counter (graph-replayable: no per-launch epoch argument)
   int* local_counter;                      // grid barrier arrival counter (device-local)
   uint32_t* local_release;                 // grid barrier release flag (device-local)
 };
@@ -28,7 +29,7 @@ struct AllreduceSgdParams {
   float* master; float* mom; float* grad;  // flat fp32 buffers (device-local)
   long long off8, n8;                      // bucket offset / length in units of 8 elements
   SgdHyper hyper;
-  uint32_t epoch;                          // barriers use epoch+1 and epoch+2
+  uint32_t epoch;                          // (unused; the kernel reads comm.epoch_dev: its barriers are counter+1 and counter+2)
   int one_shot;
 };
 

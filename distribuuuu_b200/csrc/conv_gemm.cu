@@ -550,9 +550,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constan
     const int done = atomicAdd(p.peer.ticket + 2, 1);
     if (done == (int)gridDim.x - 1) {
       p.peer.ticket[2] = 0;
+      const uint32_t e = *reinterpret_cast<volatile uint32_t*>(p.peer.epoch_dev) + 1u;
+      *reinterpret_cast<volatile uint32_t*>(p.peer.epoch_dev) = e;
       __threadfence_system();
       for (int r = 0; r < p.peer.world; ++r)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer.signal_pads[r] + p.peer.slot_base + p.peer.rank), "r"(p.peer.epoch) : "memory");
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer.signal_pads[r] + p.peer.slot_base + p.peer.rank), "r"(e) : "memory");
     }
   }
 }

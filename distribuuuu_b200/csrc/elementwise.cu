@@ -94,8 +94,10 @@ __device__ void peer_signal_at_tail(const PeerCtx& pc, unsigned total_ctas) {
     const int done = atomicAdd(pc.ticket + 2, 1);
     if (done == (int)total_ctas - 1) {
       pc.ticket[2] = 0;
+      const uint32_t e = *reinterpret_cast<volatile uint32_t*>(pc.epoch_dev) + 1u;   // this exchange
+      *reinterpret_cast<volatile uint32_t*>(pc.epoch_dev) = e;                       // the consumer kernel reads it back
       __threadfence_system();
-      for (int r = 0; r < pc.world; ++r) st_release_sys(pc.signal_pads[r] + pc.slot_base + pc.rank, pc.epoch);
+      for (int r = 0; r < pc.world; ++r) st_release_sys(pc.signal_pads[r] + pc.slot_base + pc.rank, e);
     }
   }
 }
@@ -114,6 +116,9 @@ __device__ void peer_exchange_reduce(const PeerCtx& pc, long long sym_offset, in
   __shared__ int s_ticket;
   const int tid = threadIdx.y * blockDim.x + threadIdx.x;
   const int nthreads = blockDim.x * blockDim.y;
+  // exchange number: already advanced by the producer kernel's tail (presignaled), else this launch is exchange counter + 1
+  // and its last CTA advances the counter on the way out -- nobody writes it while CTAs of this launch may still read it
+  const uint32_t epoch = *reinterpret_cast<volatile uint32_t*>(pc.epoch_dev) + (pc.presignaled ? 0u : 1u);
   if (tid == 0) s_ticket = atomicAdd(pc.ticket, 1);
   __syncthreads();
   if (s_ticket == 0) {
@@ -122,13 +127,13 @@ __device__ void peer_exchange_reduce(const PeerCtx& pc, long long sym_offset, in
     if (tid < pc.world) {
       if (!pc.presignaled) {
         __threadfence_system();
-        st_release_sys(pc.signal_pads[tid] + pc.slot_base + pc.rank, pc.epoch);
+        st_release_sys(pc.signal_pads[tid] + pc.slot_base + pc.rank, epoch);
       }
       const uint32_t* flag = pc.signal_pads[pc.rank] + pc.slot_base + tid;
       long long t0 = clock64();
-      while ((int)(ld_acquire_sys(flag) - pc.epoch) < 0) {
+      while ((int)(ld_acquire_sys(flag) - epoch) < 0) {
         if (clock64() - t0 > B200_SPIN_LIMIT_CYCLES * 20) {
-          printf("b200: peer exchange timed out (rank %d waiting for %d, epoch %u)\n", pc.rank, tid, pc.epoch);
+          printf("b200: peer exchange timed out (rank %d waiting for %d, epoch %u)\n", pc.rank, tid, epoch);
           __trap();
         }
       }
@@ -154,13 +159,13 @@ __device__ void peer_exchange_reduce(const PeerCtx& pc, long long sym_offset, in
     __syncthreads();
     if (tid == 0) {
       __threadfence();
-      st_release_gpu(pc.ready, pc.epoch);
+      st_release_gpu(pc.ready, epoch);
       if (pc.wait_ns) atomicAdd(pc.wait_ns, global_timer_ns() - t_begin);
     }
   } else {
     if (tid == 0) {
       long long t0 = clock64();
-      while ((int)(ld_acquire_gpu(pc.ready) - pc.epoch) < 0) {
+      while ((int)(ld_acquire_gpu(pc.ready) - epoch) < 0) {
         if (clock64() - t0 > B200_SPIN_LIMIT_CYCLES * 24) { printf("b200: SyncBN local release timed out\n"); __trap(); }
       }
     }
@@ -169,7 +174,11 @@ __device__ void peer_exchange_reduce(const PeerCtx& pc, long long sym_offset, in
   // last CTA out resets the ticket for the next launch that uses it
   if (tid == 0) {
     int done = atomicAdd(pc.ticket + 1, 1);
-    if (done == (int)(gridDim.x * gridDim.y) - 1) { pc.ticket[0] = 0; pc.ticket[1] = 0; __threadfence(); }
+    if (done == (int)(gridDim.x * gridDim.y) - 1) {
+      pc.ticket[0] = 0; pc.ticket[1] = 0;
+      if (!pc.presignaled) *reinterpret_cast<volatile uint32_t*>(pc.epoch_dev) = epoch;
+      __threadfence();
+    }
   }
 }
 

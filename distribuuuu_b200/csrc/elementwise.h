@@ -13,7 +13,9 @@ constexpr int kMaxPeers = 8;
 struct PeerCtx {
   int world;                        // 1 => purely local
   int rank;
-  uint32_t epoch;                   // monotonically increasing exchange counter
+  uint32_t epoch;                   // (unused: kept for layout / debugging) host-side value of the exchange counter
+  uint32_t* epoch_dev;              // device-resident exchange counter: the kernels read / advance it themselves, so a
+                                    // captured CUDA graph of the step can be replayed (no per-step value in kernel arguments)
   int slot_base;                    // first signal-pad slot used by this exchange stream
   uint32_t* signal_pads[kMaxPeers]; // signal pad of every rank
   float* sym_bufs[kMaxPeers];       // statistics buffer of every rank

@@ -341,12 +341,17 @@ class NativeEngine(nn.Module):
             cs.mc_w16 = mc + layout["w16"] if mc else 0
             cs.local_counter = self._local_sync[0:].data_ptr()
             cs.local_release = self._local_sync[4:].data_ptr()
+            # exchange / barrier counters live on the device (kernels read and advance them), so that a captured CUDA
+            # graph of the step can be replayed: [0] SyncBN exchanges, [4] gradient all-reduce barriers
+            self._epochs = torch.zeros(8, dtype=torch.int32, device=dev)
+            cs.epoch_dev = self._epochs[4:].data_ptr()
             self.comm_state = cs
             ps = self.K.PeerState()
             ps.world, ps.rank, ps.slot_base = self.world, self.rank, 64   # flag slots 64.. belong to SyncBN
             ps.signal_pads = [p + layout["flags"] for p in ptrs]
             ps.sym_bufs = [p + layout["stats"] for p in ptrs]
             ps.ticket = self._local_sync[8:].data_ptr()
+            ps.epoch_dev = self._epochs[0:].data_ptr()
             # SyncBN: one designated CTA per BN launch reduces the layer's statistics over all ranks (in the switch
             # when the buffer has a multicast mapping) into `reduced` and releases `ready`; the rest read it locally
             max_c = max([m.num_features for m in self.bn_offsets] + [8])
@@ -527,7 +532,7 @@ class NativeEngine(nn.Module):
 
     def train_step(self, inputs, targets, optimizer, topk: int):
         assert optimizer is self.optimizer, "the native engine steps its own FusedSGD (utils.construct_optimizer)"
-        if self.cuda_graph and self.world == 1 and self.device.type == "cuda" and self.module.training:
+        if self.cuda_graph and self.device.type == "cuda" and self.module.training and self.comm_mode in ("local", "peer"):
             return self._graphed_step(inputs, targets, optimizer, topk)
         return self._eager_step(inputs, targets, optimizer, topk)
 
@@ -539,8 +544,15 @@ class NativeEngine(nn.Module):
         autograd nodes -- costs 8-9 ms of Python per step, which is the wall for the reference's own per-GPU batches of
         32-64.  After a few eager steps the step is captured once per (input shape, hyper-parameters) and replayed:
         inputs are copied into static buffers, outputs (loss, hit counts) are static tensors.  A new learning rate (once
-        per epoch) re-captures.  Everything the step does on the host besides launching kernels happens here."""
-        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), optimizer.hyper(), int(topk))
+        per epoch) re-captures.  Everything the step does on the host besides launching kernels happens here.
+
+        Multi-GPU steps are captured too -- the gradient-exchange kernels on the side stream join the capture through
+        the events that order them, and the SyncBN / all-reduce exchange counters live in device memory (the kernels
+        advance them), so nothing in the kernel arguments changes from step to step.  The statistics buffers alternate
+        between two halves from step to step (a peer may still be reading the previous step's sums), hence one graph per
+        parity."""
+        parity = self._step_parity ^ 1
+        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), optimizer.hyper(), int(topk), parity)
         entry = self._graphs.get(key)
         if entry is None:
             if self._eager_steps < self._GRAPH_WARMUP_STEPS or not optimizer.has_momentum_state:
@@ -551,12 +563,13 @@ class NativeEngine(nn.Module):
         sx.copy_(inputs, non_blocking=True)
         sy.copy_(targets, non_blocking=True)
         graph.replay()
+        self._step_parity = parity
         optimizer.steps += 1
         self.graph_replays += 1
         return outs
 
     def _capture(self, key, inputs, targets, optimizer, topk):
-        if len(self._graphs) >= 4:           # e.g. one per learning rate: keep the cache (and its memory pool) small
+        if len(self._graphs) >= 6:           # (two parities per input kind / learning rate) keep the cache small
             self._graphs.pop(next(iter(self._graphs)))
         sx, sy = torch.empty_like(inputs), torch.empty_like(targets)
         sx.copy_(inputs)
@@ -567,9 +580,11 @@ class NativeEngine(nn.Module):
             self._graph_pool = torch.cuda.graph_pool_handle()
         counter = getattr(self.K, "count", None)
         steps_before = optimizer.steps
+        parity_before = self._step_parity
         with torch.cuda.graph(graph, pool=self._graph_pool):
             loss, hits1, hitsk = self._eager_step(sx, sy, optimizer, topk)
         optimizer.steps = steps_before       # nothing ran during capture; replay() does the step
+        self._step_parity = parity_before
         if counter is not None:
             self.graph_launches_per_step = self.K.count - counter
         entry = (graph, sx, sy, (loss, hits1, hitsk))
