@@ -141,8 +141,17 @@ __device__ void peer_exchange_reduce(const PeerCtx& pc, long long sym_offset, in
     __syncthreads();
     const int nvec = C / 2;                        // float4 vectors in [2][C]
     if (pc.mc_stats != nullptr) {
-      for (int i = tid; i < nvec; i += nthreads)
-        reinterpret_cast<float4*>(pc.reduced)[i] = multimem_ld_reduce_f32x4(pc.mc_stats + sym_offset + 4 * (long long)i);
+      // up to four reductions in flight per thread: one NVLink round trip for C <= 2048 (a dependent loop paid one
+      // round trip per 256 vectors, i.e. four of them on the 2048-channel layers)
+      for (int i0 = tid; i0 < nvec; i0 += 4 * nthreads) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u * nthreads < nvec) v[u] = multimem_ld_reduce_f32x4(pc.mc_stats + sym_offset + 4 * (long long)(i0 + u * nthreads));
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u * nthreads < nvec) reinterpret_cast<float4*>(pc.reduced)[i0 + u * nthreads] = v[u];
+      }
     } else {
       for (int i = tid; i < nvec; i += nthreads) {
         float4 v[kMaxPeers];
