@@ -27,7 +27,7 @@ def test_peer_memory_paths(free_port, nproc):
         pytest.skip(f"needs {nproc} GPUs")
     r = _torchrun(nproc, free_port, "tools/multigpu_check.py")
     assert r.returncode == 0, (r.stdout[-3000:] + "\n" + r.stderr[-3000:])
-    for name in ("allreduce_sgd", "syncbn", "fp32_masters", "engine"):
+    for name in ("allreduce_sgd", "syncbn", "fp32_masters", "engine", "graph_replay"):
         assert f"PASS {name}" in r.stdout, r.stdout[-3000:]
 
 

@@ -8,6 +8,7 @@ Checks (each prints PASS/FAIL on rank 0 and the script exits non-zero on any fai
   2. peer-memory SyncBN forward/backward == BatchNorm over the concatenated global batch
   3. fp32 masters of BN gamma/beta/biases identical on every rank after several fused updates (no sync_masters)
   4. NativeEngine (peer comm, SyncBN) loss trajectory == TorchEngine (NCCL all_reduce, reference-semantics SyncBN)
+  5. the multi-GPU step replayed from a CUDA graph == the same step launched eagerly
 Results are also written to gpurun_out/multigpu_check.json.
 """
 import copy
@@ -32,12 +33,12 @@ def rel_err(a, b):
 _KEEP = []   # engines own symmetric-memory allocations; releasing them is left to process exit (every rank at once)
 
 
-def make_engine(arch, dev, sync_bn, num_classes=16):
+def make_engine(arch, dev, sync_bn, num_classes=16, cuda_graph=False):
     from distribuuuu_b200 import models
     from distribuuuu_b200.parallel.native_engine import NativeEngine
     torch.manual_seed(0)
     net = models.build_model(arch, num_classes=num_classes).to(dev)
-    eng = NativeEngine(net, dev, sync_bn=sync_bn)
+    eng = NativeEngine(net, dev, sync_bn=sync_bn, cuda_graph=cuda_graph)
     _KEEP.append((net, eng))
     return net, eng
 
@@ -219,6 +220,40 @@ def check_fp32_masters(dev, rank, world, steps=4):
             "syncbn_wait_ms_total": float(eng.syncbn_wait_ns.item()) / 1e6}
 
 
+def check_graph_replay(dev, rank, world, arch="resnet50", steps=9, batch=8, size=64):
+    """The multi-GPU training step captured in a CUDA graph (SyncBN exchanges + fused all-reduce on the side stream,
+    device-side exchange counters) must follow the eagerly launched step: same data, same initial weights, two engines."""
+    _, eager = make_engine(arch, dev, sync_bn=True)
+    _, graphed = make_engine(arch, dev, sync_bn=True, cuda_graph=True)
+    oa = eager.make_optimizer(lr=0.02, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    ob = graphed.make_optimizer(lr=0.02, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    eager.train(), graphed.train()
+    g = torch.Generator(device=dev).manual_seed(300 + rank)
+    losses = []
+    for i in range(steps):
+        x = torch.randn(batch, 3, size, size, device=dev, generator=g)
+        y = torch.randint(0, 16, (batch,), device=dev, generator=g)
+        la, _, _ = eager.train_step(x, y, oa, 5)
+        la = float(la)
+        torch.cuda.synchronize(dev)
+        lb, _, _ = graphed.train_step(x, y, ob, 5)
+        lb = float(lb)
+        torch.cuda.synchronize(dev)
+        losses.append((la, lb))
+        stage(f"graph: step {i} eager {la:.4f} graphed {lb:.4f} (replays so far {graphed.graph_replays})")
+    assert graphed.graph_replays >= steps - 5, f"the step was not replayed from a graph ({graphed.graph_replays} replays)"
+    rel = max(abs(a - b) / max(abs(a), 1e-3) for a, b in losses)
+    mine = graphed.flat_w16.float()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    same = float((mine - other).abs().max())
+    drift = rel_err(graphed.flat_w16.float(), eager.flat_w16.float())
+    assert rel < 0.03, f"graph replay diverges from eager launches {losses}"
+    assert same == 0.0, f"ranks disagree on weights after graph replays by {same}"
+    return {"losses": losses, "max_rel_loss_diff": rel, "replays": graphed.graph_replays, "rank_weight_diff": same,
+            "weights_vs_eager": drift}
+
+
 def main():
     import faulthandler
     from distribuuuu_b200 import utils
@@ -229,7 +264,7 @@ def main():
     dev = utils.resolve_device()
     results, failed = {}, False
     for name, fn in [("allreduce_sgd", check_allreduce_sgd), ("syncbn", check_syncbn), ("fp32_masters", check_fp32_masters),
-                     ("engine", check_engine)]:
+                     ("engine", check_engine), ("graph_replay", check_graph_replay)]:
         stage(f"{name}: start")
         try:
             results[name] = {"ok": True, "result": fn(dev, rank, world)}
