@@ -771,11 +771,16 @@ void conv3x3_halo(const at::Tensor& x, const at::Tensor& w, at::Tensor& y, const
   const int N = x.size(0), H = x.size(1), W = x.size(2);
   TORCH_CHECK(x.size(3) == 64 && w.size(0) == 64 && w.size(1) == 3 && w.size(2) == 3 && w.size(3) == 64 && y.numel() == x.numel(),
               "conv3x3_halo handles 64 -> 64 channel 3x3 / stride 1 / pad 1 convolutions");
-  const int halo_rows = (128 + 2 * (W + 2) + 2 + 7) / 8 * 8;
-  TORCH_CHECK(halo_rows <= 256, "conv3x3_halo: feature map too wide (W <= 61)");
+  const int Wp = W + 2;
+  TORCH_CHECK(Wp <= 64, "conv3x3_halo: feature map too wide (W <= 62)");
+  const int rpt = 128 / Wp;                 // image rows per tile
+  const int halo_rows = (rpt + 2) * Wp;     // <= 256 for Wp <= 64
+  TORCH_CHECK(halo_rows <= 256 && 2 * Wp + 2 + 128 <= halo_rows + 128, "conv3x3_halo geometry");
   Conv3x3HaloParams p{};
   p.N = N; p.H = H; p.W = W;
-  p.tiles = (int)(((long long)N * (H + 2) * (W + 2) + 127) / 128);
+  p.rpt = rpt;
+  p.tiles_per_img = (H + rpt - 1) / rpt;
+  p.tiles = N * p.tiles_per_img;
   p.halo_rows = halo_rows;
   p.dgrad = dgrad ? 1 : 0;
   p.y = y.data_ptr();
@@ -783,7 +788,7 @@ void conv3x3_halo(const at::Tensor& x, const at::Tensor& w, at::Tensor& y, const
   if (stats.has_value()) TORCH_CHECK(stats->numel() >= 128 && stats->scalar_type() == at::kFloat, "stats must be fp32 [2*64]");
   p.peer = PeerCtx{}; p.peer.world = 1;
   if (peer != nullptr) { TORCH_CHECK(stats.has_value() && !dgrad, "conv3x3_halo: a peer context needs the statistics epilogue"); p.peer = peer_ctx_for_producer(peer); }
-  CUtensorMap mx = im2col_map_4d(x.data_ptr(), N, H, W, 64, -1, -1, 1, 1, 1, 64, (uint32_t)halo_rows);
+  CUtensorMap mx = tiled_map_4d(x.data_ptr(), 64, W, H, N, 64, (uint64_t)W * 64, (uint64_t)H * W * 64, 64, (uint32_t)Wp, (uint32_t)(rpt + 2), 1);
   CUtensorMap mw = tiled_map_3d(w.data_ptr(), 64, 9, 64, 64, 9 * 64, 64, 1, 64);
   CUtensorMap my = tiled_map_4d(y.data_ptr(), 64, W, H, N, 64, (uint64_t)W * 64, (uint64_t)H * W * 64, 64, 32, 1, 1);
   const int grid = std::min(p.tiles, num_sms());

@@ -4,10 +4,12 @@
 // Why a second kernel: conv_gemm.cu feeds every filter tap with its own im2col TMA load, i.e. it pulls the activation
 // tile nine times from L2.  The B200's L2 -> SM fabric delivers ~7.5 TB/s in total (measured: profiles/r2), and the
 // 64 -> 64 @ 56^2 layer moves 9 x 16 KB per 128-pixel tile over it for only 1152 tensor-core cycles of work: it ran at
-// 163 us where the tensor cores need 27 us and HBM 31 us.  Here a tile is 128 consecutive positions of the PADDED raster
-// (rows of W + 2, images of H + 2 rows): the input of tap (r, s) for position p is padded position p + r (W + 2) + s, so
-// ONE im2col TMA load of 128 + 2 (W + 2) + 2 rows (zero fill supplies the padding) serves all nine taps, each as an
-// MMA whose A descriptor simply starts r (W + 2) + s rows further down.  tools/probes/umma_shift_probe.cu established
+// 163 us where the tensor cores need 27 us and HBM 31 us.  Here a tile is `rpt` = floor(128 / (W + 2)) full rows of the
+// PADDED raster (rows of W + 2 positions): the input of tap (r, s) for position p is padded position p + r (W + 2) + s, so
+// ONE TMA load of the (rpt + 2) x (W + 2) patch around the tile (a plain tiled box starting at column -1 / row h0 - 1:
+// out-of-bounds zero fill supplies the padding) serves all nine taps, each as an MMA whose A descriptor simply starts
+// r (W + 2) + s rows further down.  (A first version loaded the halo in im2col mode: 248 "pixels" per load ran at ~16
+// cycles per pixel inside the TMA unit -- 3.9k cycles per tile against 1152 of MMA; tiled boxes move whole rows.)  tools/probes/umma_shift_probe.cu established
 // that tcgen05.mma accepts an A tile starting at any 128-byte row of a 128B-swizzled buffer (the swizzle is a function
 // of the absolute shared-memory address).  The 2 (W + 2) / (H + 2) garbage positions per row / image cost 7 % extra MMA
 // work at 56^2; the epilogue drops them (rows are written from the staging tile with per-row predicates -- a TMA box
@@ -50,8 +52,7 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int Wp = p.W + 2, Hp = p.H + 2;
-  const int img = Hp * Wp;                                  // padded positions per image
+  const int Wp = p.W + 2;
   const int halo_rows = p.halo_rows;
 
   if (warp == 0 && lane == 0) {
@@ -76,14 +77,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       for (int t = 0; t < 9; ++t) tma_load_3d(smem_u32(s_w + t * kTapBytes), &map_w, wb, 0, t, 0);
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.tiles; item += gridDim.x) {
-        const int p0 = item * BM;                           // first padded position of the tile
-        const int n = p0 / img, rem = p0 - n * img;
-        const int hp = rem / Wp, wp = rem - hp * Wp;
+        const int n = item / p.tiles_per_img, h0 = (item - n * p.tiles_per_img) * p.rpt;   // first output row of the tile
         mbar_wait(smem_u32(&empty_bar[stage]), phase ^ 1);
         const uint32_t bar = smem_u32(&full_bar[stage]);
         mbar_expect_tx(bar, (uint32_t)(halo_rows * 128));
-        // base pixel (w, h) = padded coordinate - 1 (the bounding box starts at -1); zero fill outside the image
-        tma_load_im2col_4d(smem_u32(s_a + stage * kStageBytes), &map_x, bar, 0, wp - 1, hp - 1, n, 0, 0);
+        // box = (64 channels, W + 2 columns from -1, rpt + 2 rows from h0 - 1, one image); zero fill outside the image
+        tma_load_4d(smem_u32(s_a + stage * kStageBytes), &map_x, bar, 0, -1, h0 - 1, n);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
     }
@@ -143,11 +142,12 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       mbar_wait(smem_u32(&tmem_full[acc]), acc_phase);
       acc_phase ^= 1;
       tc_fence_after();
-      // this lane's row: padded position -> (n, hp, wp) and validity
-      const int pos = item * BM + quarter * 32 + lane;
-      const int n = pos / img, rem = pos - n * img;
-      const int hp = rem / Wp, wp = rem - hp * Wp;
-      const bool valid = (n < p.N) && (hp < p.H) && (wp < p.W);
+      // this lane's row of the tile: position m -> (row hr of the tile, column wp) and validity
+      const int n = item / p.tiles_per_img, h0 = (item - n * p.tiles_per_img) * p.rpt;
+      const int m = quarter * 32 + lane;
+      const int hr = m / Wp, wp = m - hr * Wp;
+      const int hp = h0 + hr;
+      const bool valid = (hr < p.rpt) && (hp < p.H) && (wp < p.W);
       const unsigned vmask = __ballot_sync(0xffffffffu, valid);
       const long long row_off = valid ? (((long long)n * p.H + hp) * p.W + wp) * BN : -1ll;   // element offset in y
 #pragma unroll

@@ -8,8 +8,10 @@
 
 struct Conv3x3HaloParams {
   int N, H, W;          // activation [N,H,W,64] -> output [N,H,W,64]
-  int tiles;            // ceil(N (H+2) (W+2) / 128) tiles of the padded raster
-  int halo_rows;        // rows of one halo load: 128 + 2 (W+2) + 2, rounded up to 8 (<= 256)
+  int rpt;              // image rows per tile = floor(128 / (W+2)): a tile is `rpt` full padded rows (<= 128 positions)
+  int tiles_per_img;    // ceil(H / rpt)
+  int tiles;            // N * tiles_per_img
+  int halo_rows;        // padded positions of one halo load: (rpt + 2) (W+2)  (<= 256)
   int dgrad;            // 0: forward (weights K-major); 1: data gradient (same weight bytes read MN-major, taps flipped)
   void* y;              // output [N,H,W,64] bf16 (rows are written with per-row predicates; map_y is unused)
   float* stats;         // optional [2][64] BN statistics of the output (valid positions only)

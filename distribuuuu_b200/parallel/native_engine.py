@@ -552,7 +552,8 @@ class NativeEngine(nn.Module):
         between two halves from step to step (a peer may still be reading the previous step's sums), hence one graph per
         parity."""
         parity = self._step_parity ^ 1
-        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), optimizer.hyper(), int(topk), parity)
+        key = (tuple(inputs.shape), inputs.dtype, tuple(targets.shape), optimizer.hyper(), int(topk), parity,
+               bool(self.sync_bn), bool(self.debug_skip_comm))
         entry = self._graphs.get(key)
         if entry is None:
             if self._eager_steps < self._GRAPH_WARMUP_STEPS or not optimizer.has_momentum_state:

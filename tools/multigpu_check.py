@@ -220,14 +220,16 @@ def check_fp32_masters(dev, rank, world, steps=4):
             "syncbn_wait_ms_total": float(eng.syncbn_wait_ns.item()) / 1e6}
 
 
-def check_graph_replay(dev, rank, world, arch="resnet50", steps=9, batch=8, size=64):
+def check_graph_replay(dev, rank, world, arch="resnet18", steps=10, batch=16, size=64):
     """The multi-GPU training step captured in a CUDA graph (SyncBN exchanges + fused all-reduce on the side stream,
     device-side exchange counters) must follow the eagerly launched step: same data, same initial weights, two engines."""
     _, eager = make_engine(arch, dev, sync_bn=True)
+    _, eager2 = make_engine(arch, dev, sync_bn=True)          # a second eager engine measures the run-to-run noise
     _, graphed = make_engine(arch, dev, sync_bn=True, cuda_graph=True)
-    oa = eager.make_optimizer(lr=0.02, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
-    ob = graphed.make_optimizer(lr=0.02, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
-    eager.train(), graphed.train()
+    hp = dict(lr=0.005, momentum=0.9, dampening=0.0, weight_decay=5e-5, nesterov=True)
+    oa, oc, ob = eager.make_optimizer(**hp), eager2.make_optimizer(**hp), graphed.make_optimizer(**hp)
+    eager.train(), eager2.train(), graphed.train()
+    noise = 0.0
     g = torch.Generator(device=dev).manual_seed(300 + rank)
     losses = []
     for i in range(steps):
@@ -235,6 +237,9 @@ def check_graph_replay(dev, rank, world, arch="resnet50", steps=9, batch=8, size
         y = torch.randint(0, 16, (batch,), device=dev, generator=g)
         la, _, _ = eager.train_step(x, y, oa, 5)
         la = float(la)
+        torch.cuda.synchronize(dev)
+        lc, _, _ = eager2.train_step(x, y, oc, 5)
+        noise = max(noise, abs(float(lc) - la) / max(abs(la), 1e-3))
         torch.cuda.synchronize(dev)
         lb, _, _ = graphed.train_step(x, y, ob, 5)
         lb = float(lb)
@@ -248,9 +253,9 @@ def check_graph_replay(dev, rank, world, arch="resnet50", steps=9, batch=8, size
     dist.broadcast(other, src=0)
     same = float((mine - other).abs().max())
     drift = rel_err(graphed.flat_w16.float(), eager.flat_w16.float())
-    assert rel < 0.03, f"graph replay diverges from eager launches {losses}"
+    assert rel < max(0.02, 3 * noise), f"graph replay diverges from eager launches (eager-vs-eager noise {noise}) {losses}"
     assert same == 0.0, f"ranks disagree on weights after graph replays by {same}"
-    return {"losses": losses, "max_rel_loss_diff": rel, "replays": graphed.graph_replays, "rank_weight_diff": same,
+    return {"losses": losses, "max_rel_loss_diff": rel, "eager_vs_eager_noise": noise, "replays": graphed.graph_replays, "rank_weight_diff": same,
             "weights_vs_eager": drift}
 
 
