@@ -98,24 +98,27 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       const uint64_t b_hi = p.dgrad ? make_smem_desc_hi_sw128(8192, 1024) : make_smem_desc_hi_sw128(16, 1024);
       const uint32_t b_step = p.dgrad ? 128u : 2u;
       const uint32_t idesc = make_idesc_bf16(BM, BN, 0, p.dgrad ? 1u : 0u);
+      // Per-tap descriptor parts are loop invariants: with N = 64 an MMA is only 32 tensor-core cycles, so the single
+      // issuing thread -- not the tensor pipe -- sets the pace of this kernel; keep its per-MMA work to one 64-bit add.
+      uint64_t a_off[9], b_desc[9];               // A: start-address advance in 16-byte units (rows are 128 B)
+#pragma unroll
+      for (int t = 0; t < 9; ++t) {
+        a_off[t] = (uint64_t)(((t / 3) * Wp + (t % 3)) * 8);
+        const int wtap = p.dgrad ? (8 - t) : t;   // data gradient: flipped filter
+        b_desc[t] = b_hi | (uint64_t)((smem_u32(s_w + wtap * kTapBytes) >> 4) & 0x3fff);
+      }
       for (int item = blockIdx.x; item < p.tiles; item += gridDim.x) {
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
         mbar_wait(smem_u32(&full_bar[stage]), phase);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
-        const uint32_t a_base = smem_u32(s_a + stage * kStageBytes);
+        const uint64_t a0 = a_hi | (uint64_t)((smem_u32(s_a + stage * kStageBytes) >> 4) & 0x3fff);
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
+        for (int t = 0; t < 9; ++t) {
+          const uint64_t a_desc = a0 + a_off[t];
 #pragma unroll
-          for (int sx = 0; sx < 3; ++sx) {
-            const int tap = r * 3 + sx;
-            const int wtap = p.dgrad ? (8 - tap) : tap;     // data gradient: flipped filter
-            const uint64_t a_desc = a_hi | (uint64_t)(((a_base + (uint32_t)(r * Wp + sx) * 128u) >> 4) & 0x3fff);
-            const uint64_t b_desc = b_hi | (uint64_t)((smem_u32(s_w + wtap * kTapBytes) >> 4) & 0x3fff);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_d, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(b_step * k), idesc, (tap | k) ? 1u : 0u);
-          }
+          for (int k = 0; k < BK / 16; ++k)
+            umma_bf16(tmem_d, a_desc + (uint64_t)(2 * k), b_desc[t] + (uint64_t)(b_step * k), idesc, (t | k) ? 1u : 0u);
         }
         umma_commit(smem_u32(&empty_bar[stage]));
         umma_commit(smem_u32(&tmem_full[acc]));
