@@ -237,8 +237,6 @@ class ConvFn(torch.autograd.Function):
         # SyncBN on several GPUs: the weight gradient is launched BETWEEN the two passes of the preceding layer's BN
         # backward (BnActFn.backward), where it hides that layer's cross-rank exchange; otherwise right here
         defer = eng.defer_wgrad and ctx.x_needs_grad
-        if not defer:
-            wgrad()
         dx = None
         if ctx.x_needs_grad:
             addend = ctx.sink.take() if ctx.sink is not None else None
@@ -256,6 +254,8 @@ class ConvFn(torch.autograd.Function):
                 dx = _nchw_view(dxh)
         if defer:
             eng.defer(wgrad)
+        else:
+            wgrad()            # after the dgrad: mark_ready may launch the bucket update that rewrites these weights
         return dx, None, None, None, None, None, None, None
 
 
