@@ -17,8 +17,8 @@
 
 namespace b200 {
 
-__device__ __forceinline__ void st_release_sys_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_sys_u32(uint32_t* p, uint32_t v) {   // ordered by the fence before it
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ uint32_t ld_acquire_sys_u32(const uint32_t* p) {
   uint32_t v;
@@ -56,7 +56,8 @@ __device__ void rank_barrier(const CommCtx& c, uint32_t epoch) {
     if (arrived == (int)gridDim.x - 1) {
       *c.local_counter = 0;
       if (c.world > 1) {
-        for (int r = 0; r < c.world; ++r) st_release_sys_u32(c.signal_pads[r] + c.slot_base + c.rank, epoch);
+        __threadfence_system();   // the other CTAs' writes (seen through the counter) before the flags; then relaxed
+        for (int r = 0; r < c.world; ++r) st_relaxed_sys_u32(c.signal_pads[r] + c.slot_base + c.rank, epoch);  // stores pipeline
         for (int r = 0; r < c.world; ++r) {
           const uint32_t* flag = c.signal_pads[c.rank] + c.slot_base + r;
           long long t0 = clock64();

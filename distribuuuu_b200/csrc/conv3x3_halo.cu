@@ -216,9 +216,9 @@ conv3x3_halo_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
       p.peer.ticket[2] = 0;
       const uint32_t e = *reinterpret_cast<volatile uint32_t*>(p.peer.epoch_dev) + 1u;
       *reinterpret_cast<volatile uint32_t*>(p.peer.epoch_dev) = e;
-      __threadfence_system();
+      __threadfence_system();   // ONE fence, then relaxed flag stores: a st.release per peer serialises `world` NVLink round trips
       for (int r = 0; r < p.peer.world; ++r)
-        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer.signal_pads[r] + p.peer.slot_base + p.peer.rank), "r"(e) : "memory");
+        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p.peer.signal_pads[r] + p.peer.slot_base + p.peer.rank), "r"(e) : "memory");
     }
   }
 }

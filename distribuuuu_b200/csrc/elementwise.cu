@@ -54,6 +54,11 @@ __device__ __forceinline__ void ld8f(const float* p, float (&f)[8]) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// flag store AFTER an explicit __threadfence_system(): one thread raising `world` flags with st.release pays one NVLink
+// round trip per peer (each release waits for the previous remote store); relaxed stores behind one fence pipeline
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -97,7 +102,7 @@ __device__ void peer_signal_at_tail(const PeerCtx& pc, unsigned total_ctas) {
       const uint32_t e = *reinterpret_cast<volatile uint32_t*>(pc.epoch_dev) + 1u;   // this exchange
       *reinterpret_cast<volatile uint32_t*>(pc.epoch_dev) = e;                       // the consumer kernel reads it back
       __threadfence_system();
-      for (int r = 0; r < pc.world; ++r) st_release_sys(pc.signal_pads[r] + pc.slot_base + pc.rank, e);
+      for (int r = 0; r < pc.world; ++r) st_relaxed_sys(pc.signal_pads[r] + pc.slot_base + pc.rank, e);
     }
   }
 }
