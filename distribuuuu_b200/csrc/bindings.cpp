@@ -612,6 +612,63 @@ void bn_backward(const at::Tensor& y, const at::Tensor& dout, const c10::optiona
   }
 }
 
+// Stem tail (elementwise.h: BnPoolParams): y [N,H,W,C] -> BN -> ReLU -> max-pool 3x3/2/1 -> out [N,H/2,W/2,C] in one pass.
+static void bn_pool_geometry(BnPoolParams& p, const at::Tensor& y, const at::Tensor& pooled, const at::Tensor* arg) {
+  check_bf16_contig(y, "y"); check_bf16_contig(pooled, "pooled");
+  TORCH_CHECK(y.dim() == 4 && pooled.dim() == 4, "bn_relu_pool: NHWC tensors");
+  p.N = y.size(0); p.H = y.size(1); p.W = y.size(2); p.C = y.size(3);
+  p.P = pooled.size(1); p.Q = pooled.size(2);
+  TORCH_CHECK(p.H % 2 == 0 && p.W % 2 == 0 && p.C % 8 == 0 && p.P == p.H / 2 && p.Q == p.W / 2 && pooled.size(0) == p.N && pooled.size(3) == p.C,
+              "bn_relu_pool: even H/W, C % 8 == 0, pooled = [N, H/2, W/2, C]");
+  TORCH_CHECK(y.numel() < (1ll << 31), "bn_relu_pool: 32-bit pixel indices");
+  if (arg) TORCH_CHECK(arg->scalar_type() == at::kByte && arg->is_contiguous() && arg->numel() == pooled.numel(), "arg: uint8, pooled shape");
+}
+void bn_relu_pool_fwd(const at::Tensor& y, at::Tensor& out, c10::optional<at::Tensor> arg, const at::Tensor& stats, int64_t sym_offset,
+                      const c10::optional<at::Tensor>& gamma, const c10::optional<at::Tensor>& beta,
+                      c10::optional<at::Tensor> running_mean, c10::optional<at::Tensor> running_var, at::Tensor& save_mean,
+                      at::Tensor& save_invstd, double count, double eps, double momentum, bool training, PeerState* peer,
+                      bool presignaled) {
+  c10::cuda::CUDAGuard guard(y.device());
+  BnPoolParams p{};
+  bn_pool_geometry(p, y, out, arg.has_value() ? &*arg : nullptr);
+  p.y = bptr(y); p.out = bptr_mut(out); p.arg = arg.has_value() ? arg->data_ptr<uint8_t>() : nullptr;
+  p.stats = stats.data_ptr<float>(); p.sym_offset = sym_offset;
+  p.gamma = fptr(gamma); p.beta = fptr(beta);
+  p.running_mean = fptr_mut(running_mean); p.running_var = fptr_mut(running_var);
+  TORCH_CHECK(training || (p.running_mean && p.running_var), "bn_relu_pool_fwd: eval mode needs running statistics");
+  p.save_mean = save_mean.data_ptr<float>(); p.save_invstd = save_invstd.data_ptr<float>();
+  p.count = (float)count; p.eps = (float)eps; p.momentum = (float)momentum; p.training = training;
+  if (peer && training) { p.peer = presignaled ? peer->current() : peer->make(); p.peer.presignaled = presignaled ? 1 : 0; }
+  else { p.peer = PeerCtx{}; p.peer.world = 1; }
+  B200_CUDA_OK(b200_bn_relu_pool_fwd(&p, cur_stream()));
+}
+// phase: 1 = reduce pass (opens the SyncBN exchange at its tail), 2 = apply pass, 3 = both
+void bn_relu_pool_bwd(const at::Tensor& y, const at::Tensor& dout, const at::Tensor& arg, at::Tensor& dy, at::Tensor& sums,
+                      int64_t sym_offset, const c10::optional<at::Tensor>& gamma, const at::Tensor& save_mean,
+                      const at::Tensor& save_invstd, c10::optional<at::Tensor> dgamma, c10::optional<at::Tensor> dbeta,
+                      double count, PeerState* peer, int64_t phase) {
+  c10::cuda::CUDAGuard guard(y.device());
+  BnPoolParams p{};
+  bn_pool_geometry(p, y, dout, &arg);
+  check_bf16_contig(dy, "dy");
+  TORCH_CHECK(dy.numel() == y.numel(), "bn_relu_pool_bwd: dy has the shape of y");
+  p.y = bptr(y); p.dout = bptr(dout); p.arg = const_cast<uint8_t*>(arg.data_ptr<uint8_t>()); p.dy = bptr_mut(dy);
+  p.stats = sums.data_ptr<float>(); p.sym_offset = sym_offset;
+  p.gamma = fptr(gamma);
+  p.save_mean = save_mean.data_ptr<float>(); p.save_invstd = save_invstd.data_ptr<float>();
+  p.dgamma = fptr_mut(dgamma); p.dbeta = fptr_mut(dbeta);
+  p.count = (float)count; p.training = 1;
+  p.peer = PeerCtx{}; p.peer.world = 1;
+  if (phase & 1) {
+    if (peer) p.peer = peer->make();
+    B200_CUDA_OK(b200_bn_relu_pool_bwd_reduce(&p, cur_stream()));
+  }
+  if (phase & 2) {
+    if (peer) { p.peer = peer->current(); p.peer.presignaled = 1; }
+    B200_CUDA_OK(b200_bn_relu_pool_bwd_apply(&p, cur_stream()));
+  }
+}
+
 void maxpool_fwd(const at::Tensor& x, at::Tensor& out, c10::optional<at::Tensor> argmax, int64_t k, int64_t stride, int64_t pad) {
   check_bf16_contig(x, "x"); check_bf16_contig(out, "out");
   c10::cuda::CUDAGuard guard(x.device());
@@ -975,6 +1032,12 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("bn_backward", &bn_backward, py::arg("y"), py::arg("dout"), py::arg("residual"), py::arg("dy"), py::arg("dresidual"), py::arg("sums"),
         py::arg("sym_offset"), py::arg("gamma"), py::arg("beta"), py::arg("save_mean"), py::arg("save_invstd"), py::arg("dgamma"), py::arg("dbeta"),
         py::arg("count"), py::arg("act"), py::arg("peer"), py::arg("relu_mask") = py::none(), py::arg("phase") = 3);
+  m.def("bn_relu_pool_fwd", &bn_relu_pool_fwd, py::arg("y"), py::arg("out"), py::arg("arg"), py::arg("stats"), py::arg("sym_offset"),
+        py::arg("gamma"), py::arg("beta"), py::arg("running_mean"), py::arg("running_var"), py::arg("save_mean"), py::arg("save_invstd"),
+        py::arg("count"), py::arg("eps"), py::arg("momentum"), py::arg("training"), py::arg("peer") = py::none(), py::arg("presignaled") = false);
+  m.def("bn_relu_pool_bwd", &bn_relu_pool_bwd, py::arg("y"), py::arg("dout"), py::arg("arg"), py::arg("dy"), py::arg("sums"), py::arg("sym_offset"),
+        py::arg("gamma"), py::arg("save_mean"), py::arg("save_invstd"), py::arg("dgamma"), py::arg("dbeta"), py::arg("count"),
+        py::arg("peer") = py::none(), py::arg("phase") = 3);
   m.def("maxpool_fwd", &maxpool_fwd);
   m.def("maxpool_bwd", &maxpool_bwd);
   m.def("gap_fwd", &gap_fwd);

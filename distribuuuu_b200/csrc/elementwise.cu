@@ -22,6 +22,12 @@ __device__ __forceinline__ uint4 ldg_stream(const __nv_bfloat16* p) {
   asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
   return r;
 }
+// raw 16-byte load through L1 (neighbouring threads re-read the same lines: overlapping pooling windows)
+__device__ __forceinline__ uint4 ldg_cached(const __nv_bfloat16* p) {
+  uint4 r;
+  asm volatile("ld.global.nc.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
 __device__ __forceinline__ void unpack8f(const uint4& u, float (&f)[8]) {
   const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
@@ -684,6 +690,271 @@ __global__ void __launch_bounds__(256) maxpool_bwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Stem tail: BN + ReLU + max-pool 3x3 / 2 / pad 1 fused (BnPoolParams, elementwise.h).
+//   forward   out[p,q] = max(0, max over the window of (y * scale + shift)); arg = first tap that holds it, 9 = none > 0.
+//             One read of the conv output, one write of the pooled map: the normalised 112x112 map is never stored.
+//   backward  every thread owns a 2x2 block of y: exactly the four windows (bp+{0,1}, bq+{0,1}) reach it, through nine
+//             (window, element) pairs known at compile time -- dz is rebuilt from the pooled gradient and `arg` with one
+//             16-byte + one 8-byte load per window, no atomics and no scatter.  Pass 1 accumulates sum(dz), sum(dz*xhat)
+//             (and opens the SyncBN exchange at its tail), pass 2 writes dy.
+// grid: (channel-vector groups, pixel chunks); block: (cvx, 256 / cvx) as the other BN kernels.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(BnPoolParams p) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  const bool active = c0 < p.C;
+  if (p.peer.world > 1 && p.training) peer_exchange_reduce(p.peer, p.sym_offset, p.C);
+  if (!active) return;
+  float scale[8], shift[8];
+  {
+    float g[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = 1.f; b[i] = 0.f; }
+    if (p.gamma) ld8f(p.gamma + c0, g);
+    if (p.beta) ld8f(p.beta + c0, b);
+    if (p.training) {
+      float s0[8], s1[8];
+      gather_stats(p.peer, p.stats, p.sym_offset, p.C, c0, s0, s1);
+      const float inv_n = 1.f / p.count;
+      const bool writer = (blockIdx.y == 0 && threadIdx.y == 0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mean = s0[i] * inv_n;
+        const float var = fmaxf(s1[i] * inv_n - mean * mean, 0.f);
+        const float invstd = rsqrtf(var + p.eps);
+        scale[i] = g[i] * invstd;
+        shift[i] = b[i] - mean * scale[i];
+        if (writer) {
+          p.save_mean[c0 + i] = mean;
+          p.save_invstd[c0 + i] = invstd;
+          if (p.running_mean) {
+            const float unbiased = var * (p.count / fmaxf(p.count - 1.f, 1.f));
+            p.running_mean[c0 + i] = (1.f - p.momentum) * p.running_mean[c0 + i] + p.momentum * mean;
+            p.running_var[c0 + i] = (1.f - p.momentum) * p.running_var[c0 + i] + p.momentum * unbiased;
+          }
+        }
+      }
+    } else {
+      float rm[8], rv[8];
+      ld8f(p.running_mean + c0, rm);
+      ld8f(p.running_var + c0, rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        scale[i] = g[i] * rsqrtf(rv[i] + p.eps);
+        shift[i] = b[i] - rm[i] * scale[i];
+      }
+    }
+  }
+  const int total = p.N * p.P * p.Q;
+  const int pstride = gridDim.y * blockDim.y;
+  for (int px = blockIdx.y * blockDim.y + threadIdx.y; px < total; px += pstride) {
+    const int q = px % p.Q, t = px / p.Q;
+    const int ph = t % p.P, n = t / p.P;
+    const int h0 = 2 * ph - 1, w0 = 2 * q - 1;
+    const __nv_bfloat16* base = p.y + (long long)n * p.H * p.W * p.C + c0;
+    uint4 raw[9];
+    bool ok[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const int h = h0 + r, w = w0 + s2;
+        ok[r * 3 + s2] = (h >= 0 && h < p.H && w >= 0 && w < p.W);
+        raw[r * 3 + s2] = make_uint4(0u, 0u, 0u, 0u);
+        if (ok[r * 3 + s2]) raw[r * 3 + s2] = ldg_cached(base + (long long)(h * p.W + w) * p.C);
+      }
+    }
+    float best[8];
+    uint32_t arg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { best[i] = 0.f; arg[i] = 9u; }   // ReLU floor: only a positive tap can win
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      if (!ok[tap]) continue;
+      float v[8];
+      unpack8f(raw[tap], v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float z = fmaf(v[i], scale[i], shift[i]);
+        if (z > best[i]) { best[i] = z; arg[i] = (uint32_t)tap; }
+      }
+    }
+    const long long o = (long long)px * p.C + c0;
+    store8(p.out + o, best);
+    if (p.arg) {
+      uint2 packed;
+      packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+      packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+      *reinterpret_cast<uint2*>(p.arg + o) = packed;
+    }
+  }
+}
+
+// dz of the 2x2 block (rows 2bp, 2bp+1; columns 2bq, 2bq+1) of image n, channels c0..c0+7: d[br * 2 + bc][i]
+__device__ __forceinline__ void pool_bwd_block(const BnPoolParams& p, int n, int bp, int bq, int c0, float (&d)[4][8]) {
+#pragma unroll
+  for (int e = 0; e < 4; ++e)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d[e][i] = 0.f;
+#pragma unroll
+  for (int dp = 0; dp < 2; ++dp) {
+#pragma unroll
+    for (int dq = 0; dq < 2; ++dq) {
+      const int ph = bp + dp, q = bq + dq;
+      if (ph >= p.P || q >= p.Q) continue;
+      const long long o = (((long long)n * p.P + ph) * p.Q + q) * p.C + c0;
+      const uint2 a = *reinterpret_cast<const uint2*>(p.arg + o);
+      float g[8];
+      load8(p.dout + o, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int tap = (int)(((i < 4 ? a.x : a.y) >> (8 * (i & 3))) & 0xffu);
+        // window row ph covers input rows 2ph-1+r: dp=0 -> r=1 is block row 0, r=2 is block row 1; dp=1 -> r=0 is block row 1
+#pragma unroll
+        for (int br = 0; br < 2; ++br) {
+          const int r = (dp == 0) ? br + 1 : (br == 1 ? 0 : -1);
+          if (r < 0) continue;
+#pragma unroll
+          for (int bc = 0; bc < 2; ++bc) {
+            const int s2 = (dq == 0) ? bc + 1 : (bc == 1 ? 0 : -1);
+            if (s2 < 0) continue;
+            if (tap == r * 3 + s2) d[br * 2 + bc][i] += g[i];
+          }
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_relu_pool_bwd_reduce_kernel(BnPoolParams p) {
+  extern __shared__ __align__(16) float dyn[];   // [16][256] for the CTA-level reduction
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
+  if (c0 < p.C) {
+    float invstd[8], nmi[8];
+    {
+      float mean[8];
+      ld8f(p.save_mean + c0, mean);
+      ld8f(p.save_invstd + c0, invstd);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) nmi[i] = -mean[i] * invstd[i];
+    }
+    const int BP = p.H / 2, BQ = p.W / 2;
+    const int total = p.N * BP * BQ;
+    const int pstride = gridDim.y * blockDim.y;
+    for (int bx = blockIdx.y * blockDim.y + threadIdx.y; bx < total; bx += pstride) {
+      const int bq = bx % BQ, t = bx / BQ;
+      const int bp = t % BP, n = t / BP;
+      const __nv_bfloat16* yb = p.y + (((long long)n * p.H + 2 * bp) * p.W + 2 * bq) * p.C + c0;
+      uint4 raw[4];
+      raw[0] = ldg_stream(yb);
+      raw[1] = ldg_stream(yb + p.C);
+      raw[2] = ldg_stream(yb + (long long)p.W * p.C);
+      raw[3] = ldg_stream(yb + (long long)p.W * p.C + p.C);
+      float d[4][8];
+      pool_bwd_block(p, n, bp, bq, c0, d);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float y[8];
+        unpack8f(raw[e], y);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          a[i] += d[e][i];
+          b[i] = fmaf(d[e][i], fmaf(y[i], invstd[i], nmi[i]), b[i]);
+        }
+      }
+    }
+  }
+  // CTA-level reduction over threadIdx.y, then one vector RED per 4 channels (same scheme as bn_bwd_reduce_kernel)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { dyn[i * kBnThreads + tid] = a[i]; dyn[(8 + i) * kBnThreads + tid] = b[i]; }
+  __syncthreads();
+  const int bdx = blockDim.x, bdy = blockDim.y;
+  if (tid < 4 * bdx) {
+    const int quad = tid / bdx, tx = tid - quad * bdx;
+    const int c = (blockIdx.x * bdx + tx) * VEC;
+    if (c < p.C) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      const float* src = dyn + (quad * 4) * kBnThreads + tx;
+      for (int yy = 0; yy < bdy; ++yy) {
+        s0 += src[yy * bdx];
+        s1 += src[kBnThreads + yy * bdx];
+        s2 += src[2 * kBnThreads + yy * bdx];
+        s3 += src[3 * kBnThreads + yy * bdx];
+      }
+      red_add_v4(p.stats + (quad >= 2 ? p.C : 0) + c + (quad & 1) * 4, s0, s1, s2, s3);
+    }
+  }
+  if (p.peer.world > 1) peer_signal_at_tail(p.peer, gridDim.x * gridDim.y);
+}
+
+__global__ void __launch_bounds__(256) bn_relu_pool_bwd_apply_kernel(BnPoolParams p) {
+  const int cv = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c0 = cv * VEC;
+  const bool active = c0 < p.C;
+  if (p.peer.world > 1) peer_exchange_reduce(p.peer, p.sym_offset, p.C);
+  if (!active) return;
+  // dy = (dz - mean(dz) - xhat * mean(dz * xhat)) * gamma * invstd  ==  dz * scale + y * ca + cb
+  float scale[8], ca[8], cb[8];
+  {
+    float s0[8], s1[8];
+    gather_stats(p.peer, p.stats, p.sym_offset, p.C, c0, s0, s1);
+    const float inv_n = 1.f / p.count;
+    float mean[8], invstd[8], g[8];
+    ld8f(p.save_mean + c0, mean);
+    ld8f(p.save_invstd + c0, invstd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 1.f;
+    if (p.gamma) ld8f(p.gamma + c0, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float m_dz = s0[i] * inv_n, m_dzx = s1[i] * inv_n;
+      scale[i] = g[i] * invstd[i];
+      ca[i] = -invstd[i] * m_dzx * scale[i];
+      cb[i] = -m_dz * scale[i] - mean[i] * ca[i];
+    }
+    if (blockIdx.y == 0 && threadIdx.y == 0 && p.dgamma) {
+      // parameter gradients use the LOCAL sums (the gradient all-reduce averages them afterwards, as DDP does)
+      float lg[8], lb[8], dg[8], db[8];
+      ld8f(p.stats + p.C + c0, lg);
+      ld8f(p.stats + c0, lb);
+      ld8f(p.dgamma + c0, dg);
+      ld8f(p.dbeta + c0, db);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { p.dgamma[c0 + i] = dg[i] + lg[i]; p.dbeta[c0 + i] = db[i] + lb[i]; }
+    }
+  }
+  const int BP = p.H / 2, BQ = p.W / 2;
+  const int total = p.N * BP * BQ;
+  const int pstride = gridDim.y * blockDim.y;
+  for (int bx = blockIdx.y * blockDim.y + threadIdx.y; bx < total; bx += pstride) {
+    const int bq = bx % BQ, t = bx / BQ;
+    const int bp = t % BP, n = t / BP;
+    const long long e0 = (((long long)n * p.H + 2 * bp) * p.W + 2 * bq) * p.C + c0;
+    const long long rowp = (long long)p.W * p.C;
+    uint4 raw[4];
+    raw[0] = ldg_stream(p.y + e0);
+    raw[1] = ldg_stream(p.y + e0 + p.C);
+    raw[2] = ldg_stream(p.y + e0 + rowp);
+    raw[3] = ldg_stream(p.y + e0 + rowp + p.C);
+    float d[4][8];
+    pool_bwd_block(p, n, bp, bq, c0, d);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float y[8], o[8];
+      unpack8f(raw[e], y);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = fmaf(d[e][i], scale[i], fmaf(y[i], ca[i], cb[i]));
+      store8(p.dy + e0 + (e >> 1) * rowp + (e & 1) * p.C, o);
+    }
+  }
+}
+
 // Global average pool [N][HW][C] -> [N][C] and its backward (broadcast / HW).
 // CTA = (32 channel vectors) x (8 pixel lanes) of ONE sample: the pixel loop is split over threadIdx.y (4 loads in flight
 // per thread) and reduced through shared memory.  The first version had one thread walk all HW pixels of a channel
@@ -1098,6 +1369,24 @@ extern "C" int b200_bn_bwd_apply(const BnBwdParams* p, cudaStream_t s) {
   dim3 g, b;
   bn_launch_dims(p->C, p->rows, g, b);
   k.apply<<<g, b, k.smem, s>>>(*p);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_bn_relu_pool_fwd(const BnPoolParams* p, cudaStream_t s) {
+  dim3 g, b;
+  bn_launch_dims(p->C, (long long)p->N * p->P * p->Q, g, b, 8);
+  bn_relu_pool_fwd_kernel<<<g, b, 0, s>>>(*p);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_bn_relu_pool_bwd_reduce(const BnPoolParams* p, cudaStream_t s) {
+  dim3 g, b;
+  bn_launch_dims(p->C, (long long)p->N * (p->H / 2) * (p->W / 2), g, b, 4);
+  bn_relu_pool_bwd_reduce_kernel<<<g, b, 16 * kBnThreads * sizeof(float), s>>>(*p);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_bn_relu_pool_bwd_apply(const BnPoolParams* p, cudaStream_t s) {
+  dim3 g, b;
+  bn_launch_dims(p->C, (long long)p->N * (p->H / 2) * (p->W / 2), g, b, 8);
+  bn_relu_pool_bwd_apply_kernel<<<g, b, 0, s>>>(*p);
   return (int)cudaGetLastError();
 }
 // 32-bit index arithmetic is safe when the element count plus one grid stride cannot wrap

@@ -66,11 +66,36 @@ struct BnBwdParams {
   PeerCtx peer;
 };
 
+// Stem tail: BN (batch statistics from the conv epilogue) + ReLU + 3x3 / stride-2 / pad-1 max-pool in ONE pass over the
+// conv output, and its two-pass backward straight from the pooled gradient: the normalised 112x112 activation and its
+// gradient (411 MB each at batch 256) are never materialised.  H and W even, C % 8 == 0.
+struct BnPoolParams {
+  const __nv_bfloat16* y;      // conv output [N][H][W][C], contiguous
+  __nv_bfloat16* out;          // fwd: pooled activations [N][P][Q][C]
+  const __nv_bfloat16* dout;   // bwd: gradient of the pooled activations
+  uint8_t* arg;                // [N][P][Q][C]: window tap (0..8) that holds the maximum, 9 = no positive tap (ReLU-dead);
+                               // written by fwd (optional), read by bwd
+  __nv_bfloat16* dy;           // bwd: gradient wrt the conv output
+  int N, H, W, C, P, Q;
+  float* stats;                // fwd: local [2][C] sum / sumsq;  bwd: local [2][C] sum(dz), sum(dz*xhat)
+  long long sym_offset;
+  const float* gamma; const float* beta;
+  float* running_mean; float* running_var;
+  float* save_mean; float* save_invstd;
+  float* dgamma; float* dbeta;
+  float count, eps, momentum;
+  int training;
+  PeerCtx peer;
+};
+
 extern "C" {
 int b200_bn_apply(const BnApplyParams* p, cudaStream_t s);
 int b200_bn_stats(const void* y, long long rows, int C, long long ldy, float* stats, cudaStream_t s);
 int b200_bn_bwd_reduce(const BnBwdParams* p, cudaStream_t s);
 int b200_bn_bwd_apply(const BnBwdParams* p, cudaStream_t s);
+int b200_bn_relu_pool_fwd(const BnPoolParams* p, cudaStream_t s);
+int b200_bn_relu_pool_bwd_reduce(const BnPoolParams* p, cudaStream_t s);
+int b200_bn_relu_pool_bwd_apply(const BnPoolParams* p, cudaStream_t s);
 int b200_maxpool_fwd(const void* x, void* out, void* argmax, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, cudaStream_t s);
 int b200_maxpool_bwd(const void* dout, const void* argmax, void* dx, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, cudaStream_t s);
 int b200_gap_fwd(const void* x, void* out, int N, int HW, int C, cudaStream_t s);

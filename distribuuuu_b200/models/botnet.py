@@ -140,8 +140,7 @@ class BoTNet(nn.Sequential):
     9 flatten, 10 fc -- the same positions the reference's ``nn.Sequential`` produces."""
 
     def forward(self, x):
-        x = Fn.conv_bn_act(x, self[0], self[1], "relu")
-        x = Fn.max_pool2d(x, 3, 2, 1)
+        x = Fn.conv_bn_relu_maxpool(x, self[0], self[1], 3, 2, 1)
         x = self[4](x)
         x = self[5](x)
         x = self[6](x)

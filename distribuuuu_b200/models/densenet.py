@@ -101,8 +101,7 @@ class _Features(nn.Module):
     """Holds conv0/norm0/.../norm5 under the torchvision names and runs them in order."""
 
     def forward(self, x):
-        x = Fn.conv_bn_act(x, self.conv0, self.norm0, "relu")
-        x = Fn.max_pool2d(x, 3, 2, 1)
+        x = Fn.conv_bn_relu_maxpool(x, self.conv0, self.norm0, 3, 2, 1)
         for name, mod in self.named_children():
             if name.startswith(("denseblock", "transition")):
                 x = mod(x)

@@ -160,8 +160,7 @@ class ResNet(nn.Module):
         return nn.Sequential(*stage)
 
     def forward_stem(self, x):
-        x = Fn.conv_bn_act(x, self.conv1, self.bn1, "relu")
-        return Fn.max_pool2d(x, 3, 2, 1)
+        return Fn.conv_bn_relu_maxpool(x, self.conv1, self.bn1, 3, 2, 1)
 
     def forward_features(self, x):
         x = self.forward_stem(x)

@@ -52,6 +52,16 @@ def conv_bn_act(x, conv: nn.Conv2d, bn: nn.Module | None, act: str | None = None
     return _act(y, act)
 
 
+def conv_bn_relu_maxpool(x, conv: nn.Conv2d, bn: nn.Module, kernel_size: int = 3, stride: int = 2, padding: int = 1):
+    """The classifier stem ``maxpool(relu(bn(conv(x))))`` (reference models/resnet.py:194-197, densenet.py, botnet.py).
+    The native engine normalises, rectifies and pools in one pass over the conv output and back-propagates straight from
+    the pooled gradient, so the full-resolution activation is never stored."""
+    eng = runtime.active_engine()
+    if eng is not None:
+        return eng.ops.conv_bn_relu_maxpool(x, conv, bn, kernel_size, stride, padding)
+    return F.max_pool2d(F.relu(bn(conv(x)), inplace=True), kernel_size, stride, padding)
+
+
 def bn_act(x, bn: nn.Module, act: str | None = None):
     """Pre-activation normalisation (DenseNet ordering: BN -> ReLU -> conv)."""
     eng = runtime.active_engine()

@@ -453,6 +453,58 @@ class BnActFn(torch.autograd.Function):
         return _nchw_view(dy), (_nchw_view(dres) if dres is not None else None), None, None, None, None, None, None, None
 
 
+class BnReluPoolFn(torch.autograd.Function):
+    """Stem tail ``maxpool3x3/2(relu(BN(y)))`` in one pass over the conv output, backward in two passes straight from the
+    pooled gradient (csrc/elementwise.cu: bn_relu_pool_*): the normalised full-resolution map and its gradient -- 411 MB
+    each for ResNet-50 at batch 256 -- are never written.  Reference: models/resnet.py:194-197 (three modules)."""
+
+    @staticmethod
+    def forward(ctx, y, eng, bn, stats_slot, training, anchor):
+        K = eng.K
+        yh = _nhwc(y)
+        N, H, W, C = yh.shape
+        out = torch.empty((N, H // 2, W // 2, C), dtype=torch.bfloat16, device=y.device)
+        arg = torch.empty((N, H // 2, W // 2, C), dtype=torch.uint8, device=y.device) if (training and y.requires_grad) else None
+        save = torch.empty((2, C), dtype=torch.float32, device=y.device)
+        peer = eng.peer_state if (training and eng.sync_bn) else None
+        count = float(N * H * W * (eng.world if peer is not None else 1))
+        presignaled = bool(peer is not None and stats_slot is not None and stats_slot.presignaled)
+        K.bn_relu_pool_fwd(yh, out, arg, stats_slot.tensor if stats_slot is not None else save,
+                           stats_slot.sym_offset if stats_slot is not None else 0,
+                           eng.master_view(bn.weight) if bn.affine else None, eng.master_view(bn.bias) if bn.affine else None,
+                           bn.running_mean, bn.running_var, save[0], save[1], count, bn.eps,
+                           bn.momentum if bn.momentum is not None else 0.1, training, peer, presignaled)
+        if stats_slot is not None:
+            stats_slot.presignaled = False
+        if training and bn.track_running_stats:
+            eng.note_bn_step(bn)
+        ctx.eng, ctx.bn, ctx.count = eng, bn, count
+        ctx.save_for_backward(yh, arg, save)
+        return _nchw_view(out)
+
+    @staticmethod
+    def backward(ctx, dout):
+        eng, bn = ctx.eng, ctx.bn
+        K = eng.K
+        yh, arg, save = ctx.saved_tensors
+        dy = torch.empty_like(yh)
+        slot = eng.bwd_slot(bn)
+        peer = eng.peer_state if eng.sync_bn else None
+        args = (yh, _nhwc(dout), arg, dy, slot.tensor, slot.sym_offset, eng.master_view(bn.weight) if bn.affine else None,
+                save[0], save[1], eng.grad_flat_view(bn.weight) if bn.affine else None,
+                eng.grad_flat_view(bn.bias) if bn.affine else None, ctx.count, peer)
+        if peer is not None and eng.defer_wgrad:
+            K.bn_relu_pool_bwd(*args, 1)       # its last CTA opens the cross-rank exchange
+            eng.flush_deferred()               # a deferred weight-gradient GEMM hides the round trip
+            K.bn_relu_pool_bwd(*args, 2)
+        else:
+            K.bn_relu_pool_bwd(*args, 3)
+        if bn.affine:
+            eng.mark_ready(bn.weight)
+            eng.mark_ready(bn.bias)
+        return _nchw_view(dy), None, None, None, None, None
+
+
 def _frozen_bn_backward(ctx, y2, res2, save, d2):
     """Backward of BN applied with its running statistics (module in eval mode during training, e.g. fine-tuning
     with frozen BN): the statistics are constants, so dy = dz * gamma * invstd without the batch-mean corrections of
@@ -812,6 +864,32 @@ class NativeOps:
             return _torch_act(y, act)
         sink = eng.last_sink.get(residual_sink) if (residual_sink is not None and torch.is_grad_enabled()) else None
         return BnActFn.apply(y, residual, eng, bn, act, slot, training, eng.anchor, sink)
+
+    def conv_bn_relu_maxpool(self, x, conv, bn, k, s, p):
+        """Stem: conv -> BN -> ReLU -> max-pool.  3x3/2/1 pooling of an even-sized map in training (or no-grad) mode runs
+        the fused tail (BnReluPoolFn); everything else is the composition of the separate ops."""
+        eng = self.eng
+        stem = self._is_stem(conv, x)
+        fused = ((k, s, p) == (3, 2, 1) and isinstance(bn, nn.BatchNorm2d) and conv.out_channels % 8 == 0
+                 and (stem or self._native_conv_ok(conv, x)) and (bn.training or not torch.is_grad_enabled()))
+        if fused:
+            kh, st, pd, dl = conv.kernel_size[0], conv.stride[0], conv.padding[0], conv.dilation[0]
+            ho = (x.shape[2] + 2 * pd - dl * (kh - 1) - 1) // st + 1
+            wo = (x.shape[3] + 2 * pd - dl * (conv.kernel_size[1] - 1) - 1) // st + 1
+            fused = ho % 2 == 0 and wo % 2 == 0 and ho >= 2 and wo >= 2
+        if not fused:
+            return self.max_pool2d(self.conv_bn_act(x, conv, bn, "relu", None), k, s, p)
+        training = bn.training
+        slot = eng.fwd_slot(bn) if training else None
+        stats = slot.tensor if slot is not None else None
+        if stem:
+            y = StemConvFn.apply(x, eng, conv, stats, eng.anchor)
+        else:
+            peer = eng.peer_state if (slot is not None and eng.sync_bn) else None
+            y = ConvFn.apply(self._as_act(x), eng, conv, stats, eng.anchor, None, None, peer)
+            if peer is not None:
+                slot.presignaled = True
+        return BnReluPoolFn.apply(y, eng, bn, slot, training, eng.anchor)
 
     def bn_act(self, x, bn, act):
         eng = self.eng

@@ -261,6 +261,56 @@ def check_pools():
     return errs
 
 
+def check_bn_relu_pool(N=4, H=16, W=16, C=64, kmod=None, dev="cuda"):
+    """Fused stem tail (BN -> ReLU -> max-pool 3x3/2/1, csrc/elementwise.cu: bn_relu_pool_*) against
+    F.batch_norm -> relu -> F.max_pool2d in fp32 on the same bf16 conv output; negative gammas included (the maximum must
+    be taken AFTER the affine map).  ``kmod`` / ``dev`` let the CPU suite run the same check on the emulated kernels."""
+    Kmod = kmod if kmod is not None else _K()
+    g = torch.Generator(device=dev).manual_seed(21)
+    y = (torch.randn(N, H, W, C, device=dev, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = torch.rand(C, device=dev, generator=g) + 0.5
+    gamma[::5] *= -1.0
+    beta = torch.randn(C, device=dev, generator=g) * 0.2
+    rm, rv = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    stats = torch.zeros(2 * C, device=dev)
+    Kmod.bn_stats(y.view(-1, C), stats)
+    P, Q = H // 2, W // 2
+    out = torch.empty((N, P, Q, C), dtype=torch.bfloat16, device=dev)
+    arg = torch.empty((N, P, Q, C), dtype=torch.uint8, device=dev)
+    save = torch.empty(2, C, device=dev)
+    count = float(N * H * W)
+    Kmod.bn_relu_pool_fwd(y, out, arg, stats, 0, gamma, beta, rm, rv, save[0], save[1], count, 1e-5, 0.1, True, None, False)
+    yr = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    g_ref, b_ref = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    rm2, rv2 = torch.zeros(C, device=dev), torch.ones(C, device=dev)
+    o_ref = F.max_pool2d(F.relu(F.batch_norm(yr, rm2, rv2, g_ref, b_ref, True, 0.1, 1e-5)), 3, 2, 1)
+    e_out = _rel_err(out, o_ref.permute(0, 2, 3, 1))
+    assert e_out < 1e-2, f"bn_relu_pool fwd {e_out}"
+    assert _rel_err(rm, rm2) < 1e-3 and _rel_err(rv, rv2) < 1e-3, "running statistics mismatch"
+    assert int(arg.max()) <= 9
+    dout = (torch.randn(N, P, Q, C, device=dev, generator=g)).to(torch.bfloat16)
+    o_ref.backward(dout.float().permute(0, 3, 1, 2))
+    dy = torch.empty_like(y)
+    sums = torch.zeros(2 * C, device=dev)
+    dgamma, dbeta = torch.zeros(C, device=dev), torch.zeros(C, device=dev)
+    Kmod.bn_relu_pool_bwd(y, dout, arg, dy, sums, 0, gamma, save[0], save[1], dgamma, dbeta, count, None, 3)
+    if dev == "cuda":
+        torch.cuda.synchronize()
+
+    def l2(got, want):   # a tap whose z is within rounding of 0 may legitimately be dead on one side only
+        return float((got.float() - want.float()).norm() / want.float().norm().clamp_min(1e-6))
+
+    errs = {"out": e_out, "dy": l2(dy, yr.grad.permute(0, 2, 3, 1)), "dgamma": l2(dgamma, g_ref.grad), "dbeta": l2(dbeta, b_ref.grad)}
+    assert all(v < 2e-2 for v in errs.values()), f"bn_relu_pool backward mismatch {errs}"
+    # eval mode (running statistics), no argmax
+    out_e = torch.empty_like(out)
+    Kmod.bn_relu_pool_fwd(y, out_e, None, stats, 0, gamma, beta, rm2, rv2, save[0], save[1], count, 1e-5, 0.1, False, None, False)
+    o_eval = F.max_pool2d(F.relu(F.batch_norm(y.float().permute(0, 3, 1, 2), rm2, rv2, gamma, beta, False, 0.1, 1e-5)), 3, 2, 1)
+    errs["eval"] = _rel_err(out_e, o_eval.permute(0, 2, 3, 1))
+    assert errs["eval"] < 1e-2, errs
+    return errs
+
+
 def check_ce_topk(B=64, ncls=1000, topk=5):
     Kmod = _K()
     logits = _bf16(B, ncls, scale=2.0, seed=12)

@@ -367,6 +367,67 @@ class FakeKernels:
         acc.index_put_((n, h, w, c), dout.float(), accumulate=True)
         _raw(dx).copy_(acc.to(BF16))
 
+    # ---------------------------------------------------------------- fused stem tail: BN + ReLU + max-pool 3x3/2/1
+    def bn_relu_pool_fwd(self, y, out, arg, stats, sym_offset, gamma, beta, rm, rv, save_mean, save_invstd, count, eps,
+                         momentum, training, peer=None, presignaled=False):
+        self._count("bn_relu_pool_fwd")
+        assert peer is None
+        N, H, W, C = y.shape
+        assert H % 2 == 0 and W % 2 == 0 and C % 8 == 0 and tuple(out.shape) == (N, H // 2, W // 2, C)
+        yf = y.float()
+        if training:
+            mean = stats[:C] / count
+            var = (stats[C:2 * C] / count - mean * mean).clamp_min(0)
+            invstd = torch.rsqrt(var + eps)
+            _raw(save_mean).copy_(mean)
+            _raw(save_invstd).copy_(invstd)
+            if rm is not None:
+                _raw(rm).mul_(1 - momentum).add_(momentum * mean)
+                _raw(rv).mul_(1 - momentum).add_(momentum * var * (count / max(count - 1.0, 1.0)))
+        else:
+            mean, invstd = rm, torch.rsqrt(rv + eps)
+        g = gamma if gamma is not None else torch.ones(C)
+        b = beta if beta is not None else torch.zeros(C)
+        scale = g * invstd
+        z = yf * scale + (b - mean * scale)
+        o, idx = F.max_pool2d(z.permute(0, 3, 1, 2), 3, 2, 1, return_indices=True)          # idx = h * W + w
+        _raw(out).copy_(o.clamp_min(0).permute(0, 2, 3, 1).to(BF16))
+        if arg is not None:
+            P, Q = o.shape[2], o.shape[3]
+            h, w = idx // W, idx % W
+            ph = torch.arange(P).view(1, 1, P, 1)
+            q = torch.arange(Q).view(1, 1, 1, Q)
+            tap = (h - (ph * 2 - 1)) * 3 + (w - (q * 2 - 1))
+            tap = torch.where(o > 0, tap, torch.full_like(tap, 9))                         # 9: no positive tap
+            _raw(arg).copy_(tap.permute(0, 2, 3, 1).to(torch.uint8))
+
+    def bn_relu_pool_bwd(self, y, dout, arg, dy, sums, sym_offset, gamma, save_mean, save_invstd, dgamma, dbeta, count,
+                         peer=None, phase=3):
+        self._count("bn_relu_pool_bwd")
+        assert peer is None and phase == 3
+        N, H, W, C = y.shape
+        P, Q = dout.shape[1], dout.shape[2]
+        tap = arg.long()
+        live = tap < 9
+        tap = tap.clamp_max(8)
+        ph = torch.arange(P).view(1, P, 1, 1)
+        q = torch.arange(Q).view(1, 1, Q, 1)
+        h = (ph * 2 - 1 + tap // 3).clamp(0, H - 1)
+        w = (q * 2 - 1 + tap % 3).clamp(0, W - 1)
+        n = torch.arange(N).view(N, 1, 1, 1).expand_as(tap)
+        c = torch.arange(C).view(1, 1, 1, C).expand_as(tap)
+        dz = torch.zeros((N, H, W, C), dtype=torch.float32)
+        dz.index_put_((n, h, w, c), dout.float() * live, accumulate=True)
+        g = gamma if gamma is not None else torch.ones(C)
+        xhat = (y.float() - save_mean) * save_invstd
+        s0, s1 = dz.sum((0, 1, 2)), (dz * xhat).sum((0, 1, 2))
+        _raw(sums)[:C] += s0
+        _raw(sums)[C:2 * C] += s1
+        if dgamma is not None:
+            _raw(dgamma).add_(s1)
+            _raw(dbeta).add_(s0)
+        _raw(dy).copy_(((dz - s0 / count - xhat * (s1 / count)) * g * save_invstd).to(BF16))
+
     def avgpool2_fwd(self, x, out):
         _raw(out).copy_(F.avg_pool2d(_nchw(x), 2).permute(0, 2, 3, 1).to(BF16))
 

@@ -93,6 +93,9 @@ def test_training_steps_match_the_torch_path(cpu_engine, arch, size):
     assert float((eng.flat_w16.float() - eng.flat_master).abs().max()) < 2e-2
     # gradient fan-in went through the mailboxes: residual-branch gradients rode along in a dgrad epilogue
     assert fake.calls.get("conv_dgrad+addend", 0) > 0 and fake.calls.get("bn_backward+mask", 0) > 0
+    # the stem's BN + ReLU + max-pool ran as the fused tail (one forward, one backward call per step), not as three ops
+    assert fake.calls.get("bn_relu_pool_fwd", 0) == 3 == fake.calls.get("bn_relu_pool_bwd", 0)
+    assert fake.calls.get("maxpool_fwd", 0) == 0
 
 
 @pytest.mark.parametrize("arch,size,batch", [("efficientnet_b0", 128, 16), ("densenet121", 64, 8), ("regnety_160", 64, 4),

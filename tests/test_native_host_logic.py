@@ -136,3 +136,12 @@ def test_projection_shortcut_hint_is_ignored_on_the_torch_path():
     out.sum().backward(); want.sum().backward()
     assert torch.allclose(h.grad, h2.grad, atol=1e-5)
     assert Fn.conv_bn_act(x, net.conv1, net.bn1, "relu", input_grad_to=net.conv1).shape == (2, 64, 32, 32)
+
+
+def test_fused_stem_tail_emulation_matches_autograd():
+    """BN -> ReLU -> max-pool fused op: the emulated kernels (and with them the check the GPU suite runs on the real
+    ones) against F.batch_norm / relu / max_pool2d autograd."""
+    from fake_kernels import FakeKernels
+    from distribuuuu_b200 import selftest
+    errs = selftest.check_bn_relu_pool(N=3, H=12, W=8, C=16, kmod=FakeKernels(), dev="cpu")
+    assert errs["dy"] < 2e-2

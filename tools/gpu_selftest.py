@@ -26,6 +26,9 @@ def registry():
         "bn_none": lambda: st.check_bn(act=None, residual=False, C=256),
         "bn_silu_c24": lambda: st.check_bn(act="silu", residual=False, C=24),
         "pools": st.check_pools,
+        "bn_relu_pool": st.check_bn_relu_pool,
+        "bn_relu_pool_c96_odd": lambda: st.check_bn_relu_pool(N=3, H=10, W=14, C=96),
+        "bn_relu_pool_prod": lambda: st.check_bn_relu_pool(N=64, H=112, W=112, C=64),
         "ce_topk": st.check_ce_topk,
         "sgd": st.check_sgd,
         "stem": st.check_stem,
