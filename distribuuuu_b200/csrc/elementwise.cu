@@ -955,6 +955,267 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_apply_kernel(BnPoolParam
   }
 }
 
+// ---- strip versions of the stem tail: whole image rows are brought into shared memory with linear bulk copies
+// (cp.async.bulk + mbarrier, two stages), so the loads of the next strip are in flight while this one is computed.
+// The register versions above (loads consumed right after they are issued, ~2 loads in flight per thread) reached only
+// 1.3-2.9 TB/s on the 112x112x64 stem; they remain the fallback when a strip does not fit in shared memory.
+// block: (cvs = C/8, by); thread (tx, ty) owns channel vector tx and walks the strip's pixels / 2x2 blocks ty, ty+by, ...
+__device__ __forceinline__ void unpack8_smem(const unsigned char* base, float (&f)[8]) {
+  unpack8f(*reinterpret_cast<const uint4*>(base), f);
+}
+
+__global__ void __launch_bounds__(256) bn_relu_pool_fwd_strip_kernel(BnPoolParams p) {
+  extern __shared__ __align__(128) unsigned char strip[];    // [2][3 rows][W][C] bf16
+  __shared__ __align__(8) uint64_t full[2];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * blockDim.x + tx;
+  const int c0 = tx * VEC;
+  const uint32_t row_bytes = (uint32_t)p.W * p.C * 2u;
+  const uint32_t stage_bytes = 3u * row_bytes;
+  const int strips = p.N * p.P;
+  auto issue = [&](int s, int stage) {        // thread 0 only
+    const int n = s / p.P, ph = s - n * p.P;
+    const int h_lo = max(2 * ph - 1, 0);                    // rows h_lo .. 2ph+1 are contiguous in memory
+    const uint32_t bytes = (uint32_t)(2 * ph + 2 - h_lo) * row_bytes;
+    const uint32_t bar = smem_u32(&full[stage]);
+    mbar_expect_tx(bar, bytes);
+    bulk_load_1d(smem_u32(strip + (size_t)stage * stage_bytes + (size_t)(h_lo - (2 * ph - 1)) * row_bytes),
+                 p.y + ((long long)n * p.H + h_lo) * p.W * p.C, bytes, bar);
+  };
+  if (tid == 0) { mbar_init(smem_u32(&full[0]), 1); mbar_init(smem_u32(&full[1]), 1); fence_barrier_init(); }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < strips) issue(blockIdx.x, 0);
+  if (p.peer.world > 1 && p.training) peer_exchange_reduce(p.peer, p.sym_offset, p.C);
+  float scale[8], shift[8];
+  {
+    float g[8], b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { g[i] = 1.f; b[i] = 0.f; }
+    if (p.gamma) ld8f(p.gamma + c0, g);
+    if (p.beta) ld8f(p.beta + c0, b);
+    if (p.training) {
+      float s0[8], s1[8];
+      gather_stats(p.peer, p.stats, p.sym_offset, p.C, c0, s0, s1);
+      const float inv_n = 1.f / p.count;
+      const bool writer = (blockIdx.x == 0 && ty == 0);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float mean = s0[i] * inv_n;
+        const float var = fmaxf(s1[i] * inv_n - mean * mean, 0.f);
+        const float invstd = rsqrtf(var + p.eps);
+        scale[i] = g[i] * invstd;
+        shift[i] = b[i] - mean * scale[i];
+        if (writer) {
+          p.save_mean[c0 + i] = mean;
+          p.save_invstd[c0 + i] = invstd;
+          if (p.running_mean) {
+            const float unbiased = var * (p.count / fmaxf(p.count - 1.f, 1.f));
+            p.running_mean[c0 + i] = (1.f - p.momentum) * p.running_mean[c0 + i] + p.momentum * mean;
+            p.running_var[c0 + i] = (1.f - p.momentum) * p.running_var[c0 + i] + p.momentum * unbiased;
+          }
+        }
+      }
+    } else {
+      float rm[8], rv[8];
+      ld8f(p.running_mean + c0, rm);
+      ld8f(p.running_var + c0, rv);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        scale[i] = g[i] * rsqrtf(rv[i] + p.eps);
+        shift[i] = b[i] - rm[i] * scale[i];
+      }
+    }
+  }
+  int it = 0;
+  for (int s = blockIdx.x; s < strips; s += gridDim.x, ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && s + (int)gridDim.x < strips) issue(s + gridDim.x, stage ^ 1);   // that stage was drained in iteration it-1
+    mbar_wait(smem_u32(&full[stage]), (uint32_t)((it >> 1) & 1));
+    const int ph = s % p.P;
+    const unsigned char* base = strip + (size_t)stage * stage_bytes + (size_t)c0 * 2;
+    const int r_lo = (ph == 0) ? 1 : 0;                    // row 2ph-1 does not exist for the first pooled row
+    for (int q = ty; q < p.Q; q += blockDim.y) {
+      float best[8];
+      uint32_t arg[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { best[i] = 0.f; arg[i] = 9u; }   // ReLU floor: only a positive tap can win
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        if (r < r_lo) continue;
+#pragma unroll
+        for (int s2 = 0; s2 < 3; ++s2) {
+          const int w = 2 * q - 1 + s2;
+          if (w < 0 || w >= p.W) continue;
+          float v[8];
+          unpack8_smem(base + ((size_t)r * p.W + w) * p.C * 2, v);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float z = fmaf(v[i], scale[i], shift[i]);
+            if (z > best[i]) { best[i] = z; arg[i] = (uint32_t)(r * 3 + s2); }
+          }
+        }
+      }
+      const long long o = ((long long)s * p.Q + q) * p.C + c0;
+      store8(p.out + o, best);
+      if (p.arg) {
+        uint2 packed;
+        packed.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+        packed.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+        *reinterpret_cast<uint2*>(p.arg + o) = packed;
+      }
+    }
+    __syncthreads();      // everyone is done with this stage before thread 0 refills it in the next iteration
+  }
+}
+
+// strip = block row bp of image n: y rows 2bp, 2bp+1 | dout rows bp, bp+1 | arg rows bp, bp+1 (the +1 rows absent at the end)
+template <bool APPLY>
+__global__ void __launch_bounds__(256) bn_relu_pool_bwd_strip_kernel(BnPoolParams p) {
+  extern __shared__ __align__(128) unsigned char strip[];    // [2][ 2*W*C*2 | 2*Q*C*2 | 2*Q*C ]
+  __shared__ __align__(8) uint64_t full[2];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int tid = ty * blockDim.x + tx;
+  const int c0 = tx * VEC;
+  const int BP = p.H / 2, BQ = p.W / 2;
+  const uint32_t y_bytes = 2u * p.W * p.C * 2u, d_row = (uint32_t)p.Q * p.C * 2u, a_row = (uint32_t)p.Q * p.C;
+  const uint32_t stage_bytes = y_bytes + 2u * d_row + 2u * a_row;
+  const int strips = p.N * BP;
+  auto issue = [&](int s, int stage) {        // thread 0 only
+    const int n = s / BP, bp = s - n * BP;
+    const int rows = (bp + 1 < p.P) ? 2 : 1;
+    const uint32_t bar = smem_u32(&full[stage]);
+    unsigned char* st = strip + (size_t)stage * stage_bytes;
+    mbar_expect_tx(bar, y_bytes + rows * (d_row + a_row));
+    bulk_load_1d(smem_u32(st), p.y + ((long long)n * p.H + 2 * bp) * p.W * p.C, y_bytes, bar);
+    const long long o = ((long long)n * p.P + bp) * p.Q * p.C;
+    bulk_load_1d(smem_u32(st + y_bytes), p.dout + o, rows * d_row, bar);
+    bulk_load_1d(smem_u32(st + y_bytes + 2 * d_row), p.arg + o, rows * a_row, bar);
+  };
+  if (tid == 0) { mbar_init(smem_u32(&full[0]), 1); mbar_init(smem_u32(&full[1]), 1); fence_barrier_init(); }
+  __syncthreads();
+  if (tid == 0 && (int)blockIdx.x < strips) issue(blockIdx.x, 0);
+  float ka[8], kb[8], kc[8];   // reduce: invstd, -mean*invstd, -   apply: scale, ca, cb
+  if (APPLY) {
+    if (p.peer.world > 1) peer_exchange_reduce(p.peer, p.sym_offset, p.C);
+    float s0[8], s1[8];
+    gather_stats(p.peer, p.stats, p.sym_offset, p.C, c0, s0, s1);
+    const float inv_n = 1.f / p.count;
+    float mean[8], invstd[8], g[8];
+    ld8f(p.save_mean + c0, mean);
+    ld8f(p.save_invstd + c0, invstd);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) g[i] = 1.f;
+    if (p.gamma) ld8f(p.gamma + c0, g);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float m_dz = s0[i] * inv_n, m_dzx = s1[i] * inv_n;
+      ka[i] = g[i] * invstd[i];
+      kb[i] = -invstd[i] * m_dzx * ka[i];
+      kc[i] = -m_dz * ka[i] - mean[i] * kb[i];
+    }
+    if (blockIdx.x == 0 && ty == 0 && p.dgamma) {
+      float lg[8], lb[8], dg[8], db[8];
+      ld8f(p.stats + p.C + c0, lg);
+      ld8f(p.stats + c0, lb);
+      ld8f(p.dgamma + c0, dg);
+      ld8f(p.dbeta + c0, db);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { p.dgamma[c0 + i] = dg[i] + lg[i]; p.dbeta[c0 + i] = db[i] + lb[i]; }
+    }
+  } else {
+    float mean[8];
+    ld8f(p.save_mean + c0, mean);
+    ld8f(p.save_invstd + c0, ka);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { kb[i] = -mean[i] * ka[i]; kc[i] = 0.f; }
+  }
+  float a[8], b[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { a[i] = 0.f; b[i] = 0.f; }
+  int it = 0;
+  for (int s = blockIdx.x; s < strips; s += gridDim.x, ++it) {
+    const int stage = it & 1;
+    if (tid == 0 && s + (int)gridDim.x < strips) issue(s + gridDim.x, stage ^ 1);
+    mbar_wait(smem_u32(&full[stage]), (uint32_t)((it >> 1) & 1));
+    const int bp = s % BP;
+    const bool row2 = bp + 1 < p.P;
+    const unsigned char* ys = strip + (size_t)stage * stage_bytes + (size_t)c0 * 2;
+    const unsigned char* ds = strip + (size_t)stage * stage_bytes + y_bytes + (size_t)c0 * 2;
+    const unsigned char* as = strip + (size_t)stage * stage_bytes + y_bytes + 2 * d_row + c0;
+    for (int bq = ty; bq < BQ; bq += blockDim.y) {
+      float d[4][8];
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) d[e][i] = 0.f;
+#pragma unroll
+      for (int dp = 0; dp < 2; ++dp) {
+#pragma unroll
+        for (int dq = 0; dq < 2; ++dq) {
+          const int q = bq + dq;
+          if ((dp == 1 && !row2) || q >= p.Q) continue;
+          const size_t o = ((size_t)dp * p.Q + q) * p.C;
+          const uint2 av = *reinterpret_cast<const uint2*>(as + o);
+          float g[8];
+          unpack8_smem(ds + o * 2, g);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int tap = (int)(((i < 4 ? av.x : av.y) >> (8 * (i & 3))) & 0xffu);
+#pragma unroll
+            for (int br = 0; br < 2; ++br) {
+              const int r = (dp == 0) ? br + 1 : (br == 1 ? 0 : -1);
+              if (r < 0) continue;
+#pragma unroll
+              for (int bc = 0; bc < 2; ++bc) {
+                const int s2 = (dq == 0) ? bc + 1 : (bc == 1 ? 0 : -1);
+                if (s2 < 0) continue;
+                if (tap == r * 3 + s2) d[br * 2 + bc][i] += g[i];
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float y[8];
+        const size_t yo = ((size_t)(e >> 1) * p.W + 2 * bq + (e & 1)) * p.C;
+        unpack8_smem(ys + yo * 2, y);
+        if (APPLY) {
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o[i] = fmaf(d[e][i], ka[i], fmaf(y[i], kb[i], kc[i]));
+          store8(p.dy + ((long long)s * 2 * p.W) * p.C + yo + c0, o);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            a[i] += d[e][i];
+            b[i] = fmaf(d[e][i], fmaf(y[i], ka[i], kb[i]), b[i]);
+          }
+        }
+      }
+    }
+    __syncthreads();
+  }
+  if (!APPLY) {
+    // CTA reduction over ty in the (now idle) strip memory, then one vector RED per 4 channels
+    float* red = reinterpret_cast<float*>(strip);            // [by][cvs][16]
+    const int cvs = blockDim.x, by = blockDim.y;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { red[(ty * cvs + tx) * 16 + i] = a[i]; red[(ty * cvs + tx) * 16 + 8 + i] = b[i]; }
+    __syncthreads();
+    for (int j = tid; j < cvs * 4; j += cvs * by) {          // j = (cv, quad): quad 0,1 -> sum(dz) halves; 2,3 -> sum(dz*xhat)
+      const int cv = j >> 2, quad = j & 3;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int yy = 0; yy < by; ++yy) {
+        const float* src = red + (yy * cvs + cv) * 16 + quad * 4;
+        s0 += src[0]; s1 += src[1]; s2 += src[2]; s3 += src[3];
+      }
+      red_add_v4(p.stats + (quad >= 2 ? p.C : 0) + cv * VEC + (quad & 1) * 4, s0, s1, s2, s3);
+    }
+    if (p.peer.world > 1) peer_signal_at_tail(p.peer, gridDim.x * gridDim.y);
+  }
+}
+
 // Global average pool [N][HW][C] -> [N][C] and its backward (broadcast / HW).
 // CTA = (32 channel vectors) x (8 pixel lanes) of ONE sample: the pixel loop is split over threadIdx.y (4 loads in flight
 // per thread) and reduced through shared memory.  The first version had one thread walk all HW pixels of a channel
@@ -1371,20 +1632,60 @@ extern "C" int b200_bn_bwd_apply(const BnBwdParams* p, cudaStream_t s) {
   k.apply<<<g, b, k.smem, s>>>(*p);
   return (int)cudaGetLastError();
 }
+// strip kernels: block (cvs, by) with by chosen so the strip's items split evenly; two stages of the strip in shared memory
+static inline bool pool_strip_cfg(int C, int items, size_t stage_bytes, dim3& grid, dim3& block, size_t& smem, int strips) {
+  const int cvs = C / VEC;
+  if (cvs > 64) return false;
+  smem = 2 * stage_bytes;
+  if (smem < (size_t)(256 / cvs) * cvs * 16 * sizeof(float)) smem = (size_t)(256 / cvs) * cvs * 16 * sizeof(float);
+  if (smem > 200 * 1024) return false;
+  int by = 256 / cvs;
+  if (by > items) by = items;
+  const int rounds = (items + by - 1) / by;
+  by = (items + rounds - 1) / rounds;
+  block = dim3(cvs, by);
+  const int per_sm = smem <= 100 * 1024 ? 2 : 1;
+  int g = 148 * per_sm;
+  if (g > strips) g = strips;
+  grid = dim3(g);
+  return true;
+}
+template <typename Kern>
+static inline cudaError_t pool_strip_attr(Kern kern) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
 extern "C" int b200_bn_relu_pool_fwd(const BnPoolParams* p, cudaStream_t s) {
   dim3 g, b;
+  size_t smem;
+  static cudaError_t once = pool_strip_attr(bn_relu_pool_fwd_strip_kernel);
+  if (once == cudaSuccess && pool_strip_cfg(p->C, p->Q, (size_t)3 * p->W * p->C * 2, g, b, smem, p->N * p->P)) {
+    bn_relu_pool_fwd_strip_kernel<<<g, b, smem, s>>>(*p);
+    return (int)cudaGetLastError();
+  }
   bn_launch_dims(p->C, (long long)p->N * p->P * p->Q, g, b, 8);
   bn_relu_pool_fwd_kernel<<<g, b, 0, s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_relu_pool_bwd_reduce(const BnPoolParams* p, cudaStream_t s) {
   dim3 g, b;
+  size_t smem;
+  static cudaError_t once = pool_strip_attr(bn_relu_pool_bwd_strip_kernel<false>);
+  if (once == cudaSuccess && pool_strip_cfg(p->C, p->W / 2, (size_t)7 * p->W * p->C, g, b, smem, p->N * (p->H / 2))) {
+    bn_relu_pool_bwd_strip_kernel<false><<<g, b, smem, s>>>(*p);
+    return (int)cudaGetLastError();
+  }
   bn_launch_dims(p->C, (long long)p->N * (p->H / 2) * (p->W / 2), g, b, 4);
   bn_relu_pool_bwd_reduce_kernel<<<g, b, 16 * kBnThreads * sizeof(float), s>>>(*p);
   return (int)cudaGetLastError();
 }
 extern "C" int b200_bn_relu_pool_bwd_apply(const BnPoolParams* p, cudaStream_t s) {
   dim3 g, b;
+  size_t smem;
+  static cudaError_t once = pool_strip_attr(bn_relu_pool_bwd_strip_kernel<true>);
+  if (once == cudaSuccess && pool_strip_cfg(p->C, p->W / 2, (size_t)7 * p->W * p->C, g, b, smem, p->N * (p->H / 2))) {
+    bn_relu_pool_bwd_strip_kernel<true><<<g, b, smem, s>>>(*p);
+    return (int)cudaGetLastError();
+  }
   bn_launch_dims(p->C, (long long)p->N * (p->H / 2) * (p->W / 2), g, b, 8);
   bn_relu_pool_bwd_apply_kernel<<<g, b, 0, s>>>(*p);
   return (int)cudaGetLastError();

@@ -29,6 +29,7 @@ def registry():
         "bn_relu_pool": st.check_bn_relu_pool,
         "bn_relu_pool_c96_odd": lambda: st.check_bn_relu_pool(N=3, H=10, W=14, C=96),
         "bn_relu_pool_prod": lambda: st.check_bn_relu_pool(N=64, H=112, W=112, C=64),
+        "bn_relu_pool_wide_fallback": lambda: st.check_bn_relu_pool(N=2, H=4, W=600, C=64),
         "ce_topk": st.check_ce_topk,
         "sgd": st.check_sgd,
         "stem": st.check_stem,
