@@ -777,7 +777,9 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_kernel(BnPoolParams p) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float z = fmaf(v[i], scale[i], shift[i]);
-        if (z > best[i]) { best[i] = z; arg[i] = (uint32_t)tap; }
+        const bool gt = z > best[i];
+        best[i] = gt ? z : best[i];
+        arg[i] = gt ? (uint32_t)tap : arg[i];
       }
     }
     const long long o = (long long)px * p.C + c0;
@@ -819,7 +821,7 @@ __device__ __forceinline__ void pool_bwd_block(const BnPoolParams& p, int n, int
           for (int bc = 0; bc < 2; ++bc) {
             const int s2 = (dq == 0) ? bc + 1 : (bc == 1 ? 0 : -1);
             if (s2 < 0) continue;
-            if (tap == r * 3 + s2) d[br * 2 + bc][i] += g[i];
+            d[br * 2 + bc][i] += (tap == r * 3 + s2) ? g[i] : 0.f;   // select, not a (divergent) branch
           }
         }
       }
@@ -1034,6 +1036,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_strip_kernel(BnPoolParam
     const int ph = s % p.P;
     const unsigned char* base = strip + (size_t)stage * stage_bytes + (size_t)c0 * 2;
     const int r_lo = (ph == 0) ? 1 : 0;                    // row 2ph-1 does not exist for the first pooled row
+#pragma unroll 2
     for (int q = ty; q < p.Q; q += blockDim.y) {
       float best[8];
       uint32_t arg[8];
@@ -1051,7 +1054,9 @@ __global__ void __launch_bounds__(256) bn_relu_pool_fwd_strip_kernel(BnPoolParam
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float z = fmaf(v[i], scale[i], shift[i]);
-            if (z > best[i]) { best[i] = z; arg[i] = (uint32_t)(r * 3 + s2); }
+            const bool gt = z > best[i];
+            best[i] = gt ? z : best[i];
+            arg[i] = gt ? (uint32_t)(r * 3 + s2) : arg[i];
           }
         }
       }
@@ -1142,6 +1147,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_strip_kernel(BnPoolParam
     const unsigned char* ys = strip + (size_t)stage * stage_bytes + (size_t)c0 * 2;
     const unsigned char* ds = strip + (size_t)stage * stage_bytes + y_bytes + (size_t)c0 * 2;
     const unsigned char* as = strip + (size_t)stage * stage_bytes + y_bytes + 2 * d_row + c0;
+#pragma unroll 2
     for (int bq = ty; bq < BQ; bq += blockDim.y) {
       float d[4][8];
 #pragma unroll
@@ -1169,7 +1175,7 @@ __global__ void __launch_bounds__(256) bn_relu_pool_bwd_strip_kernel(BnPoolParam
               for (int bc = 0; bc < 2; ++bc) {
                 const int s2 = (dq == 0) ? bc + 1 : (bc == 1 ? 0 : -1);
                 if (s2 < 0) continue;
-                if (tap == r * 3 + s2) d[br * 2 + bc][i] += g[i];
+                d[br * 2 + bc][i] += (tap == r * 3 + s2) ? g[i] : 0.f;   // select, not a (divergent) branch
               }
             }
           }
