@@ -110,10 +110,16 @@ CUtensorMap tiled_map_4d(const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2,
 
 // im2col map over an NHWC bf16 activation (dims C, W, H, N).
 CUtensorMap im2col_map_4d(const void* ptr, int N, int H, int W, int C, int low_w, int low_h, int up_w, int up_h,
-                          int stride, uint32_t channels_per_pixel, uint32_t pixels_per_column) {
-  MapKey key{{(uint64_t)ptr, (uint64_t)N, (uint64_t)H, (uint64_t)W, (uint64_t)C, (uint64_t)(uint32_t)low_w,
-              (uint64_t)(uint32_t)low_h, (uint64_t)(uint32_t)up_w, (uint64_t)(uint32_t)up_h, (uint64_t)stride,
-              ((uint64_t)channels_per_pixel << 32) | pixels_per_column, 2}};
+                          int stride, uint32_t channels_per_pixel, uint32_t pixels_per_column, uint64_t sw_el = 0,
+                          uint64_t sh_el = 0, uint64_t sn_el = 0) {
+  // sw/sh/sn: element strides of the W / H / N dimensions; 0 = dense NHWC.  They may be SMALLER than the extent below
+  // them (overlapping pixels): the space-to-depth stem reads 4 neighbouring 16-channel pixels as one 64-channel pixel.
+  if (!sw_el) sw_el = (uint64_t)C;
+  if (!sh_el) sh_el = (uint64_t)W * sw_el;
+  if (!sn_el) sn_el = (uint64_t)H * sh_el;
+  auto pk = [](int a, int b) { return ((uint64_t)(uint32_t)a << 32) | (uint32_t)b; };
+  MapKey key{{(uint64_t)ptr, pk(N, H), pk(W, C), pk(low_w, low_h), pk(up_w, up_h), (uint64_t)stride,
+              ((uint64_t)channels_per_pixel << 32) | pixels_per_column, sw_el, sh_el, sn_el, 0, 2}};
   std::lock_guard<std::mutex> lock(g_map_mutex);
   auto it = g_map_cache.find(key);
   if (it != g_map_cache.end()) return it->second;
@@ -121,7 +127,8 @@ CUtensorMap im2col_map_4d(const void* ptr, int N, int H, int W, int C, int low_w
   TORCH_CHECK(((uintptr_t)ptr & 15) == 0 && (C % 8) == 0, "im2col TMA needs 16-byte aligned base and C % 8 == 0");
   CUtensorMap m;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  TORCH_CHECK(sw_el % 8 == 0 && sh_el % 8 == 0 && sn_el % 8 == 0, "im2col TMA strides must be multiples of 16 bytes");
+  cuuint64_t strides[3] = {(cuuint64_t)sw_el * 2, (cuuint64_t)sh_el * 2, (cuuint64_t)sn_el * 2};
   int lower[2] = {low_w, low_h};
   int upper[2] = {up_w, up_h};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
@@ -134,7 +141,8 @@ CUtensorMap im2col_map_4d(const void* ptr, int N, int H, int W, int C, int low_w
   // workaround CUTLASS applies in make_im2col_tma_copy_desc).
   int drv = 0;
   cudaDriverGetVersion(&drv);
-  if (drv <= 13010 && (uint64_t)N * H * W * C * 2 < 131072) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
+  const uint64_t span_bytes = ((uint64_t)(N - 1) * sn_el + (uint64_t)(H - 1) * sh_el + (uint64_t)(W - 1) * sw_el + (uint64_t)C) * 2;
+  if (drv <= 13010 && span_bytes < 131072) reinterpret_cast<uint64_t*>(&m)[1] &= ~(1ull << 21);
   if (g_map_cache.size() > 8192) g_map_cache.clear();
   g_map_cache.emplace(key, m);
   return m;
@@ -232,7 +240,11 @@ struct PeerState;
 PeerCtx peer_ctx_for_producer(PeerState* peer);
 void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const c10::optional<at::Tensor>& stats,
                 const c10::optional<at::Tensor>& bias, int64_t stride, int64_t pad, int64_t dil, int64_t groups, PeerState* peer) {
-  check_bf16_contig(x, "x"); check_bf16_contig(w, "w");
+  check_bf16_contig(w, "w");
+  // x: dense NHWC, or (non-pointwise only) any view with contiguous channels and 16-byte-multiple W/H/N strides -- the
+  // im2col tensor map takes the strides as they are, including overlapping pixels (space-to-depth stem, ops/native.py)
+  const bool x_dense = x.is_contiguous();
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.dim() == 4 && x.stride(3) == 1, "x must be an NHWC bf16 CUDA tensor");
   c10::cuda::CUDAGuard guard(x.device());
   const ConvGeom g = geom(x, w, stride, pad, dil, groups);
   // out: [N,P,Q,K] bf16, channels contiguous, uniform pixel pitch >= K (a channel slice of a wider NHWC buffer is fine:
@@ -249,6 +261,7 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   if (bias.has_value()) plan.cg = 1;    // the bias epilogue (classifier) is only instantiated for single-CTA tiles
   const int bn = plan.bn;
   const bool pointwise = (g.R == 1 && g.S == 1 && stride == 1 && pad == 0);
+  TORCH_CHECK(x_dense || !pointwise, "a strided activation view needs the im2col path");
   ConvGemmParams p{};
   p.b_resident = plan.resident; p.res_stages = plan.res_stages;
   p.kind = KIND_FPROP; p.epi = EPI_BF16;
@@ -277,7 +290,7 @@ void conv_fprop(const at::Tensor& x, const at::Tensor& w, at::Tensor& out, const
   CUtensorMap ma = pointwise
                        ? tiled_map_3d(x.data_ptr(), g.C, 1, M, g.C, g.C, 64, 1, 128)
                        : im2col_map_4d(x.data_ptr(), g.N, g.H, g.W, g.C, -pad, -pad, pad - (g.S - 1) * dil,
-                                       pad - (g.R - 1) * dil, stride, 64, 128);
+                                       pad - (g.R - 1) * dil, stride, 64, 128, x.stride(2), x.stride(1), x.stride(0));
   CUtensorMap mb = tiled_map_4d(w.data_ptr(), cin_g, p.taps, cout_g, G, cin_g, (uint64_t)p.taps * cin_g,
                                 (uint64_t)p.taps * cin_g * cout_g, 64, 1, bn / cg, 1);   // pair: each CTA loads half the N tile
   CUtensorMap mo = tiled_map_3d(out.data_ptr(), cout_g, M, G, out_pitch, cout_g, 64, 32, 1);
@@ -416,8 +429,9 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   const int N = x.size(0), H = x.size(1), W = x.size(2), C = x.size(3);
   // x: NHWC bf16; a pointwise layer may read a channel slice of a wider buffer (uniform pixel pitch)
   const int64_t x_pitch = x.stride(2);
-  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.stride(3) == 1 && x_pitch >= C && x_pitch % 8 == 0 &&
-              x.stride(1) == W * x_pitch && x.stride(0) == (int64_t)H * W * x_pitch, "x must be NHWC bf16 with a uniform pixel pitch");
+  const bool x_uniform = x_pitch >= C && x.stride(1) == W * x_pitch && x.stride(0) == (int64_t)H * W * x_pitch;
+  TORCH_CHECK(x.is_cuda() && x.scalar_type() == at::kBFloat16 && x.stride(3) == 1 && x_pitch % 8 == 0,
+              "x must be NHWC bf16 with contiguous channels");
   const int K = dw.size(0), R = dw.size(1), S = dw.size(2);
   const int P = dy.size(1), Q = dy.size(2);
   const int G = groups, cin_g = C / G, cout_g = K / G;
@@ -425,7 +439,9 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   TORCH_CHECK(cin_g % 8 == 0 && cout_g % 8 == 0, "channels per group must be multiples of 8");
   const long long pixels = (long long)N * P * Q;
   const bool pointwise = (R == 1 && S == 1 && stride == 1 && pad == 0);
-  TORCH_CHECK(pointwise || x_pitch == C, "only 1x1 weight gradients accept a channel-sliced input");
+  // pointwise: a channel slice of a wider buffer (uniform pixel pitch); otherwise any strided view, overlapping pixels
+  // included (the im2col tensor map takes the strides as they are)
+  TORCH_CHECK(!pointwise || x_uniform, "1x1 weight gradients need a uniform pixel pitch");
   // B operand = "virtual boxes": (tap, 64-channel slice of Cin).  One work item accumulates up to 4 of them
   // (N = 64..256 TMEM columns) against a single load of the dY^T tile, so dY is re-read taps*Cin/(64*vpi) times
   // instead of taps*Cin/64 times.
@@ -464,7 +480,7 @@ void conv_wgrad(const at::Tensor& dy, const at::Tensor& x, at::Tensor& dw, int64
   CUtensorMap ma = tiled_map_3d(dy.data_ptr(), K, 1, pixels, K, K, 64, 1, 64);
   CUtensorMap mb = pointwise ? tiled_map_3d(x.data_ptr(), C, 1, pixels, x_pitch, x_pitch, 64, 1, 64)
                              : im2col_map_4d(x.data_ptr(), N, H, W, C, -pad, -pad, pad - (S - 1) * dil,
-                                             pad - (R - 1) * dil, stride, 64, 64);
+                                             pad - (R - 1) * dil, stride, 64, 64, x.stride(2), x.stride(1), x.stride(0));
   const int grid = cg == 2 ? 2 * std::min(p.total_items, num_sms() / 2) : std::min(p.total_items, num_sms());
   B200_CUDA_OK(b200_conv_gemm_launch(&ma, &mb, &ma, &ma, &p, bn, grid, cur_stream()));
 }
@@ -760,6 +776,33 @@ void unpad_add(const at::Tensor& src, at::Tensor& dst, int64_t rows, int64_t col
   B200_CUDA_OK(b200_unpad_add(src.data_ptr<float>(), dst.data_ptr<float>(), rows, cols, cols_pad, cur_stream()));
 }
 
+// Space-to-depth stem (extras.cu): x [N,3,H,W] fp32 / uint8 -> out [N,Hs,Ws,16] bf16 with out[n,i,j,(u*2+v)*3+c] = x[n,c,2i+u-3,2j+v-3]
+void stem_s2d(const at::Tensor& x, at::Tensor& out, const std::vector<double>& mean, const std::vector<double>& std_) {
+  c10::cuda::CUDAGuard guard(x.device());
+  const bool u8 = x.scalar_type() == at::kByte;
+  TORCH_CHECK(x.is_cuda() && (u8 || x.scalar_type() == at::kFloat) && x.is_contiguous() && x.dim() == 4 && x.size(1) == 3, "stem_s2d: [N,3,H,W] fp32 / uint8");
+  check_bf16_contig(out, "out");
+  TORCH_CHECK(out.dim() == 4 && out.size(0) == x.size(0) && out.size(3) == 16, "stem_s2d: out [N,Hs,Ws,16]");
+  float sc[3] = {1.f, 1.f, 1.f}, bi[3] = {0.f, 0.f, 0.f};
+  if (u8) {
+    TORCH_CHECK(mean.size() == 3 && std_.size() == 3, "stem_s2d: uint8 input needs per-channel mean/std");
+    for (int c = 0; c < 3; ++c) { sc[c] = (float)(1.0 / (255.0 * std_[c])); bi[c] = (float)(-mean[c] / std_[c]); }
+  }
+  B200_CUDA_OK(b200_stem_s2d(x.data_ptr(), u8 ? 1 : 0, out.data_ptr(), x.size(0), x.size(2), x.size(3), out.size(1), out.size(2), sc, bi, cur_stream()));
+}
+void stem_s2d_pack_w(const at::Tensor& w, at::Tensor& wp) {
+  check_bf16_contig(w, "w"); check_bf16_contig(wp, "wp");
+  c10::cuda::CUDAGuard guard(w.device());
+  TORCH_CHECK(w.numel() % 147 == 0 && wp.numel() == w.numel() / 147 * 256, "stem_s2d_pack_w: w [K,7,7,3] -> wp [K,4,1,64]");
+  B200_CUDA_OK(b200_stem_s2d_pack_w(w.data_ptr(), wp.data_ptr(), w.numel() / 147, cur_stream()));
+}
+void stem_s2d_unpack_dw(const at::Tensor& dwp, at::Tensor& dw) {
+  c10::cuda::CUDAGuard guard(dwp.device());
+  TORCH_CHECK(dwp.scalar_type() == at::kFloat && dw.scalar_type() == at::kFloat && dwp.is_contiguous() && dw.is_contiguous() &&
+              dw.numel() % 147 == 0 && dwp.numel() == dw.numel() / 147 * 256, "stem_s2d_unpack_dw: dwp [K,4,1,64] fp32 -> dw [K,7,7,3] fp32");
+  B200_CUDA_OK(b200_stem_s2d_unpack_dw(dwp.data_ptr<float>(), dw.data_ptr<float>(), dw.numel() / 147, cur_stream()));
+}
+
 // ---------------------------------------------------------------------------------------------- extras
 void colsum_add(const at::Tensor& d, at::Tensor& out) {
   c10::cuda::CUDAGuard guard(d.device());
@@ -995,6 +1038,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("conv3x3_halo", &conv3x3_halo, "3x3/s1/p1 64->64 convolution with one halo load per tile (forward or data gradient)",
         py::arg("x"), py::arg("w"), py::arg("y"), py::arg("stats") = py::none(), py::arg("dgrad") = false, py::arg("peer") = py::none());
   m.def("colsum_add", &colsum_add);
+  m.def("stem_s2d", &stem_s2d, py::arg("x"), py::arg("out"), py::arg("mean") = std::vector<double>{}, py::arg("std") = std::vector<double>{});
+  m.def("stem_s2d_pack_w", &stem_s2d_pack_w);
+  m.def("stem_s2d_unpack_dw", &stem_s2d_unpack_dw);
   m.def("strided_add_inplace", &strided_add_inplace);
   m.def("blockdiag_pack", &blockdiag_pack);
   m.def("blockdiag_unpack_add", &blockdiag_unpack_add);

@@ -378,10 +378,92 @@ __global__ void __launch_bounds__(256) channel_add_bcast_kernel(__nv_bfloat16* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------ space-to-depth stem
+// A 7x7 / stride 2 / pad 3 convolution over 3 channels equals a 4x4 / stride 1 convolution over the 2x2 space-to-depth
+// image (12 channels, padded to 16):  r = 2a + u, s = 2b + v  =>  out[p,q] = sum_{a,b<4} W'[a,b,(u,v,c)] . S[p+a, q+b, (u,v,c)],
+// S[i,j,(u*2+v)*3+c] = x[c, 2i+u-3, 2j+v-3].  Four horizontally adjacent 16-channel pixels of S are 128 contiguous bytes,
+// i.e. ONE 64-channel "pixel" of a virtual NHWC tensor whose W-stride is 16 elements -- so the stem runs on the generic
+// im2col tcgen05 kernels as a 4x1 convolution over that overlapping view (ops/native.py: StemConvFn), and the 1 GB
+// explicit patch tensor of the im2col path (read again by wgrad) shrinks to the 108 MB S.
+template <typename T>
+__global__ void __launch_bounds__(256) stem_s2d_kernel(const T* __restrict__ x /*[N][3][H][W]*/, __nv_bfloat16* __restrict__ out /*[N][Hs][Ws][16]*/,
+                                                       int N, int H, int W, int Hs, int Ws, float sc0, float sc1, float sc2,
+                                                       float bi0, float bi1, float bi2) {
+  const long long total = (long long)N * Hs * Ws;
+  const float sc[3] = {sc0, sc1, sc2}, bi[3] = {bi0, bi1, bi2};
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int j = (int)(idx % Ws);
+    const long long t = idx / Ws;
+    const int i = (int)(t % Hs), n = (int)(t / Hs);
+    float v[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) v[k] = 0.f;      // zero padding lives in the normalised domain (Normalize -> Conv2d(padding))
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int h = 2 * i + u - 3;
+      if (h < 0 || h >= H) continue;
+#pragma unroll
+      for (int vv = 0; vv < 2; ++vv) {
+        const int w = 2 * j + vv - 3;
+        if (w < 0 || w >= W) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const T raw = __ldg(x + (((long long)n * 3 + c) * H + h) * W + w);
+          v[(u * 2 + vv) * 3 + c] = sizeof(T) == 1 ? fmaf((float)raw, sc[c], bi[c]) : (float)raw;
+        }
+      }
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { lo[k] = v[k]; hi[k] = v[8 + k]; }
+    st8(out + idx * 16, lo);
+    st8(out + idx * 16 + 8, hi);
+  }
+}
+// w [K][7][7][3] bf16 -> w' [K][4][1][64] bf16: w'[k][a][b*16 + (u*2+v)*3 + c] = w[k][2a+u][2b+v][c] (0 where 2a+u or 2b+v is 7)
+__global__ void stem_s2d_pack_w_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wp, int K) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * 256) return;
+  const int k = idx >> 8, a = (idx >> 6) & 3, b = (idx >> 4) & 3, ch = idx & 15;
+  __nv_bfloat16 val = __float2bfloat16_rn(0.f);
+  if (ch < 12) {
+    const int uv = ch / 3, c = ch - uv * 3, r = 2 * a + (uv >> 1), s2 = 2 * b + (uv & 1);
+    if (r < 7 && s2 < 7) val = w[((k * 7 + r) * 7 + s2) * 3 + c];
+  }
+  wp[idx] = val;
+}
+// dw [K][7][7][3] fp32 += dw' [K][4][1][64] fp32 (inverse index map of the above)
+__global__ void stem_s2d_unpack_dw_kernel(const float* __restrict__ dwp, float* __restrict__ dw, int K) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * 147) return;
+  const int k = idx / 147, rem = idx - k * 147;
+  const int r = rem / 21, s2 = (rem / 3) % 7, c = rem % 3;
+  dw[idx] += dwp[k * 256 + (r >> 1) * 64 + (s2 >> 1) * 16 + ((r & 1) * 2 + (s2 & 1)) * 3 + c];
+}
+
 }  // namespace b200
 
 using namespace b200;
 
+extern "C" int b200_stem_s2d(const void* x, int x_is_u8, void* out, int N, int H, int W, int Hs, int Ws, const float* scale3,
+                             const float* bias3, cudaStream_t s) {
+  const long long total = (long long)N * Hs * Ws;
+  const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+  if (x_is_u8)
+    stem_s2d_kernel<uint8_t><<<grid, 256, 0, s>>>((const uint8_t*)x, (__nv_bfloat16*)out, N, H, W, Hs, Ws, scale3[0], scale3[1], scale3[2],
+                                                  bias3[0], bias3[1], bias3[2]);
+  else
+    stem_s2d_kernel<float><<<grid, 256, 0, s>>>((const float*)x, (__nv_bfloat16*)out, N, H, W, Hs, Ws, 1.f, 1.f, 1.f, 0.f, 0.f, 0.f);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_stem_s2d_pack_w(const void* w, void* wp, int K, cudaStream_t s) {
+  stem_s2d_pack_w_kernel<<<(K * 256 + 255) / 256, 256, 0, s>>>((const __nv_bfloat16*)w, (__nv_bfloat16*)wp, K);
+  return (int)cudaGetLastError();
+}
+extern "C" int b200_stem_s2d_unpack_dw(const float* dwp, float* dw, int K, cudaStream_t s) {
+  stem_s2d_unpack_dw_kernel<<<(K * 147 + 255) / 256, 256, 0, s>>>(dwp, dw, K);
+  return (int)cudaGetLastError();
+}
 extern "C" int b200_colsum_add(const void* d, long long rows, int C, long long ld, float* out, cudaStream_t s) {
   dim3 grid((C / 8 + 31) / 32, (unsigned)std::min<long long>(64, (rows + 7) / 8));
   if (grid.y < 1) grid.y = 1;

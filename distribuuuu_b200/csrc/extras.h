@@ -5,6 +5,9 @@
 
 extern "C" {
 int b200_colsum_add(const void* d, long long rows, int C, long long ld, float* out, cudaStream_t s);
+int b200_stem_s2d(const void* x, int x_is_u8, void* out, int N, int H, int W, int Hs, int Ws, const float* scale3, const float* bias3, cudaStream_t s);
+int b200_stem_s2d_pack_w(const void* w, void* wp, int K, cudaStream_t s);
+int b200_stem_s2d_unpack_dw(const float* dwp, float* dw, int K, cudaStream_t s);
 int b200_parity_interleave(const void* const* src4, const void* addend, void* dx, int N, int H, int W, int C, cudaStream_t s);
 int b200_strided_add_inplace(void* dx, const void* compact, int N, int H, int W, int C, int P, int Q, int stride, cudaStream_t s);
 int b200_blockdiag_pack(const void* thin, void* dense, int K, int taps, int cg, cudaStream_t s);

@@ -330,10 +330,22 @@ class DwConvFn(torch.autograd.Function):
 
 
 class StemConvFn(torch.autograd.Function):
-    """7x7/2 stem on the raw NCHW batch: explicit im2col to [pixels, 160] bf16 (K = 147 padded), then the
-    tcgen05 GEMM; wgrad is the same GEMM transposed.  The input needs no gradient.  The batch is either fp32
-    (already normalised, as the reference's loader produces, utils.py:127-135) or uint8 pixels, which the im2col
-    kernel normalises with ``eng.input_mean/std`` while staging them."""
+    """Stem convolution on the raw NCHW batch (fp32, already normalised, as the reference's loader produces,
+    utils.py:127-135 -- or uint8 pixels, normalised with ``eng.input_mean/std`` while they are staged).
+    The input needs no gradient.
+
+    * 7x7 / stride 2 / pad 3 over 3 channels (ResNet, DenseNet, BoTNet): **space-to-depth**.  One pass turns the image
+      into S[N, P+3, Q+3, 16] (2x2 pixel blocks as channels, csrc/extras.cu), on which the stem is a 4x4 stride-1
+      convolution; four horizontally adjacent 16-channel pixels of S are 128 contiguous bytes, so an ``as_strided`` view
+      with a W-stride of 16 elements presents them as ONE 64-channel pixel and the generic im2col tcgen05 kernels run
+      fprop and wgrad as a 4x1 convolution over that (overlapping) view -- the im2col TMA map takes the strides as
+      they are.  108 MB of S instead of 1.03 GB of explicit patches (written once, read by fprop and again by wgrad).
+    * any other small-Cin stem (3x3/2 of RegNet / EfficientNet): explicit im2col to [pixels, Kpad] bf16, then the GEMM."""
+
+    @staticmethod
+    def _s2d_ok(eng, conv, x):
+        return (eng.stem_s2d and conv.kernel_size == (7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3)
+                and conv.in_channels == 3 and conv.out_channels % 8 == 0)
 
     @staticmethod
     def forward(ctx, x_nchw_f32, eng, conv, stats, anchor):
@@ -343,32 +355,61 @@ class StemConvFn(torch.autograd.Function):
         s, p = conv.stride[0], conv.padding[0]
         P = (H + 2 * p - (R - 1) - 1) // s + 1
         Q = (W + 2 * p - (S - 1) - 1) // s + 1
+        x = x_nchw_f32.contiguous()
+        norm = (list(eng.input_mean), list(eng.input_std)) if x.dtype == torch.uint8 else ()
+        ctx.eng, ctx.conv = eng, conv
+        if StemConvFn._s2d_ok(eng, conv, x):
+            try:
+                xs = torch.empty((N, P + 3, Q + 3, 16), dtype=torch.bfloat16, device=x.device)
+                K.stem_s2d(x, xs, *norm)
+                xv = StemConvFn._virtual(xs, Q)
+                w2 = eng.scratch("stem_w_s2d", (Kc, 4, 1, 64), torch.bfloat16)
+                K.stem_s2d_pack_w(eng.w16_krsc(conv.weight), w2)
+                y = torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
+                K.conv_fprop(xv, w2, y, stats, None, 1, 0, 1)
+                ctx.s2d, ctx.Q = True, Q
+                ctx.save_for_backward(xs)
+                return _nchw_view(y)
+            except RuntimeError as exc:          # e.g. a driver that rejects the overlapping tensor map: say so, keep training
+                from loguru import logger
+                logger.warning(f"[b200] space-to-depth stem unavailable ({exc}); using the explicit im2col stem")
+                eng.stem_s2d = False
         kdim = R * S * C
         kpad = (kdim + 15) // 16 * 16
-        patches = torch.empty((N * P * Q, 1, 1, kpad), dtype=torch.bfloat16, device=x_nchw_f32.device)
-        if x_nchw_f32.dtype == torch.uint8:
-            K.stem_im2col(x_nchw_f32.contiguous(), patches, R, S, s, p, P, Q, list(eng.input_mean), list(eng.input_std))
-        else:
-            K.stem_im2col(x_nchw_f32.contiguous(), patches, R, S, s, p, P, Q)
+        patches = torch.empty((N * P * Q, 1, 1, kpad), dtype=torch.bfloat16, device=x.device)
+        K.stem_im2col(x, patches, R, S, s, p, P, Q, *norm)
         wpad = eng.scratch("stem_w", (Kc, 1, 1, kpad), torch.bfloat16)
         K.pad_rows(eng.w16_krsc(conv.weight), wpad, Kc, kdim, kpad)
-        y = torch.empty((N * P * Q, 1, 1, Kc), dtype=torch.bfloat16, device=x_nchw_f32.device)
+        y = torch.empty((N * P * Q, 1, 1, Kc), dtype=torch.bfloat16, device=x.device)
         K.conv_fprop(patches, wpad, y, stats, None, 1, 0, 1)
-        ctx.eng, ctx.conv, ctx.dims = eng, conv, (Kc, kdim, kpad)
+        ctx.s2d, ctx.dims = False, (Kc, kdim, kpad)
         ctx.save_for_backward(patches)
         return _nchw_view(y.view(N, P, Q, Kc))
+
+    @staticmethod
+    def _virtual(xs, Q):
+        """[N, Hs, Ws, 16] -> the overlapping [N, Hs, Q, 64] view: pixel q = S-pixels q..q+3 (Ws = Q + 3)."""
+        N, Hs, Ws, _ = xs.shape
+        return xs.as_strided((N, Hs, Q, 64), (Hs * Ws * 16, Ws * 16, 16, 1))
 
     @staticmethod
     def backward(ctx, dy):
         eng, conv = ctx.eng, ctx.conv
         K = eng.K
-        Kc, kdim, kpad = ctx.dims
-        (patches,) = ctx.saved_tensors
-        dyh = _nhwc(dy).reshape(-1, 1, 1, Kc)
-        dwp = eng.scratch("stem_dw", (Kc, 1, 1, kpad), torch.float32)
-        dwp.zero_()
-        K.conv_wgrad(dyh, patches, dwp, 1, 0, 1)
-        K.unpad_add(dwp, eng.grad_flat_view(conv.weight), Kc, kdim, kpad)
+        Kc = conv.out_channels
+        (saved,) = ctx.saved_tensors
+        if ctx.s2d:
+            dwp = eng.scratch("stem_dw_s2d", (Kc, 4, 1, 64), torch.float32)
+            dwp.zero_()
+            K.conv_wgrad(_nhwc(dy), StemConvFn._virtual(saved, ctx.Q), dwp, 1, 0, 1)
+            K.stem_s2d_unpack_dw(dwp, eng.grad_flat_view(conv.weight))
+        else:
+            Kc, kdim, kpad = ctx.dims
+            dyh = _nhwc(dy).reshape(-1, 1, 1, Kc)
+            dwp = eng.scratch("stem_dw", (Kc, 1, 1, kpad), torch.float32)
+            dwp.zero_()
+            K.conv_wgrad(dyh, saved, dwp, 1, 0, 1)
+            K.unpad_add(dwp, eng.grad_flat_view(conv.weight), Kc, kdim, kpad)
         eng.mark_ready(conv.weight)
         return None, None, None, None, None
 

@@ -26,6 +26,7 @@ Checkpoints stay reference-compatible: ``module.state_dict()`` reads fp32 views 
 """
 from __future__ import annotations
 
+import os
 from dataclasses import dataclass
 from typing import Dict, List
 
@@ -116,6 +117,8 @@ class NativeEngine(nn.Module):
         super().__init__()
         # CUDA-graph replay of the training step (B200.CUDA_GRAPH); see _graphed_step
         self.cuda_graph = bool(cuda_graph)
+        # 7x7/2 stems as a space-to-depth 4x1 convolution on the im2col tcgen05 kernels (ops/native.py: StemConvFn)
+        self.stem_s2d = os.environ.get("B200_STEM_S2D", "1") != "0"
         self._graphs = {}
         self._graph_pool = None
         self._eager_steps = 0

@@ -584,6 +584,57 @@ def check_stem():
     return {"im2col": e, "im2col_uint8": eu}
 
 
+def check_stem_s2d(N=2, H=64, W=64, Kc=64):
+    """7x7/2 stem as a space-to-depth 4x1 convolution over an overlapping NHWC view (ops/native.py: StemConvFn):
+    the S tensor, the packed weights, fprop (+ statistics) and wgrad through the generic im2col kernels, against
+    F.conv2d / conv2d_weight in fp32 on the same bf16-rounded operands."""
+    Kmod = _K()
+    from .ops.native import StemConvFn
+    from .utils.data import IMAGENET_MEAN, IMAGENET_STD, normalize_uint8
+    g = torch.Generator(device="cuda").manual_seed(31)
+    x = torch.randn(N, 3, H, W, device="cuda", generator=g)
+    w = (torch.randn(Kc, 7, 7, 3, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    P, Q = H // 2, W // 2
+    xs = torch.empty((N, P + 3, Q + 3, 16), dtype=torch.bfloat16, device="cuda")
+    Kmod.stem_s2d(x, xs)
+    xp = torch.zeros((N, 3, 2 * (P + 3), 2 * (Q + 3)), device="cuda")
+    xp[:, :, 3:3 + H, 3:3 + W] = x
+    ref_s = torch.zeros((N, P + 3, Q + 3, 16), device="cuda")
+    for u in range(2):
+        for v in range(2):
+            ref_s[..., (u * 2 + v) * 3:(u * 2 + v) * 3 + 3] = xp[:, :, u::2, v::2].permute(0, 2, 3, 1)
+    e_s = _rel_err(xs, ref_s.to(torch.bfloat16))
+    assert e_s < 1e-6, f"stem_s2d {e_s}"
+    xu = torch.randint(0, 256, (N, 3, H, W), device="cuda", dtype=torch.uint8)
+    xsu = torch.empty_like(xs)
+    Kmod.stem_s2d(xu, xsu, list(IMAGENET_MEAN), list(IMAGENET_STD))
+    xs_ref_u = torch.empty_like(xs)
+    Kmod.stem_s2d(normalize_uint8(xu), xs_ref_u)
+    e_u = _rel_err(xsu, xs_ref_u)
+    assert e_u < 1e-2, f"stem_s2d uint8 {e_u}"
+    xv = StemConvFn._virtual(xs, Q)
+    w2 = torch.empty((Kc, 4, 1, 64), dtype=torch.bfloat16, device="cuda")
+    Kmod.stem_s2d_pack_w(w, w2)
+    y = torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device="cuda")
+    stats = torch.zeros(2 * Kc, device="cuda")
+    Kmod.conv_fprop(xv, w2, y, stats, None, 1, 0, 1)
+    xb = x.to(torch.bfloat16).float()
+    ref = F.conv2d(xb, w.float().permute(0, 3, 1, 2), None, 2, 3)
+    e_y = _rel_err(y, ref.permute(0, 2, 3, 1))
+    yf = y.float().view(-1, Kc)
+    e_st = max(_rel_err(stats[:Kc], yf.sum(0)), _rel_err(stats[Kc:], (yf * yf).sum(0)))
+    dy = (torch.randn(N, P, Q, Kc, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    dwp = torch.zeros((Kc, 4, 1, 64), device="cuda")
+    Kmod.conv_wgrad(dy, xv, dwp, 1, 0, 1)
+    dw = torch.zeros((Kc, 7, 7, 3), device="cuda")
+    Kmod.stem_s2d_unpack_dw(dwp, dw)
+    ref_dw = torch.nn.grad.conv2d_weight(xb, (Kc, 3, 7, 7), dy.float().permute(0, 3, 1, 2), 2, 3).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    errs = {"s2d": e_s, "s2d_uint8": e_u, "fprop": e_y, "stats": e_st, "wgrad": _rel_err(dw, ref_dw)}
+    assert errs["fprop"] < 1e-2 and errs["stats"] < 1e-2 and errs["wgrad"] < 2e-2, errs
+    return errs
+
+
 def check_uint8_input(arch="resnet18", batch=8, size=64):
     """The engine fed raw uint8 pixels gives the logits of the same engine fed the host-normalised fp32 batch."""
     from . import models

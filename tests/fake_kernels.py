@@ -78,6 +78,42 @@ class FakeKernels:
         flat.zero_()
         flat[:, : R * S * C] = cols.to(BF16)
 
+    def stem_s2d(self, x, out, mean=(), std=()):
+        self._count("stem_s2d")
+        if x.dtype == torch.uint8:
+            m = torch.tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+            sd = torch.tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+            x = (x.float() / 255.0 - m) / sd
+        N, C, H, W = x.shape
+        Hs, Ws = out.shape[1], out.shape[2]
+        xp = torch.zeros((N, C, 2 * Hs, 2 * Ws), dtype=torch.float32)
+        xp[:, :, 3:3 + H, 3:3 + W] = x.float()
+        o = _raw(out)
+        o.zero_()
+        for u in range(2):
+            for v in range(2):
+                blk = xp[:, :, u::2, v::2].permute(0, 2, 3, 1)                      # [N, Hs, Ws, 3]
+                o[..., (u * 2 + v) * 3:(u * 2 + v) * 3 + 3] = blk.to(BF16)
+
+    def stem_s2d_pack_w(self, w, wp):
+        K = w.numel() // 147
+        w7 = torch.zeros((K, 8, 8, 3), dtype=torch.float32)
+        w7[:, :7, :7] = w.reshape(K, 7, 7, 3).float()
+        o = torch.zeros((K, 4, 4, 16), dtype=torch.float32)
+        for u in range(2):
+            for v in range(2):
+                o[..., (u * 2 + v) * 3:(u * 2 + v) * 3 + 3] = w7[:, u::2, v::2]
+        _raw(wp).copy_(o.reshape(K, 4, 1, 64).to(BF16))
+
+    def stem_s2d_unpack_dw(self, dwp, dw):
+        K = dw.numel() // 147
+        o = dwp.reshape(K, 4, 4, 16)
+        g = torch.zeros((K, 8, 8, 3), dtype=torch.float32)
+        for u in range(2):
+            for v in range(2):
+                g[:, u::2, v::2] = o[..., (u * 2 + v) * 3:(u * 2 + v) * 3 + 3]
+        _raw(dw).view(K, 7, 7, 3).add_(g[:, :7, :7])
+
     def pad_rows(self, src, dst, rows, cols, cols_pad):
         d = _raw(dst).view(rows, cols_pad)
         d.zero_()

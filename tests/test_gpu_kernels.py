@@ -83,6 +83,12 @@ def test_stem_im2col_and_layout_conversion():
     selftest.check_stem()
 
 
+@pytest.mark.parametrize("kw", [dict(), dict(N=16, H=224, W=224), dict(N=3, H=96, W=160, Kc=96)], ids=["64", "224", "96x160_k96"])
+def test_stem_space_to_depth_on_im2col_kernels(kw):
+    from distribuuuu_b200 import selftest
+    selftest.check_stem_s2d(**kw)
+
+
 @pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
 def test_native_engine_tracks_fp32_reference(arch):
     from distribuuuu_b200 import selftest

@@ -171,7 +171,12 @@ def test_uint8_batches_match_host_normalisation(cpu_engine):
     with torch.no_grad():
         la, _, _ = eng.eval_step(x, y, 5)
         lb, _, _ = eng.eval_step(normalize_uint8(x), y, 5)
-    assert abs(float(la) - float(lb)) < 1e-2 and fake.calls["stem_im2col"] == 2
+    assert abs(float(la) - float(lb)) < 1e-2 and fake.calls["stem_s2d"] == 2     # 7x7/2 stem: space-to-depth path
+    # the explicit-im2col stem (what 3x3/2 stems use, and the fallback of the 7x7 one) gives the same answer
+    eng.stem_s2d = False
+    with torch.no_grad():
+        lc, _, _ = eng.eval_step(x, y, 5)
+    assert abs(float(la) - float(lc)) < 1e-2 and fake.calls["stem_im2col"] == 1
 
 
 def test_eval_matches_torch_in_eval_mode(cpu_engine):

@@ -33,6 +33,9 @@ def registry():
         "ce_topk": st.check_ce_topk,
         "sgd": st.check_sgd,
         "stem": st.check_stem,
+        "stem_s2d": st.check_stem_s2d,
+        "stem_s2d_224": lambda: st.check_stem_s2d(N=16, H=224, W=224),
+        "stem_s2d_odd_batch_96": lambda: st.check_stem_s2d(N=3, H=96, W=160, Kc=96),
         "uint8_input": st.check_uint8_input,
         "channel_scale": st.check_channel_scale,
         "grouped_regnety": lambda: st.check_grouped_conv(C=224, K=224, G=2),
