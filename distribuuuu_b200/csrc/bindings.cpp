@@ -18,6 +18,7 @@
 #include "extras.h"
 #include "attention.h"
 #include "conv3x3_halo.h"
+#include "stem_conv.h"
 
 namespace {
 
@@ -895,6 +896,25 @@ void conv3x3_halo(const at::Tensor& x, const at::Tensor& w, at::Tensor& y, const
   B200_CUDA_OK(b200_conv3x3_halo_launch(&mx, &mw, &my, &p, grid, cur_stream()));
 }
 
+// Space-to-depth stem forward with a cp.async-gathered A tile (stem_conv.cu): xs [N,P+3,Q+3,16], w2 [64,4,1,64] -> y [N,P,Q,64]
+void stem_conv_fprop(const at::Tensor& xs, const at::Tensor& w2, at::Tensor& y, const c10::optional<at::Tensor>& stats, PeerState* peer) {
+  check_bf16_contig(xs, "xs"); check_bf16_contig(w2, "w2"); check_bf16_contig(y, "y");
+  c10::cuda::CUDAGuard guard(xs.device());
+  TORCH_CHECK(xs.dim() == 4 && xs.size(3) == 16 && y.dim() == 4 && y.size(3) == 64 && w2.numel() == 64 * 256, "stem_conv_fprop: xs [N,Hs,Ws,16], w2 [64,4,1,64], y [N,P,Q,64]");
+  StemConvParams p{};
+  p.N = xs.size(0); p.Hs = xs.size(1); p.Ws = xs.size(2); p.P = y.size(1); p.Q = y.size(2);
+  TORCH_CHECK(y.size(0) == p.N && p.Hs == p.P + 3 && p.Ws == p.Q + 3 && p.Q <= 128, "stem_conv_fprop geometry (Q <= 128)");
+  p.tiles = p.N * p.P;
+  p.s = xs.data_ptr(); p.y = y.data_ptr();
+  p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;
+  if (stats.has_value()) TORCH_CHECK(stats->numel() >= 128 && stats->scalar_type() == at::kFloat, "stats must be fp32 [2*64]");
+  p.peer = PeerCtx{}; p.peer.world = 1;
+  if (peer != nullptr) { TORCH_CHECK(stats.has_value(), "stem_conv_fprop: a peer context needs the statistics epilogue"); p.peer = peer_ctx_for_producer(peer); }
+  CUtensorMap mw = tiled_map_3d(w2.data_ptr(), 64, 4, 64, 64, 4 * 64, 64, 1, 64);
+  const int grid = std::min(p.tiles, num_sms());
+  B200_CUDA_OK(b200_stem_conv_launch(&mw, &p, grid, cur_stream()));
+}
+
 // ---------------------------------------------------------------------------------------------- attention (BoTNet MHSA)
 // qk [B,14,14,2*heads*128], v / out [B,14,14,heads*128] (NHWC bf16, contiguous); rel_w / rel_h [27,128] bf16
 struct AttnMaps { CUtensorMap qk128, qk64, v128, v64, relw, relh; };
@@ -1040,6 +1060,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("colsum_add", &colsum_add);
   m.def("stem_s2d", &stem_s2d, py::arg("x"), py::arg("out"), py::arg("mean") = std::vector<double>{}, py::arg("std") = std::vector<double>{});
   m.def("stem_s2d_pack_w", &stem_s2d_pack_w);
+  m.def("stem_conv_fprop", &stem_conv_fprop, py::arg("xs"), py::arg("w2"), py::arg("y"), py::arg("stats"), py::arg("peer") = py::none());
   m.def("stem_s2d_unpack_dw", &stem_s2d_unpack_dw);
   m.def("strided_add_inplace", &strided_add_inplace);
   m.def("blockdiag_pack", &blockdiag_pack);

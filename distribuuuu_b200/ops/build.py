@@ -17,7 +17,7 @@ _PKG = os.path.dirname(_HERE)
 CSRC = os.path.join(_PKG, "csrc")
 BUILD_DIR = os.path.join(_PKG, "_ext")
 NAME = "b200_kernels"
-SOURCES = ["bindings.cpp", "conv_gemm.cu", "elementwise.cu", "comm.cu", "dwconv.cu", "extras.cu", "attention.cu", "conv3x3_halo.cu"]
+SOURCES = ["bindings.cpp", "conv_gemm.cu", "elementwise.cu", "comm.cu", "dwconv.cu", "extras.cu", "attention.cu", "conv3x3_halo.cu", "stem_conv.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 

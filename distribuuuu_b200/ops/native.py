@@ -340,6 +340,8 @@ class StemConvFn(torch.autograd.Function):
       with a W-stride of 16 elements presents them as ONE 64-channel pixel and the generic im2col tcgen05 kernels run
       fprop and wgrad as a 4x1 convolution over that (overlapping) view -- the im2col TMA map takes the strides as
       they are.  108 MB of S instead of 1.03 GB of explicit patches (written once, read by fprop and again by wgrad).
+      For 64 output channels the forward has its own kernel (csrc/stem_conv.cu) that gathers the A tile with cp.async, so
+      the four-fold overlap hits in L1 instead of crossing the L2 -> SM fabric four times.
     * any other small-Cin stem (3x3/2 of RegNet / EfficientNet): explicit im2col to [pixels, Kpad] bf16, then the GEMM."""
 
     @staticmethod
@@ -366,7 +368,10 @@ class StemConvFn(torch.autograd.Function):
                 w2 = eng.scratch("stem_w_s2d", (Kc, 4, 1, 64), torch.bfloat16)
                 K.stem_s2d_pack_w(eng.w16_krsc(conv.weight), w2)
                 y = torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
-                K.conv_fprop(xv, w2, y, stats, None, 1, 0, 1)
+                if eng.stem_gather and Kc == 64 and Q <= 128:
+                    K.stem_conv_fprop(xs, w2, y, stats)      # A tile gathered with cp.async: each S row read once per tile
+                else:
+                    K.conv_fprop(xv, w2, y, stats, None, 1, 0, 1)
                 ctx.s2d, ctx.Q = True, Q
                 ctx.save_for_backward(xs)
                 return _nchw_view(y)

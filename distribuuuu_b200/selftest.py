@@ -623,6 +623,15 @@ def check_stem_s2d(N=2, H=64, W=64, Kc=64):
     e_y = _rel_err(y, ref.permute(0, 2, 3, 1))
     yf = y.float().view(-1, Kc)
     e_st = max(_rel_err(stats[:Kc], yf.sum(0)), _rel_err(stats[Kc:], (yf * yf).sum(0)))
+    e_g = e_gst = 0.0
+    if Kc == 64 and Q <= 128:       # dedicated forward kernel: A tile gathered with cp.async (csrc/stem_conv.cu)
+        y2 = torch.empty_like(y)
+        stats2 = torch.zeros(2 * Kc, device="cuda")
+        Kmod.stem_conv_fprop(xs, w2, y2, stats2)
+        e_g = _rel_err(y2, ref.permute(0, 2, 3, 1))
+        y2f = y2.float().view(-1, Kc)
+        e_gst = max(_rel_err(stats2[:Kc], y2f.sum(0)), _rel_err(stats2[Kc:], (y2f * y2f).sum(0)))
+        assert e_g < 1e-2 and e_gst < 1e-2, f"stem_conv_fprop {e_g} {e_gst}"
     dy = (torch.randn(N, P, Q, Kc, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
     dwp = torch.zeros((Kc, 4, 1, 64), device="cuda")
     Kmod.conv_wgrad(dy, xv, dwp, 1, 0, 1)
@@ -630,7 +639,8 @@ def check_stem_s2d(N=2, H=64, W=64, Kc=64):
     Kmod.stem_s2d_unpack_dw(dwp, dw)
     ref_dw = torch.nn.grad.conv2d_weight(xb, (Kc, 3, 7, 7), dy.float().permute(0, 3, 1, 2), 2, 3).permute(0, 2, 3, 1)
     torch.cuda.synchronize()
-    errs = {"s2d": e_s, "s2d_uint8": e_u, "fprop": e_y, "stats": e_st, "wgrad": _rel_err(dw, ref_dw)}
+    errs = {"s2d": e_s, "s2d_uint8": e_u, "fprop": e_y, "stats": e_st, "fprop_gather": e_g, "stats_gather": e_gst,
+            "wgrad": _rel_err(dw, ref_dw)}
     assert errs["fprop"] < 1e-2 and errs["stats"] < 1e-2 and errs["wgrad"] < 2e-2, errs
     return errs
 

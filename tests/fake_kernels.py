@@ -95,6 +95,13 @@ class FakeKernels:
                 blk = xp[:, :, u::2, v::2].permute(0, 2, 3, 1)                      # [N, Hs, Ws, 3]
                 o[..., (u * 2 + v) * 3:(u * 2 + v) * 3 + 3] = blk.to(BF16)
 
+    def stem_conv_fprop(self, xs, w2, y, stats, peer=None):
+        self._count("stem_conv_fprop")
+        N, Hs, Ws, _ = xs.shape
+        Q = Ws - 3
+        xv = xs.as_strided((N, Hs, Q, 64), (Hs * Ws * 16, Ws * 16, 16, 1))
+        self.conv_fprop(xv, w2, y, stats, None, 1, 0, 1)
+
     def stem_s2d_pack_w(self, w, wp):
         K = w.numel() // 147
         w7 = torch.zeros((K, 8, 8, 3), dtype=torch.float32)
