@@ -5,7 +5,7 @@
 // pulls every 32-byte S pixel four times over the L2 -> SM fabric (4 taps x 16 KB per 128 output pixels, 1.6 GB per step
 // at batch 256: 358 us, the fabric's ~7.5 TB/s).  Here one tile is one output row (n, p): thread q of four producer warps
 // copies, for each of the four filter rows, the 128 contiguous bytes S[n, p + a, q .. q + 3, :] into row q of a
-// 128B-swizzled K-major sub-tile with eight `cp.async.ca` of 16 bytes -- the four-fold overlap between neighbouring q now
+// 128B-swizzled K-major sub-tile (a slot of an 8-slot ring, six slots in flight) with eight `cp.async.ca` of 16 bytes -- the four-fold overlap between neighbouring q now
 // hits in L1, so the SM reads each S row once (14.7 KB per tile instead of 64 KB).  The packed weights (4 x 8 KB) stay
 // resident; MMA issue, TMEM double buffering, the two-group epilogue with predicated coalesced row stores, the BN statistics
 // and the SyncBN flag at the tail are those of conv3x3_halo.cu.
@@ -20,14 +20,14 @@ namespace stemk {
 constexpr int BM = 128, BN = 64, BK = 64, kTaps = 4;
 constexpr int kTapBytes = BN * BK * 2;            // 8 KB: one filter row's [64 x 64] weight tile
 constexpr int kWBytes = kTaps * kTapBytes;        // 32 KB resident weights
-constexpr int kSubBytes = BM * 128;               // 16 KB: A sub-tile of one filter row
-constexpr int kStageBytes = kTaps * kSubBytes;    // 64 KB
-constexpr int kStages = 2;
+constexpr int kSubBytes = BM * 128;               // 16 KB: A sub-tile of one filter row = one slot of the ring
+constexpr int kRing = 8;                          // slots (two tiles' worth); the producers run kAhead slots ahead of the MMA
+constexpr int kAhead = 6;
 constexpr int kEpiWarps = 8, kProdWarps = 4;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kThreads = 64 + kEpiWarps * 32 + kProdThreads;
 constexpr int kStagingBytes = kEpiWarps * 4096;
-constexpr int kSmem = kWBytes + kStages * kStageBytes + kStagingBytes + 1024 + 256;
+constexpr int kSmem = kWBytes + kRing * kSubBytes + kStagingBytes + 1024 + 256;
 }  // namespace stemk
 using namespace stemk;
 
@@ -41,11 +41,11 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem;
   uint8_t* s_a = smem + kWBytes;
-  uint8_t* s_out = s_a + kStages * kStageBytes;
+  uint8_t* s_out = s_a + kRing * kSubBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kStagingBytes);
-  uint64_t* full_bar = bars;                 // [kStages]   kProdThreads arrivals
-  uint64_t* empty_bar = bars + kStages;      // [kStages]   tcgen05.commit
-  uint64_t* tmem_full = bars + 2 * kStages;  // [2]
+  uint64_t* full_bar = bars;                 // [kRing]   kProdThreads arrivals
+  uint64_t* empty_bar = bars + kRing;        // [kRing]   tcgen05.commit
+  uint64_t* tmem_full = bars + 2 * kRing;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint64_t* w_bar = tmem_empty + 2;          // [1]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
@@ -53,11 +53,11 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // rows q >= Q of the A tiles are never written by the producers: zero them once (the MMA reads all 128 rows)
-  for (int i = threadIdx.x; i < kStages * kStageBytes / 16; i += kThreads) reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
+  for (int i = threadIdx.x; i < kRing * kSubBytes / 16; i += kThreads) reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0u, 0u, 0u, 0u);
   fence_proxy_async_smem();
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&map_w);
-    for (int i = 0; i < kStages; ++i) { mbar_init(smem_u32(&full_bar[i]), kProdThreads); mbar_init(smem_u32(&empty_bar[i]), 1); }
+    for (int i = 0; i < kRing; ++i) { mbar_init(smem_u32(&full_bar[i]), kProdThreads); mbar_init(smem_u32(&empty_bar[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiWarps / 2); }
     mbar_init(smem_u32(w_bar), 1);
     fence_barrier_init();
@@ -90,20 +90,19 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       for (int t = 0; t < kTaps; ++t) b_desc[t] = hi | (uint64_t)((smem_u32(s_w + t * kTapBytes) >> 4) & 0x3fff);
       int local = 0;
       for (int item = blockIdx.x; item < p.tiles; item += gridDim.x, ++local) {
-        const int stage = local & 1;
-        const uint32_t phase = (uint32_t)((local >> 1) & 1);
         mbar_wait(smem_u32(&tmem_empty[acc]), acc_phase ^ 1);
-        mbar_wait(smem_u32(&full_bar[stage]), phase);
-        tc_fence_after();
         const uint32_t tmem_d = tmem_base + acc * BN;
 #pragma unroll
         for (int t = 0; t < kTaps; ++t) {
-          const uint64_t a_desc = hi | (uint64_t)((smem_u32(s_a + stage * kStageBytes + t * kSubBytes) >> 4) & 0x3fff);
+          const int j = local * kTaps + t, slot = j & (kRing - 1);          // (tile, filter row) pair j lives in ring slot j % 8
+          mbar_wait(smem_u32(&full_bar[slot]), (uint32_t)((j >> 3) & 1));
+          tc_fence_after();
+          const uint64_t a_desc = hi | (uint64_t)((smem_u32(s_a + slot * kSubBytes) >> 4) & 0x3fff);
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)
             umma_bf16(tmem_d, a_desc + (uint64_t)(2 * k), b_desc[t] + (uint64_t)(2 * k), idesc, (t | k) ? 1u : 0u);
+          umma_commit(smem_u32(&empty_bar[slot]));                           // the slot is free once these four MMAs have read it
         }
-        umma_commit(smem_u32(&empty_bar[stage]));
         umma_commit(smem_u32(&tmem_full[acc]));
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
@@ -181,36 +180,31 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     const int q = threadIdx.x - (64 + kEpiWarps * 32);
     const bool has_row = q < p.Q;
     const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(p.s);
-    auto issue = [&](int item, int stage) {
+    const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * kTaps;           // (tile, filter row) pairs of this CTA, in MMA order
+    const uint32_t dst_row = smem_u32(s_a + q * 128);
+    auto issue = [&](int j) {
+      const int slot = j & (kRing - 1);
+      mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)(((j >> 3) & 1) ^ 1));   // the MMAs of pair j - 8 have read the slot
       if (has_row) {
+        const int item = (int)blockIdx.x + (j >> 2) * (int)gridDim.x, a = j & 3;
         const int n = item / p.P, pr = item - n * p.P;
-        const __nv_bfloat16* src0 = s + (((long long)n * p.Hs + pr) * p.Ws + q) * 16;
-        const uint32_t dst0 = smem_u32(s_a + stage * kStageBytes + q * 128);
+        const __nv_bfloat16* src = s + (((long long)n * p.Hs + pr + a) * p.Ws + q) * 16;
 #pragma unroll
-        for (int a = 0; a < kTaps; ++a) {
-          const __nv_bfloat16* src = src0 + (long long)a * p.Ws * 16;
-#pragma unroll
-          for (int c = 0; c < 8; ++c) cp_async16_ca(dst0 + a * kSubBytes + ((c ^ (q & 7)) << 4), src + c * 8);
-        }
+        for (int c = 0; c < 8; ++c) cp_async16_ca(dst_row + slot * kSubBytes + ((c ^ (q & 7)) << 4), src + c * 8);
       }
-      asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    int local = 0;
-    int item = blockIdx.x;
-    if (item < p.tiles) issue(item, 0);           // stage 0 is free at start
-    for (; item < p.tiles; item += gridDim.x, ++local) {
-      const int stage = local & 1;
-      const int next = item + gridDim.x;
-      if (next < p.tiles) {
-        const int nl = local + 1;                 // tile nl uses stage nl & 1 for the (nl >> 1)-th time
-        mbar_wait(smem_u32(&empty_bar[nl & 1]), (uint32_t)(((nl >> 1) & 1) ^ 1));
-        issue(next, nl & 1);
-        asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's copies have landed
-      } else {
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-      }
+    // kAhead pairs in flight: group g is complete when at most kAhead newer groups are pending
+    for (int j = 0; j < kAhead; ++j) {
+      if (j < total) issue(j);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int j = 0; j < total; ++j) {
+      if (j + kAhead < total) issue(j + kAhead);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");   // pair j has landed
       fence_proxy_async_smem();                   // generic-proxy writes -> visible to the tensor core (async proxy)
-      mbar_arrive(smem_u32(&full_bar[stage]));
+      mbar_arrive(smem_u32(&full_bar[j & (kRing - 1)]));
     }
   }
 

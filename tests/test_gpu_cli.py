@@ -30,3 +30,14 @@ def test_train_resume_eval_native_engine(tmp_path, free_port):
     r3 = _run("test_net.py", free_port + 2, out, ["MODEL.WEIGHTS", os.path.join(out, "best.pth.tar")])
     assert r3.returncode == 0, r3.stderr[-3000:]
     assert "ACCURACY: TOP1" in r3.stderr
+
+
+def test_train_with_captured_step(tmp_path, free_port):
+    """B200.CUDA_GRAPH: three eager steps, then the step is captured and replayed (two statistics parities -> two graphs);
+    the run trains, checkpoints and evaluates exactly as without it."""
+    out = str(tmp_path / "exp_graph")
+    r = _run("train_net.py", free_port, out, ["OPTIM.MAX_EPOCH", "1", "B200.CUDA_GRAPH", "True", "B200.MAX_ITERS", "10",
+                                              "B200.DUMMY_LEN", "256"])
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert "captured the training step in a CUDA graph" in r.stderr, r.stderr[-3000:]
+    assert os.path.exists(os.path.join(out, "checkpoints", "ckpt_ep_001.pth.tar")) and "ACCURACY: TOP1" in r.stderr

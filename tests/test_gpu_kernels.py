@@ -92,7 +92,10 @@ def test_stem_space_to_depth_on_im2col_kernels(kw):
 @pytest.mark.parametrize("arch", ["resnet18", "resnet50"])
 def test_native_engine_tracks_fp32_reference(arch):
     from distribuuuu_b200 import selftest
-    selftest.check_engine_vs_torch(arch, batch=8, size=64)
+    # 16 x 96^2 and a small step: with 8 x 64^2 the last BN layers see 32 samples per channel and lr 0.01 blows the loss
+    # up to ~10 within three steps -- a chaotic regime in which the run-to-run noise of the fp32 atomics alone moved the
+    # deviation between 1 % and 8 % (tools/rep_engine_check.py), whatever stem path was used
+    selftest.check_engine_vs_torch(arch, batch=16, size=96, lr=0.002)
 
 
 @pytest.mark.parametrize("arch,batch,size", [("resnext50_32x4d", 8, 64), ("densenet121", 8, 64), ("efficientnet_b0", 16, 128),
