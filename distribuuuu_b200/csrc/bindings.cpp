@@ -903,7 +903,7 @@ void stem_conv_fprop(const at::Tensor& xs, const at::Tensor& w2, at::Tensor& y, 
   TORCH_CHECK(xs.dim() == 4 && xs.size(3) == 16 && y.dim() == 4 && y.size(3) == 64 && w2.numel() == 64 * 256, "stem_conv_fprop: xs [N,Hs,Ws,16], w2 [64,4,1,64], y [N,P,Q,64]");
   StemConvParams p{};
   p.N = xs.size(0); p.Hs = xs.size(1); p.Ws = xs.size(2); p.P = y.size(1); p.Q = y.size(2);
-  TORCH_CHECK(y.size(0) == p.N && p.Hs == p.P + 3 && p.Ws == p.Q + 3 && p.Q <= 117, "stem_conv_fprop geometry (Q <= 117: four S rows fit the 15 KB staging)");
+  TORCH_CHECK(y.size(0) == p.N && p.Hs == p.P + 3 && p.Ws == p.Q + 3 && p.Q <= 128, "stem_conv_fprop geometry (Q <= 128)");
   p.tiles = p.N * p.P;
   p.s = xs.data_ptr(); p.y = y.data_ptr();
   p.stats = stats.has_value() ? stats->data_ptr<float>() : nullptr;

@@ -1,17 +1,25 @@
 // Forward of the space-to-depth stem (7x7 / stride 2 / pad 3 over 3 channels == 4x4 / stride 1 over the 16-channel S image,
 // extras.cu: stem_s2d_kernel) with the A tile GATHERED by cp.async instead of loaded by im2col TMA.
 //
-// Why: as a 4x1 convolution over the overlapping [N, P+3, Q, 64] view of S (ops/native.py: StemConvFn) the generic kernel
-// pulls every 32-byte S pixel four times over the L2 -> SM fabric (4 taps x 16 KB per 128 output pixels, 1.6 GB per step
-// at batch 256: 358 us, the fabric's ~7.5 TB/s).  Here one tile is one output row (n, p): the four S rows it needs are 4
-// (Q + 3) 32 = 14.7 KB of CONTIGUOUS memory, brought in by one linear bulk copy (two staging stages); four producer
-// warps then expand them in shared memory -- row q of filter row a's 128B-swizzled K-major sub-tile is the 128 bytes at
-// staging[a][q .. q+3] -- with 16-byte LDS / STS (conflict-free both ways), into an 8-slot ring the MMA thread drains.
-// (A first version gathered the sub-tiles straight from global memory with `cp.async.ca`: 325 us, two stages or six
-// slots in flight alike -- the four-fold overlap between neighbouring q was NOT absorbed by L1, the kernel stayed on the
-// L2 -> SM roofline of the TMA version.)  The packed weights (4 x 8 KB) stay resident; MMA issue, TMEM double
-// buffering, the two-group epilogue with predicated coalesced row stores, the BN statistics and the SyncBN flag at the
-// tail are those of conv3x3_halo.cu.
+// Status: an experiment kept behind B200_STEM_GATHER=1 (default off) -- measured 324 us against 358 us for the generic
+// kernel on the 256 x 3 x 224 x 224 stem, and the reason it cannot do much better is worth recording:
+//
+// As a 4x1 convolution over the overlapping [N, P+3, Q, 64] view of S (ops/native.py: StemConvFn) the generic kernel pulls
+// every 32-byte S pixel four times over the L2 -> SM fabric (4 taps x 16 KB per 128 output pixels).  Here one tile is one
+// output row (n, p): thread q of four producer warps copies, for each of the four filter rows, the 128 contiguous bytes
+// S[n, p + a, q .. q + 3, :] into row q of a 128B-swizzled K-major sub-tile (a slot of an 8-slot ring, six slots in flight)
+// with eight `cp.async.ca` of 16 bytes.  Three producers were measured (profiles/r2/ncu_prof_stem_conv_expand.txt):
+// cp.async with two 64 KB stages 325 us, this ring 324 us, and one linear bulk copy of the four S rows per tile expanded
+// smem -> smem 358 us.  The time does not depend on how the A tile gets into shared memory, the tensor pipe is 16 % active
+// and the epilogue warps spend 33 % of their samples waiting for an accumulator, so the pace is set between "A tile in
+// shared memory" and "accumulator complete".  The working hypothesis is shared-memory bandwidth: with N = 64 an SS-mode
+// tcgen05.mma (128 x 64 x 16) reads 4 KB of A + 2 KB of B for 32 tensor-core cycles, and a tile costs 96 KB of operand
+// reads + 64 KB of A-tile writes + 48 KB of epilogue staging -- 1.6k cycles at 128 B/clk against 3.3k measured.  The halo
+// kernel (also N = 64) shows the same picture (35 % tensor activity).  An A operand read straight from the staged rows
+// (32-byte-swizzle descriptors, one MMA per (filter row, column) pair, no expanded copy) or N >= 128 would test it.
+//
+// The packed weights (4 x 8 KB) stay resident; MMA issue, TMEM double buffering, the two-group epilogue with predicated
+// coalesced row stores, the BN statistics and the SyncBN flag at the tail are those of conv3x3_halo.cu.
 //
 // Reference: models/resnet.py:194 (nn.Conv2d(3, 64, 7, 2, 3) -> cuDNN); SURVEY G1.
 #include "common.cuh"
@@ -24,16 +32,19 @@ constexpr int BM = 128, BN = 64, BK = 64, kTaps = 4;
 constexpr int kTapBytes = BN * BK * 2;            // 8 KB: one filter row's [64 x 64] weight tile
 constexpr int kWBytes = kTaps * kTapBytes;        // 32 KB resident weights
 constexpr int kSubBytes = BM * 128;               // 16 KB: A sub-tile of one filter row = one slot of the ring
-constexpr int kRing = 8;                          // slots (two tiles' worth)
-constexpr int kSStageBytes = 15 * 1024;           // staging of the four S rows of a tile: 4 (Q + 3) 32 B <= 15 KB  <=>  Q <= 117
-constexpr int kSStages = 2;
+constexpr int kRing = 8;                          // slots (two tiles' worth); the producers run kAhead slots ahead of the MMA
+constexpr int kAhead = 6;
 constexpr int kEpiWarps = 8, kProdWarps = 4;
 constexpr int kProdThreads = kProdWarps * 32;
 constexpr int kThreads = 64 + kEpiWarps * 32 + kProdThreads;
 constexpr int kStagingBytes = kEpiWarps * 4096;
-constexpr int kSmem = kWBytes + kRing * kSubBytes + kSStages * kSStageBytes + kStagingBytes + 1024 + 256;
+constexpr int kSmem = kWBytes + kRing * kSubBytes + kStagingBytes + 1024 + 256;
 }  // namespace stemk
 using namespace stemk;
+
+__device__ __forceinline__ void cp_async16_ca(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 
 __global__ void __launch_bounds__(kThreads, 1)
 stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ StemConvParams p) {
@@ -41,17 +52,14 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_w = smem;
   uint8_t* s_a = smem + kWBytes;
-  uint8_t* s_s = s_a + kRing * kSubBytes;      // [kSStages] raw S rows
-  uint8_t* s_out = s_s + kSStages * kSStageBytes;
+  uint8_t* s_out = s_a + kRing * kSubBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + kStagingBytes);
   uint64_t* full_bar = bars;                 // [kRing]   kProdThreads arrivals
   uint64_t* empty_bar = bars + kRing;        // [kRing]   tcgen05.commit
   uint64_t* tmem_full = bars + 2 * kRing;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;      // [2]
   uint64_t* w_bar = tmem_empty + 2;          // [1]
-  uint64_t* s_full = w_bar + 1;              // [kSStages]  bulk copy landed
-  uint64_t* s_empty = s_full + kSStages;     // [kSStages]  kProdThreads arrivals: the tile has been expanded
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(s_empty + kSStages);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -63,7 +71,6 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
     for (int i = 0; i < kRing; ++i) { mbar_init(smem_u32(&full_bar[i]), kProdThreads); mbar_init(smem_u32(&empty_bar[i]), 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&tmem_full[i]), 1); mbar_init(smem_u32(&tmem_empty[i]), kEpiWarps / 2); }
     mbar_init(smem_u32(w_bar), 1);
-    for (int i = 0; i < kSStages; ++i) { mbar_init(smem_u32(&s_full[i]), 1); mbar_init(smem_u32(&s_empty[i]), kProdThreads); }
     fence_barrier_init();
   }
   if (warp == 1) { tmem_alloc(smem_u32(tmem_ptr), 2 * BN); tmem_relinquish(); }
@@ -79,17 +86,6 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       const uint32_t wb = smem_u32(w_bar);
       mbar_expect_tx(wb, (uint32_t)kWBytes);
       for (int t = 0; t < kTaps; ++t) tma_load_3d(smem_u32(s_w + t * kTapBytes), &map_w, wb, 0, t, 0);
-      // then the S rows of every tile: rows p .. p+3 of image n are one contiguous block
-      const uint32_t bytes = 4u * (uint32_t)p.Ws * 32u;
-      int local = 0;
-      for (int item = blockIdx.x; item < p.tiles; item += gridDim.x, ++local) {
-        const int st = local & (kSStages - 1);
-        mbar_wait(smem_u32(&s_empty[st]), (uint32_t)(((local / kSStages) & 1) ^ 1));
-        const int n = item / p.P, pr = item - n * p.P;
-        const uint32_t bar = smem_u32(&s_full[st]);
-        mbar_expect_tx(bar, bytes);
-        bulk_load_1d(smem_u32(s_s + st * kSStageBytes), reinterpret_cast<const __nv_bfloat16*>(p.s) + ((long long)n * p.Hs + pr) * p.Ws * 16, bytes, bar);
-      }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -191,35 +187,35 @@ stem_conv_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constan
       if (p.peer.world > 1) __threadfence();
     }
   } else {
-    // =============================== producers: expand the staged S rows into the ring's swizzled sub-tiles (smem -> smem)
-    // thread t handles 16-byte chunk (t & 7) of rows (t >> 3) + 16 i: a warp reads 4 rows x 128 B that overlap by 96 B (<= 2
-    // wavefronts) and writes 4 full swizzled rows (4 wavefronts, the minimum for 512 B)
-    const int t = threadIdx.x - (64 + kEpiWarps * 32);
-    const int chunk = t & 7, row0 = t >> 3;
-    const uint32_t row_bytes = (uint32_t)p.Ws * 32u;
-    int local = 0;
-    for (int item = blockIdx.x; item < p.tiles; item += gridDim.x, ++local) {
-      const int st = local & (kSStages - 1);
-      mbar_wait(smem_u32(&s_full[st]), (uint32_t)((local / kSStages) & 1));
-      const uint8_t* src0 = s_s + st * kSStageBytes + chunk * 16;
+    // =============================== producers: thread q gathers row q of the four sub-tiles (8 x 16 B per filter row)
+    const int q = threadIdx.x - (64 + kEpiWarps * 32);
+    const bool has_row = q < p.Q;
+    const __nv_bfloat16* s = reinterpret_cast<const __nv_bfloat16*>(p.s);
+    const int my_tiles = (p.tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int total = my_tiles * kTaps;           // (tile, filter row) pairs of this CTA, in MMA order
+    const uint32_t dst_row = smem_u32(s_a + q * 128);
+    auto issue = [&](int j) {
+      const int slot = j & (kRing - 1);
+      mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)(((j >> 3) & 1) ^ 1));   // the MMAs of pair j - 8 have read the slot
+      if (has_row) {
+        const int item = (int)blockIdx.x + (j >> 2) * (int)gridDim.x, a = j & 3;
+        const int n = item / p.P, pr = item - n * p.P;
+        const __nv_bfloat16* src = s + (((long long)n * p.Hs + pr + a) * p.Ws + q) * 16;
 #pragma unroll
-      for (int a = 0; a < kTaps; ++a) {
-        const int j = local * kTaps + a, slot = j & (kRing - 1);
-        mbar_wait(smem_u32(&empty_bar[slot]), (uint32_t)(((j >> 3) & 1) ^ 1));   // the MMAs of pair j - 8 have read the slot
-        uint8_t* dst0 = s_a + slot * kSubBytes;
-        const uint8_t* srca = src0 + a * row_bytes;
-#pragma unroll
-        for (int i = 0; i < BM / 16; ++i) {
-          const int row = row0 + 16 * i;
-          if (row < p.Q) {
-            const uint4 v = *reinterpret_cast<const uint4*>(srca + row * 32);
-            *reinterpret_cast<uint4*>(dst0 + row * 128 + ((chunk ^ (row & 7)) << 4)) = v;
-          }
-        }
-        fence_proxy_async_smem();                 // generic-proxy writes -> visible to the tensor core (async proxy)
-        mbar_arrive(smem_u32(&full_bar[slot]));
+        for (int c = 0; c < 8; ++c) cp_async16_ca(dst_row + slot * kSubBytes + ((c ^ (q & 7)) << 4), src + c * 8);
       }
-      mbar_arrive(smem_u32(&s_empty[st]));        // the loader may refill this staging stage
+    };
+    // kAhead pairs in flight: group g is complete when at most kAhead newer groups are pending
+    for (int j = 0; j < kAhead; ++j) {
+      if (j < total) issue(j);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    for (int j = 0; j < total; ++j) {
+      if (j + kAhead < total) issue(j + kAhead);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group %0;" ::"n"(kAhead) : "memory");   // pair j has landed
+      fence_proxy_async_smem();                   // generic-proxy writes -> visible to the tensor core (async proxy)
+      mbar_arrive(smem_u32(&full_bar[j & (kRing - 1)]));
     }
   }
 

@@ -368,7 +368,7 @@ class StemConvFn(torch.autograd.Function):
                 w2 = eng.scratch("stem_w_s2d", (Kc, 4, 1, 64), torch.bfloat16)
                 K.stem_s2d_pack_w(eng.w16_krsc(conv.weight), w2)
                 y = torch.empty((N, P, Q, Kc), dtype=torch.bfloat16, device=x.device)
-                if eng.stem_gather and Kc == 64 and Q <= 117:
+                if eng.stem_gather and Kc == 64 and Q <= 128:
                     K.stem_conv_fprop(xs, w2, y, stats)      # A tile gathered with cp.async: each S row read once per tile
                 else:
                     K.conv_fprop(xv, w2, y, stats, None, 1, 0, 1)

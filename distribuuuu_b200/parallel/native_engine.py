@@ -119,7 +119,7 @@ class NativeEngine(nn.Module):
         self.cuda_graph = bool(cuda_graph)
         # 7x7/2 stems as a space-to-depth 4x1 convolution on the im2col tcgen05 kernels (ops/native.py: StemConvFn)
         self.stem_s2d = os.environ.get("B200_STEM_S2D", "1") != "0"
-        self.stem_gather = os.environ.get("B200_STEM_GATHER", "1") != "0"    # csrc/stem_conv.cu for 64-channel stems
+        self.stem_gather = os.environ.get("B200_STEM_GATHER", "0") == "1"    # csrc/stem_conv.cu (experiment, see its header)
         self._graphs = {}
         self._graph_pool = None
         self._eager_steps = 0

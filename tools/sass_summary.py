@@ -18,7 +18,8 @@ INTERESTING = re.compile(r"^(UTCHMMA|UTCQMMA|UTCBAR|UTCATOMSWS|LDTM|STTM|UTMALDG
 FULL = [r"conv_gemm_kernel<256, 0, 2>", r"conv_gemm_kernel<256, 0, 1>", r"conv_gemm_kernel<256, 1, 2>", r"conv_gemm_kernel<64, 0, 1>",
         r"conv_gemm_kernel<256, 3, 2>", r"allreduce_sgd_kernel", r"bn_apply_kernel<1, true>", r"bn_bwd_apply_kernel<1, 1>",
         r"bn_bwd_reduce_kernel<1, 1>", r"attn_fwd_kernel", r"attn_bwd_dq_kernel", r"attn_bwd_dkv_kernel", r"dw_fprop", r"ce_topk_kernel",
-        r"se_gate_fwd_kernel", r"stem_im2col_kernel<unsigned char>"]
+        r"se_gate_fwd_kernel", r"stem_im2col_kernel<unsigned char>", r"conv3x3_halo_kernel", r"stem_conv_kernel",
+        r"bn_relu_pool_fwd_strip_kernel", r"bn_relu_pool_bwd_strip_kernel<true>", r"dw_fprop_fast_kernel<3, 1>"]
 
 
 def main():
