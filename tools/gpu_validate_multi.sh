@@ -1,6 +1,7 @@
 #!/usr/bin/env bash
 # Multi-GPU validation (run through `gpurun --gpus N`):  tools/gpu_validate_multi.sh N [--archs]
-#   gate -> tools/multigpu_check.py at N ranks -> bench.py with the captured step on and off [-> the other families].
+#   gate -> tools/multigpu_check.py at N ranks -> bench.py with the captured step on and off (BENCH_MODES="on" for one)
+#   [-> the other families].
 set -u
 cd "$(dirname "$0")/.."
 n=${1:-2}
@@ -19,7 +20,7 @@ except Exception as e:
     print(sys.argv[1], "unreadable:", e)
 PY
 }
-for g in on off; do
+for g in ${BENCH_MODES:-on off}; do
   f=gpurun_out/bench_ours_${n}gpu_graph_$g
   timeout 240 $TR --master-port 29602 bench.py --gpus $n --steps 20 --warmup 5 --graph $g > $f.json 2> $f.err
   show $f.json; tail -1 $f.err | cut -c1-200
