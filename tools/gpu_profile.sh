@@ -33,6 +33,8 @@ while IFS='|' read -r name regex skip arch; do
   fi
 done <<'LIST'
 prof_halo_fprop|conv3x3_halo_kernel|8|resnet50
+prof_stem_tail_fwd|bn_relu_pool_fwd_strip_kernel|2|resnet50
+prof_stem_tail_bwd|bn_relu_pool_bwd_strip_kernel|3|resnet50
 prof_ce_topk|ce_topk_kernel|2|resnet50
 prof_sgd_local|sgd_local_kernel|2|resnet50
 prof_dw_fprop|dw_fprop_fast_kernel|20|efficientnet_b0
