@@ -58,8 +58,9 @@ def launch_table(path):
             rows.append((row["Kernel Name"], float(row["Metric Value"].replace(",", ""))))
         except Exception:
             pass
-    # one step = a stem_im2col launch up to the optimizer kernel that follows it; take the LAST COMPLETE one
-    starts = [i for i, (n, v) in enumerate(rows) if "stem_im2col" in n]
+    # one step = the stem's first kernel (space-to-depth / im2col) up to the optimizer kernel that follows it; take the LAST
+    # COMPLETE one
+    starts = [i for i, (n, v) in enumerate(rows) if "stem_im2col" in n or "stem_s2d_kernel" in n]
     ends = [i for i, (n, v) in enumerate(rows) if "sgd_local" in n or "allreduce_sgd" in n]
     step = rows
     for k in range(len(starts) - 1, -1, -1):
