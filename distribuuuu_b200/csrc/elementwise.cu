@@ -1676,7 +1676,9 @@ extern "C" int b200_bn_relu_pool_bwd_reduce(const BnPoolParams* p, cudaStream_t 
   dim3 g, b;
   size_t smem;
   static cudaError_t once = pool_strip_attr(bn_relu_pool_bwd_strip_kernel<false>);
-  if (once == cudaSuccess && pool_strip_cfg(p->C, p->W / 2, (size_t)7 * p->W * p->C, g, b, smem, p->N * (p->H / 2))) {
+  // the arg rows are copied with cp.async.bulk: Q * C bytes per row must be a multiple of 16
+  if (once == cudaSuccess && ((p->W / 2) * p->C) % 16 == 0 &&
+      pool_strip_cfg(p->C, p->W / 2, (size_t)7 * p->W * p->C, g, b, smem, p->N * (p->H / 2))) {
     bn_relu_pool_bwd_strip_kernel<false><<<g, b, smem, s>>>(*p);
     return (int)cudaGetLastError();
   }
@@ -1688,7 +1690,9 @@ extern "C" int b200_bn_relu_pool_bwd_apply(const BnPoolParams* p, cudaStream_t s
   dim3 g, b;
   size_t smem;
   static cudaError_t once = pool_strip_attr(bn_relu_pool_bwd_strip_kernel<true>);
-  if (once == cudaSuccess && pool_strip_cfg(p->C, p->W / 2, (size_t)7 * p->W * p->C, g, b, smem, p->N * (p->H / 2))) {
+  // the arg rows are copied with cp.async.bulk: Q * C bytes per row must be a multiple of 16
+  if (once == cudaSuccess && ((p->W / 2) * p->C) % 16 == 0 &&
+      pool_strip_cfg(p->C, p->W / 2, (size_t)7 * p->W * p->C, g, b, smem, p->N * (p->H / 2))) {
     bn_relu_pool_bwd_strip_kernel<true><<<g, b, smem, s>>>(*p);
     return (int)cudaGetLastError();
   }

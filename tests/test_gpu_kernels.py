@@ -56,8 +56,9 @@ def test_pool_kernels():
     selftest.check_pools()
 
 
-@pytest.mark.parametrize("kw", [dict(), dict(N=3, H=10, W=14, C=96), dict(N=64, H=112, W=112, C=64), dict(N=2, H=4, W=600, C=64)],
-                         ids=["small", "c96_odd", "stem_shape", "wide_rows_register_fallback"])
+@pytest.mark.parametrize("kw", [dict(), dict(N=3, H=10, W=14, C=96), dict(N=64, H=112, W=112, C=64), dict(N=2, H=4, W=600, C=64),
+                                dict(N=2, H=6, W=10, C=24)],
+                         ids=["small", "c96_odd", "stem_shape", "wide_rows_register_fallback", "c24_unaligned_arg_rows"])
 def test_fused_stem_tail_bn_relu_maxpool(kw):
     from distribuuuu_b200 import selftest
     selftest.check_bn_relu_pool(**kw)
