@@ -221,3 +221,38 @@ def test_checkpoints_interchange_with_plain_torch(cpu_engine, fresh_cfg, tmp_pat
     la, _, _ = eng.train_step(x, y, opt, 5)
     lb, _, _ = eng2.train_step(x, y, opt2, 5)
     assert float(la.detach()) == float(lb.detach()) and torch.equal(eng.flat_master, eng2.flat_master)
+
+
+def test_stem_paths_and_their_fallbacks(cpu_engine):
+    """The 7x7/2 stem: space-to-depth + fused BN/ReLU/max-pool tail when the geometry allows; a conv output with an odd
+    side takes the three separate ops; a kernel module / driver that rejects the space-to-depth map (RuntimeError) makes the
+    engine fall back to the explicit-im2col stem for good, with the same loss."""
+    eng, ref, fake = cpu_engine("resnet18", num_classes=16)
+    opt = eng.make_optimizer(lr=0.01, momentum=0.9, dampening=0.0, weight_decay=0.0, nesterov=True)
+    eng.train(), ref.train()
+    g = torch.Generator().manual_seed(3)
+    y = torch.randint(0, 16, (4,), generator=g)
+    # 62x62 input -> 31x31 conv output: the pooling windows do not tile 2x2 blocks, separate BN / pool kernels
+    x_odd = torch.randn(4, 3, 62, 62, generator=g)
+    lr_, _, _ = Fn.cross_entropy_topk(ref(x_odd), y, 5)          # same (initial) weights as the engine
+    lb, _, _ = eng.train_step(x_odd, y, opt, 5)
+    assert fake.calls.get("stem_s2d", 0) == 1 and fake.calls.get("maxpool_fwd", 0) == 1 and fake.calls.get("maxpool_bwd", 0) == 1
+    assert fake.calls.get("bn_relu_pool_fwd", 0) == 0
+    assert abs(float(lb.detach()) - float(lr_.detach())) / float(lr_.detach()) < 0.05
+    # 64x64 input -> 32x32 conv output: fused tail
+    x = torch.randn(4, 3, 64, 64, generator=g)
+    la, _, _ = eng.train_step(x, y, opt, 5)
+    assert fake.calls.get("stem_s2d", 0) == 2 and fake.calls.get("bn_relu_pool_fwd", 0) == 1 and fake.calls.get("maxpool_fwd", 0) == 1
+    assert fake.calls.get("bn_relu_pool_bwd", 0) == 1 and float(la.detach()) == float(la.detach())
+    # the space-to-depth kernel refuses: explicit im2col from then on
+    real = fake.stem_s2d
+
+    def refuse(*a, **k):
+        raise RuntimeError("cuTensorMapEncodeIm2col failed (emulated)")
+    fake.stem_s2d = refuse
+    before = fake.calls.get("stem_im2col", 0)
+    lc, _, _ = eng.train_step(x, y, opt, 5)
+    fake.stem_s2d = real
+    assert eng.stem_s2d is False and fake.calls.get("stem_im2col", 0) == before + 1
+    ld, _, _ = eng.train_step(x, y, opt, 5)
+    assert fake.calls.get("stem_im2col", 0) == before + 2 and float(ld.detach()) == float(ld.detach())
