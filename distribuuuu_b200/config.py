@@ -263,9 +263,10 @@ _C.B200.MAX_ITERS = 0
 # failure detection (utils/health.py): process-group timeout, step watchdog, per-rank heartbeat files
 # capture the native engine's whole training step (forward + backward + fused update, ~330 launches for ResNet-50)
 # in a CUDA graph after a few eager steps and replay it; removes the per-step Python / launch overhead that bounds
-# the small-batch configs (batch 32-64 per GPU).  Works on one or several GPUs (the exchange counters of the peer-memory
-# kernels live in device memory).
-_C.B200.CUDA_GRAPH = False
+# the small-batch configs (batch 32-64 per GPU: BoTNet-50 10.3 -> 6.2 ms/step).  Works on one or several GPUs (the exchange
+# counters of the peer-memory kernels live in device memory); a new learning rate (once per epoch) or batch shape is
+# captured again, evaluation and the torch engine are unaffected.  False = launch every kernel from Python.
+_C.B200.CUDA_GRAPH = True
 _C.B200.DIST_TIMEOUT_MIN = 30
 _C.B200.WATCHDOG_S = 0          # 0 = off; else seconds without a finished iteration before stacks are dumped
 _C.B200.WATCHDOG_ABORT = False  # exit(3) when the watchdog fires so the launcher restarts the job (AUTO_RESUME)
